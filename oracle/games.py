@@ -1,0 +1,350 @@
+"""Oracle restatement of the configured example games.  TEST INFRASTRUCTURE ONLY.
+
+Each game is (a) a builder that turns ASCII art into an `engine_model.World`
+the way `ascii_art.ascii_art_to_game` + the example's `make_game` do, and (b) a
+"program": `program(world, char, actions)` = the `update()` of the entity that
+paints `char`.  Reference (under /root/reference/pycolab/):
+
+  examples/scrolly_maze.py:212-364            -> make_scrolly_maze / scrolly_maze_program
+  examples/warehouse_manager.py:139-295       -> make_warehouse / warehouse_program
+  examples/extraterrestrial_marauders.py:91-256 -> make_marauders / marauders_program
+  tests/test_things.py:153-295 (fixtures)     -> make_fixture_world / fixture_program
+  ascii_art.py:31-292                         -> split_art
+"""
+
+import numpy as np
+
+from oracle import engine_model as em
+
+
+def art_to_array(art):
+  """ascii_art.py:295-328."""
+  return np.vstack([np.frombuffer(line.encode('ascii'), dtype=np.uint8)
+                    for line in art]).copy()
+
+
+def split_art(art, entity_chars, what_lies_beneath):
+  """ascii_art.py:241-289: masks/positions per entity char + the backdrop that
+  remains once every entity char is replaced by what lies beneath it."""
+  art = art_to_array(art)
+  if isinstance(what_lies_beneath, str):
+    beneath = np.full_like(art, ord(what_lies_beneath))
+  else:
+    beneath = art_to_array(what_lies_beneath)
+  masks = {}
+  for ch in entity_chars:
+    mask = art == ord(ch)
+    masks[ch] = mask
+    art[mask] = beneath[mask]
+  return art, masks
+
+
+def mask_position(mask):
+  """ascii_art.py:262-268: a sprite absent from the art sits at (0, 0)."""
+  rr, cc = np.where(mask)
+  assert len(rr) <= 1
+  return (int(rr[0]), int(cc[0])) if len(rr) else (0, 0)
+
+
+# ==========================================================================
+# scrolly_maze
+# ==========================================================================
+
+def make_scrolly_maze(maze_art, board_art, corner_mark='+', beneath='#'):
+  """examples/scrolly_maze.py:212-242 with Scrolly.PatternInfo
+  (drapes.py:166-291) inlined."""
+  world_art = art_to_array(maze_art)
+  marks = np.argwhere(world_art == ord(corner_mark))
+  assert len(marks) == 1
+  corner = (int(marks[0][0]), int(marks[0][1]))
+  world_art[corner] = ord(beneath)
+  board_shape = (len(board_art), len(board_art[0]))
+
+  def vpos(ch):
+    where = np.argwhere(world_art == ord(ch))
+    assert len(where) == 1, ch
+    return (int(where[0][0]) - corner[0], int(where[0][1]) - corner[1])
+
+  backdrop, _ = split_art(board_art, 'Pabc#@', ' ')
+  things = {}
+  for ch in '#@':
+    things[ch] = em.Scrolly(ch, board_shape, world_art == ord(ch), corner)
+  for ch in 'abc':
+    w = em.Walker(ch, board_shape, (0, 0), impassable='#')
+    em.walker_teleport(w, *vpos(ch))
+    w.aux['moving_east'] = bool(ord(ch) % 2)     # scrolly_maze.py:282
+    things[ch] = w
+  p = em.Walker('P', board_shape, (0, 0), impassable='#', egocentric=True)
+  em.walker_teleport(p, *vpos('P'))
+  things['P'] = p
+  return em.World(board_shape[0], board_shape[1], backdrop, things,
+                  z_order='abc@#P',
+                  groups=[['#'], ['a', 'b', 'c', 'P'], ['@']],
+                  program=scrolly_maze_program)
+
+
+# Action -> motion for P, '#', '@' (scrolly_maze.py:262-271, 320-329, 352-363).
+_SCROLLY_ACTION_MOTION = {0: em.M_N, 1: em.M_S, 2: em.M_W, 3: em.M_E,
+                          4: em.M_STAY}
+
+
+def scrolly_maze_program(world, ch, actions):
+  plot = world.plot
+  ent = world.things[ch]
+  motion = _SCROLLY_ACTION_MOTION.get(actions, em.NO_MOTION) \
+      if actions is not None else em.NO_MOTION
+  if ch == '#':                                   # MazeDrape :308-329
+    if motion != em.NO_MOTION:
+      em.scrolly_move(ent, world, motion)
+  elif ch == 'P':                                 # PlayerSprite :245-271
+    if motion != em.NO_MOTION:
+      em.walker_move(ent, world.board, plot, motion)
+  elif ch in 'abc':                               # PatrollerSprite :274-305
+    if plot.frame % 2:
+      em.walker_move(ent, world.board, plot, em.M_STAY)
+      return
+    walls = world.things['#']
+    prow, pcol = em.scrolly_prescroll(walls, ent.virtual_position, plot)
+    step = 1 if ent.aux['moving_east'] else -1
+    if walls.pattern[prow, pcol + step]:
+      ent.aux['moving_east'] = not ent.aux['moving_east']
+    em.walker_move(ent, world.board, plot,
+                   em.M_E if ent.aux['moving_east'] else em.M_W)
+    if ent.virtual_position == world.things['P'].virtual_position:
+      plot.terminate_episode()
+  elif ch == '@':                                 # CashDrape :332-364
+    where = em.scrolly_prescroll(ent, world.things['P'].position, plot)
+    if ent.pattern[where]:
+      plot.add_reward(100)
+      ent.pattern[where] = False
+      if not ent.pattern.any():
+        plot.terminate_episode()
+    if motion != em.NO_MOTION:
+      em.scrolly_move(ent, world, motion)
+    elif actions == 5:
+      plot.terminate_episode()
+  else:
+    raise KeyError(ch)
+
+
+# ==========================================================================
+# warehouse_manager
+# ==========================================================================
+
+_BOXES = '1234567890'          # update order, warehouse_manager.py:168
+
+
+def make_warehouse(art, what_lies_beneath=' '):
+  """examples/warehouse_manager.py:139-178."""
+  flat = ''.join(art)
+  boxes = [c for c in _BOXES if c in flat]
+  entity_chars = boxes + ['X', 'P']
+  backdrop, masks = split_art(art, entity_chars, what_lies_beneath)
+  shape = backdrop.shape
+  things = {}
+  for ch in boxes:                               # BoxSprite :203-206
+    things[ch] = em.Walker(ch, shape, mask_position(masks[ch]),
+                           impassable=set('#.0123456789PX') - set(ch))
+  judge = em.PlainDrape('X', masks['X'])         # JudgeDrape :241-243
+  judge.aux['last_on_goals'] = 0
+  things['X'] = judge
+  things['P'] = em.Walker('P', shape, mask_position(masks['P']),
+                          impassable='#.0123456789X')
+  world = em.World(shape[0], shape[1], backdrop, things,
+                   z_order=entity_chars,
+                   groups=[boxes, ['X'], ['P']],
+                   program=warehouse_program)
+  world.aux_boxes = boxes
+  return world
+
+
+def warehouse_program(world, ch, actions):
+  plot = world.plot
+  ent = world.things[ch]
+  board = world.board
+  if ch == 'X':                                   # JudgeDrape.update :245-266
+    ent.curtain.fill(False)
+    for b in (c for c in '0123456789' if c in world.things):
+      ent.curtain[world.things[b].position] = True
+    num_boxes = int(ent.curtain.sum())
+    ent.curtain &= (world.backdrop == ord('_'))
+    on_goals = int(ent.curtain.sum())
+    plot.add_reward(on_goals - ent.aux['last_on_goals'])
+    ent.aux['last_on_goals'] = on_goals
+    if actions == 5 or on_goals == num_boxes:
+      plot.terminate_episode()
+  elif ch == 'P':                                 # PlayerSprite.update :284-295
+    motion = {0: em.M_N, 1: em.M_S, 2: em.M_W, 3: em.M_E}.get(actions) \
+        if actions is not None else None
+    if motion is not None:
+      em.walker_move(ent, board, plot, motion)
+  else:                                           # BoxSprite.update :208-226
+    r, c = ent.position
+    is_p = lambda rr, cc: board[rr, cc] == ord('P')   # layers['P'][rr, cc]
+    # NumPy index semantics: -1 wraps, >= size raises (the stock and generated
+    # levels keep boxes away from the rim, so only the wrap can occur).
+    if actions == 0:
+      if is_p(r + 1, c): em.walker_move(ent, board, plot, em.M_N)
+    elif actions == 1:
+      if is_p(r - 1, c): em.walker_move(ent, board, plot, em.M_S)
+    elif actions == 2:
+      if is_p(r, c + 1): em.walker_move(ent, board, plot, em.M_W)
+    elif actions == 3:
+      if is_p(r, c - 1): em.walker_move(ent, board, plot, em.M_E)
+
+
+# ==========================================================================
+# extraterrestrial_marauders
+# ==========================================================================
+
+_UP_BOLTS = 'abcd'             # extraterrestrial_marauders.py:62
+_DOWN_BOLTS = 'yz'             # :66
+_ALL_BOLTS = _UP_BOLTS + _DOWN_BOLTS
+
+
+def make_marauders(art, rng):
+  """examples/extraterrestrial_marauders.py:91-101.  `rng` is the
+  numpy.random.RandomState standing in for the global NumPy RNG (:253)."""
+  order = ['P', 'B', 'X'] + list(_ALL_BOLTS)
+  backdrop, masks = split_art(art, order, ' ')
+  shape = backdrop.shape
+  things = {}
+  things['P'] = em.Walker('P', shape, mask_position(masks['P']),
+                          impassable='', confined=True)      # :173-176
+  things['B'] = em.PlainDrape('B', masks['B'])
+  marauders = em.PlainDrape('X', masks['X'])
+  marauders.aux['dx'] = -1                                   # :140
+  things['X'] = marauders
+  for ch in _ALL_BOLTS:                                      # :192-196, :226-230
+    w = em.Walker(ch, shape, mask_position(masks[ch]), impassable='')
+    em.walker_teleport(w, -1, -1)
+    things[ch] = w
+  world = em.World(shape[0], shape[1], backdrop, things, z_order=order,
+                   groups=[order], program=marauders_program)
+  world.rng = rng
+  return world
+
+
+def marauders_program(world, ch, actions):
+  plot = world.plot
+  ent = world.things[ch]
+  board = world.board
+  layer = lambda c: board == ord(c)
+  if ch == 'P':                                   # PlayerSprite.update :178-186
+    if actions == 0:
+      em.walker_move(ent, board, plot, em.M_W)
+    elif actions == 1:
+      em.walker_move(ent, board, plot, em.M_E)
+    elif actions == 4:
+      plot.terminate_episode()
+  elif ch == 'B':                                 # BunkerDrape.update :113-120
+    bolts = np.zeros(board.shape, dtype=bool)
+    for c in _ALL_BOLTS:
+      bolts |= layer(c)
+    hits = bolts & ent.curtain
+    ent.curtain ^= hits
+    plot.add_reward(-int(hits.sum()))
+    plot.store['bunker_hitters'] = [chr(c) for c in board[hits]]
+  elif ch == 'X':                                 # MarauderDrape.update :142-163
+    bolts = np.zeros(board.shape, dtype=bool)
+    for c in _UP_BOLTS:
+      bolts |= layer(c)
+    hits = bolts & ent.curtain
+    ent.curtain ^= hits
+    plot.add_reward(int(hits.sum()) * 10)
+    plot.store['marauder_hitters'] = [chr(c) for c in board[hits]]
+    if (not ent.curtain.any()) or ent.curtain[10, :].any():
+      plot.terminate_episode()
+      return
+    # Float cadence: frame % max(1, count // 8.0000001)   (:157)
+    if plot.frame % max(1, int(ent.curtain.sum()) // 8.0000001):
+      return
+    if np.any(ent.curtain[:, 0] | ent.curtain[:, -1]):
+      ent.aux['dx'] = -ent.aux['dx']
+      ent.curtain[:] = np.roll(ent.curtain, shift=1, axis=0)
+    ent.curtain[:] = np.roll(ent.curtain, shift=ent.aux['dx'], axis=1)
+  elif ch in _UP_BOLTS:                           # UpwardLaserBoltSprite :198-220
+    if ent.visible:
+      if (ch in plot.store['bunker_hitters'] or
+          ch in plot.store['marauder_hitters']):
+        em.walker_teleport(ent, -1, -1)
+      else:
+        em.walker_move(ent, board, plot, em.M_N)
+    elif actions == 2:
+      if plot.store.get('last_player_shot') == plot.frame:
+        return
+      plot.store['last_player_shot'] = plot.frame
+      row, col = world.things['P'].position
+      em.walker_teleport(ent, row - 1, col)
+  elif ch in _DOWN_BOLTS:                         # DownwardLaserBoltSprite :232-256
+    if ent.visible:
+      if ch in plot.store['bunker_hitters']:
+        em.walker_teleport(ent, -1, -1)
+        return
+      if ent.position == world.things['P'].position:
+        plot.terminate_episode()
+      em.walker_move(ent, board, plot, em.M_S)
+    else:
+      if plot.store.get('last_marauder_shot') == plot.frame:
+        return
+      plot.store['last_marauder_shot'] = plot.frame
+      seen = layer('X')
+      cols = np.nonzero(seen.sum(axis=0))[0]
+      col = int(world.rng.choice(cols))
+      row = int(np.nonzero(seen[:, col])[0][-1]) + 1
+      em.walker_teleport(ent, row, col)
+  else:
+    raise KeyError(ch)
+
+
+# ==========================================================================
+# Test-fixture world: generic MazeWalkers / Scrollys / static drapes driven by
+# per-entity motion codes (tests/test_things.py:203-295).
+# ==========================================================================
+
+def make_fixture_world(art, what_lies_beneath, walkers, scrollys=None,
+                       drapes='', update_schedule=None, z_order=None):
+  """Build a world of fixture entities from ASCII art.
+
+  walkers:  {char: dict(impassable=..., confined=..., egocentric=..., group=...)}
+  scrollys: {char: dict(pattern=bool array, corner=(r, c), margins=..., group=...)}
+  drapes:   chars of static drapes (TestDrape: curtain never changes).
+  """
+  scrollys = scrollys or {}
+  chars = list(walkers) + list(scrollys) + list(drapes)
+  if update_schedule is None:
+    update_schedule = [chars]
+  flat = [c for g in update_schedule for c in g]
+  assert sorted(flat) == sorted(chars)
+  backdrop, masks = split_art(art, flat, what_lies_beneath)
+  shape = backdrop.shape
+  things = {}
+  for ch in flat:
+    if ch in walkers:
+      things[ch] = em.Walker(ch, shape, mask_position(masks[ch]), **walkers[ch])
+    elif ch in scrollys:
+      kw = dict(scrollys[ch])
+      things[ch] = em.Scrolly(ch, shape, kw.pop('pattern'), kw.pop('corner'),
+                              **kw)
+    else:
+      things[ch] = em.PlainDrape(ch, masks[ch])
+  return em.World(shape[0], shape[1], backdrop, things,
+                  z_order=z_order if z_order is not None else flat,
+                  groups=update_schedule, program=fixture_program)
+
+
+def fixture_program(world, ch, actions):
+  """TestMazeWalker.real_update / TestScrolly.real_update: `actions` is None,
+  one motion code for everybody, or {char: motion code}; entities with no code
+  call `_stay` (test_things.py:219-250, 268-295)."""
+  ent = world.things[ch]
+  if isinstance(actions, dict):
+    motion = actions.get(ch, em.M_STAY)
+  elif actions is None:
+    motion = em.M_STAY
+  else:
+    motion = actions
+  if isinstance(ent, em.Walker):
+    em.walker_move(ent, world.board, world.plot, motion)
+  elif isinstance(ent, em.Scrolly):
+    em.scrolly_move(ent, world, motion)

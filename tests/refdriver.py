@@ -1,0 +1,148 @@
+"""Drive the REAL reference (imported from /root/reference) on arbitrary art.
+
+Only usable where /root/reference exists (this build container); used by
+`tests/golden/make_golden.py` to produce the committed golden fixtures and by
+`tests/test_oracle_vs_reference.py` for live differential checks.  Never
+imported on the GPU box.
+"""
+
+import os
+import sys
+
+import numpy as np
+
+REFERENCE_ROOT = '/root/reference'
+
+
+def available():
+  return os.path.isdir(os.path.join(REFERENCE_ROOT, 'pycolab'))
+
+
+def _import():
+  if REFERENCE_ROOT not in sys.path:
+    sys.path.insert(0, REFERENCE_ROOT)
+  import warnings
+  warnings.filterwarnings('ignore', category=DeprecationWarning)
+  from pycolab import ascii_art, cropping
+  from pycolab.examples import (scrolly_maze, warehouse_manager,
+                                extraterrestrial_marauders)
+  from pycolab.tests import test_things
+  return dict(ascii_art=ascii_art, cropping=cropping, scrolly_maze=scrolly_maze,
+              warehouse_manager=warehouse_manager,
+              extraterrestrial_marauders=extraterrestrial_marauders,
+              test_things=test_things)
+
+
+def ref_scrolly_maze(maze_art, board_art, beneath='#', level=None):
+  m = _import()['scrolly_maze']
+  if level is not None:
+    return m.make_game(level)
+  saved = (m.MAZES_ART, m.MAZES_WHAT_LIES_BENEATH, m.STAR_ART)
+  try:
+    m.MAZES_ART = [maze_art]
+    m.MAZES_WHAT_LIES_BENEATH = [beneath]
+    m.STAR_ART = board_art
+    return m.make_game(0)
+  finally:
+    m.MAZES_ART, m.MAZES_WHAT_LIES_BENEATH, m.STAR_ART = saved
+
+
+def ref_stock_scrolly_art(level):
+  m = _import()['scrolly_maze']
+  return (list(m.MAZES_ART[level]), list(m.STAR_ART),
+          m.MAZES_WHAT_LIES_BENEATH[level])
+
+
+def ref_warehouse(art, beneath=' ', level=None):
+  m = _import()['warehouse_manager']
+  if level is not None:
+    return m.make_game(level)
+  saved = (m.WAREHOUSES_ART, m.WAREHOUSES_WHAT_LIES_BENEATH)
+  try:
+    m.WAREHOUSES_ART = [art]
+    m.WAREHOUSES_WHAT_LIES_BENEATH = [beneath]
+    return m.make_game(0)
+  finally:
+    m.WAREHOUSES_ART, m.WAREHOUSES_WHAT_LIES_BENEATH = saved
+
+
+def ref_stock_warehouse_art(level):
+  m = _import()['warehouse_manager']
+  wlb = m.WAREHOUSES_WHAT_LIES_BENEATH[level]
+  return list(m.WAREHOUSES_ART[level]), (wlb if isinstance(wlb, str) else list(wlb))
+
+
+def ref_marauders(art=None):
+  m = _import()['extraterrestrial_marauders']
+  if art is None:
+    return m.make_game()
+  saved = m.GAME_ART
+  try:
+    m.GAME_ART = art
+    return m.make_game()
+  finally:
+    m.GAME_ART = saved
+
+
+def ref_stock_marauders_art():
+  return list(_import()['extraterrestrial_marauders'].GAME_ART)
+
+
+_NAMES = ('n', 'ne', 'e', 'se', 's', 'sw', 'w', 'nw', 'stay')
+
+
+def ref_fixture(art, what_lies_beneath, walkers, scrollys=None, drapes='',
+                update_schedule=None, z_order=None):
+  """Same signature as oracle.games.make_fixture_world, built from the
+  reference's own test fixtures (tests/test_things.py)."""
+  mods = _import()
+  aa, tt = mods['ascii_art'], mods['test_things']
+  scrollys = scrollys or {}
+  sprites = {}
+  for ch, kw in walkers.items():
+    sprites[ch] = aa.Partial(
+        tt.TestMazeWalker, impassable=kw.get('impassable', ''),
+        confined_to_board=kw.get('confined', False),
+        egocentric_scroller=kw.get('egocentric', False),
+        scrolling_group=kw.get('group', ''))
+  dr = {}
+  shape = (len(art), len(art[0]))
+  for ch, kw in scrollys.items():
+    dr[ch] = aa.Partial(
+        tt.TestScrolly, board_shape=shape,
+        whole_pattern=np.array(kw['pattern'], dtype=bool),
+        board_northwest_corner=tuple(kw['corner']),
+        scroll_margins=kw.get('margins', (2, 3)),
+        scrolling_group=kw.get('group', ''))
+  for ch in drapes:
+    dr[ch] = tt.TestDrape
+  chars = list(walkers) + list(scrollys) + list(drapes)
+  if update_schedule is None:
+    update_schedule = [chars]
+  return aa.ascii_art_to_game(art, what_lies_beneath, sprites, dr,
+                              update_schedule=update_schedule, z_order=z_order)
+
+
+def fixture_actions_to_ref(actions):
+  """Oracle motion codes -> the strings TestMazeWalker/TestScrolly expect."""
+  if actions is None:
+    return None
+  if isinstance(actions, dict):
+    return {ch: _NAMES[m] for ch, m in actions.items()}
+  return _NAMES[actions]
+
+
+def reward_pair(reward):
+  """(value, has_reward) encoding used by fixtures and the device."""
+  if reward is None:
+    return 0, 0
+  return int(reward), 1
+
+
+def snapshot_things(engine):
+  """{char: (row, col, visible)} for sprites of a reference engine."""
+  out = {}
+  for ch, ent in engine.things.items():
+    if hasattr(ent, 'position'):
+      out[ch] = (int(ent.position[0]), int(ent.position[1]), bool(ent.visible))
+  return out
