@@ -1,0 +1,250 @@
+"""Generate the golden fixtures in this directory from the REAL reference.
+
+Run in the build container (where /root/reference exists):
+
+    python tests/golden/make_golden.py
+
+Every .npz written here holds the inputs (level art as uint8 arrays, action
+stream, RNG seed, entity configuration as JSON) and the outputs the unmodified
+reference produced for them (board per frame, reward, discount, game_over,
+sprite registers, crops).  The GPU box has no /root/reference: the `-m gpu`
+parity tests and the oracle tests compare against these files.
+"""
+
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import refdriver
+import trajectory as tj
+from pycolab_b200 import levels
+
+
+def save(name, **arrays):
+  path = os.path.join(HERE, name + '.npz')
+  np.savez_compressed(path, **arrays)
+  print('%-32s %8.1f KiB' % (name, os.path.getsize(path) / 1024.0))
+
+
+def sprite_recorder(chars, sink):
+  def on_frame(env, out):
+    things = env.things
+    row = []
+    for ch in chars:
+      s = things[ch]
+      vp = getattr(s, 'virtual_position', s.position)
+      row.append([int(s.position[0]), int(s.position[1]), int(bool(s.visible)),
+                  int(vp[0]), int(vp[1])])
+    sink.append(row)
+  return on_frame
+
+
+def scrolly(name, maze, board, beneath, actions, level=None):
+  sprites = []
+  if level is not None:
+    make = lambda: refdriver.ref_scrolly_maze(None, None, level=level)
+  else:
+    make = lambda: refdriver.ref_scrolly_maze(maze, board, beneath)
+  traj = tj.run_trajectory(make, actions,
+                           on_frame=sprite_recorder('Pabc', sprites))
+  save(name, maze_art=tj.art_to_u8(maze), board_art=tj.art_to_u8(board),
+       beneath=np.array([ord(beneath)], dtype=np.uint8),
+       actions=np.array(actions, dtype=np.int32),
+       sprites=np.array(sprites, dtype=np.int32), **traj)
+
+
+def warehouse(name, art, wlb, actions, level=None):
+  chars = [c for c in '1234567890' if c in ''.join(art)] + ['P']
+  sprites = []
+  if level is not None:
+    make = lambda: refdriver.ref_warehouse(None, level=level)
+  else:
+    make = lambda: refdriver.ref_warehouse(art, wlb)
+  traj = tj.run_trajectory(make, actions,
+                           on_frame=sprite_recorder(chars, sprites))
+  wlb_arr = (np.array([[ord(wlb)]], dtype=np.uint8) if isinstance(wlb, str)
+             else tj.art_to_u8(wlb))
+  save(name, art=tj.art_to_u8(art), what_lies_beneath=wlb_arr,
+       sprite_chars=np.frombuffer(''.join(chars).encode(), dtype=np.uint8),
+       actions=np.array(actions, dtype=np.int32),
+       sprites=np.array(sprites, dtype=np.int32), **traj)
+
+
+def marauders(name, seed, actions):
+  art = refdriver.ref_stock_marauders_art()
+  chars = 'Pabcdyz'
+  sprites = []
+  np.random.seed(seed)            # the reference uses the global NumPy RNG
+  traj = tj.run_trajectory(lambda: refdriver.ref_marauders(), actions,
+                           on_frame=sprite_recorder(chars, sprites))
+  save(name, art=tj.art_to_u8(art), rng_seed=np.array([seed], dtype=np.int64),
+       actions=np.array(actions, dtype=np.int32),
+       sprites=np.array(sprites, dtype=np.int32), **traj)
+
+
+def fixture_walkers(name, seed, T=300):
+  rs = np.random.RandomState(seed)
+  H, W = int(rs.randint(5, 12)), int(rs.randint(5, 14))
+  art = np.full((H, W), ord(' '), dtype=np.uint8)
+  art[rs.random_sample((H, W)) < 0.25] = ord('#')
+  art[rs.random_sample((H, W)) < 0.1] = ord('%')
+  free = np.argwhere(art == ord(' '))
+  picks = free[rs.permutation(len(free))[:3]]
+  for ch, (r, c) in zip('abc', picks):
+    art[r, c] = ord(ch)
+  walkers = {
+      'a': dict(impassable='#', confined=bool(rs.randint(2))),
+      'b': dict(impassable='#%a', confined=bool(rs.randint(2))),
+      'c': dict(impassable='', confined=False),
+  }
+  schedule = [['a'], ['b', 'c']] if rs.randint(2) else [['a', 'b', 'c']]
+  z_order = ''.join(rs.permutation(list('abc')))
+  art_l = tj.u8_to_art(art)
+  motions = rs.randint(0, 9, size=(T, 3)).astype(np.int32)
+  sprites = []
+  traj = tj.run_trajectory(
+      lambda: refdriver.ref_fixture(art_l, ' ', walkers,
+                                    update_schedule=schedule, z_order=z_order),
+      motions,
+      convert_action=lambda m: refdriver.fixture_actions_to_ref(
+          {ch: int(v) for ch, v in zip('abc', m)}),
+      on_frame=sprite_recorder('abc', sprites))
+  cfg = dict(walkers=walkers, scrollys={}, drapes='', schedule=schedule,
+             z_order=z_order, what_lies_beneath=' ', action_chars='abc')
+  save(name, art=art, config=np.frombuffer(json.dumps(cfg).encode(), np.uint8),
+       actions=motions, sprites=np.array(sprites, dtype=np.int32), **traj)
+
+
+def fixture_scrolly(name, seed, margins, second_ego, T=400):
+  rs = np.random.RandomState(1000 + seed)
+  PH, PW, H, W = 17, 23, 8, 11
+  pattern = rs.random_sample((PH, PW)) < 0.2
+  pattern2 = rs.random_sample((PH, PW)) < 0.1
+  corner = (int(rs.randint(0, PH - H + 1)), int(rs.randint(0, PW - W + 1)))
+  art = np.full((H, W), ord(' '), dtype=np.uint8)
+  art[3, 4] = ord('P')
+  art[5, 7] = ord('q')
+  art_l = tj.u8_to_art(art)
+  walkers = {'P': dict(impassable='#', egocentric=True),
+             'q': dict(impassable='#', egocentric=bool(second_ego))}
+  scrollys = {'#': dict(pattern=pattern, corner=corner, margins=margins),
+              '@': dict(pattern=pattern2, corner=corner, margins=margins)}
+  schedule = [['#'], ['P', 'q'], ['@']]
+  motions = rs.randint(0, 9, size=(T,)).astype(np.int32)
+  sprites, curtains = [], []
+  rec = sprite_recorder('Pq', sprites)
+
+  def on_frame(env, out):
+    rec(env, out)
+    curtains.append(np.stack([env.things['#'].curtain.copy(),
+                              env.things['@'].curtain.copy()]))
+
+  env = refdriver.ref_fixture(art_l, ' ', walkers, scrollys,
+                              update_schedule=schedule, z_order='@#Pq')
+  out = env.its_showtime()
+  boards = [tj.board_of(out[0]).copy()]
+  on_frame(env, out)
+  used = []
+  for m in motions:
+    try:
+      out = env.play(refdriver.fixture_actions_to_ref(int(m)))
+    except RuntimeError:
+      break                         # reference rejects a (0,0)-clipped order
+    used.append(int(m))
+    boards.append(tj.board_of(out[0]).copy())
+    on_frame(env, out)
+  cfg = dict(
+      walkers=walkers,
+      scrollys={ch: dict(corner=list(corner),
+                         margins=None if margins is None else list(margins))
+                for ch in '#@'},
+      drapes='', schedule=schedule, z_order='@#Pq', what_lies_beneath=' ',
+      action_chars='')
+  save(name, art=art, config=np.frombuffer(json.dumps(cfg).encode(), np.uint8),
+       pattern_hash=pattern.astype(np.uint8), pattern_at=pattern2.astype(np.uint8),
+       actions=np.array(used, dtype=np.int32), boards=np.stack(boards),
+       sprites=np.array(sprites, dtype=np.int32),
+       curtains=np.stack(curtains).astype(np.uint8))
+
+
+def cropper(name, pad, margins, offset, saccade, T=300):
+  cropping = refdriver._import()['cropping']
+  maze, board, beneath = levels.scrolly_maze_level(5, world_shape=(65, 65),
+                                                   board_shape=(32, 32))
+  rs = np.random.RandomState(11)
+  actions = rs.randint(0, 5, size=T)
+  crops, corners = [], []
+  state = {}
+
+  def make():
+    eng = refdriver.ref_scrolly_maze(maze, board, beneath)
+    if 'c' not in state:
+      state['c'] = cropping.ScrollingCropper(
+          rows=9, cols=9, to_track=['P'], scroll_margins=margins,
+          pad_char=pad, initial_offset=offset, saccade=saccade)
+    state['c'].set_engine(eng)
+    return eng
+
+  def on_frame(env, out):
+    crops.append(state['c'].crop(out[0]).board.copy())
+    corners.append(list(state['c']._corner))
+
+  traj = tj.run_trajectory(make, actions.tolist(), on_frame=on_frame)
+  cfg = dict(rows=9, cols=9, pad=pad, margins=list(margins),
+             offset=None if offset is None else list(offset), saccade=saccade)
+  save(name, maze_art=tj.art_to_u8(maze), board_art=tj.art_to_u8(board),
+       beneath=np.array([ord(beneath)], dtype=np.uint8),
+       config=np.frombuffer(json.dumps(cfg).encode(), np.uint8),
+       actions=actions.astype(np.int32), crops=np.stack(crops),
+       corners=np.array(corners, dtype=np.int32), **traj)
+
+
+def main():
+  assert refdriver.available(), '/root/reference is required'
+  # BASELINE.json configs[0]: stock scrolly_maze, 1000 random-action steps.
+  for level, T in ((0, 1000), (1, 400), (2, 400)):
+    maze, board, beneath = refdriver.ref_stock_scrolly_art(level)
+    rs = np.random.RandomState(100 + level)
+    scrolly('scrolly_stock_L%d' % level, maze, board, beneath,
+            rs.randint(0, 5, size=T).tolist(), level=level)
+  maze, board, beneath = refdriver.ref_stock_scrolly_art(0)
+  scrolly('scrolly_stock_L0_quit', maze, board, beneath,
+          np.random.RandomState(7).randint(0, 6, size=300).tolist(), level=0)
+  for seed in (0, 1):
+    maze, board, beneath = levels.scrolly_maze_level(seed)
+    acts = np.random.RandomState(seed).choice(
+        [0, 1, 2, 3, 4], size=300, p=[.3, .15, .3, .15, .1]).tolist()
+    scrolly('scrolly_gen64_s%d' % seed, maze, board, beneath, acts)
+
+  for level in (0, 1, 2):
+    art, wlb = refdriver.ref_stock_warehouse_art(level)
+    warehouse('warehouse_stock_L%d' % level, art, wlb,
+              np.random.RandomState(200 + level).randint(0, 5, size=600).tolist(),
+              level=level)
+  art = levels.warehouse_level(3)
+  warehouse('warehouse_gen80_s3', art, ' ',
+            np.random.RandomState(3).randint(0, 4, size=250).tolist())
+
+  for seed in (0, 1, 2):
+    marauders('marauders_stock_s%d' % seed, seed,
+              np.random.RandomState(300 + seed).randint(0, 4, size=1000).tolist())
+
+  for seed in range(6):
+    fixture_walkers('fixture_walkers_%d' % seed, seed)
+  for seed, margins, ego2 in ((0, (2, 3), 0), (1, None, 1), (2, (1, 1), 0),
+                              (3, None, 0), (4, (2, 2), 1), (5, (1, 2), 1)):
+    fixture_scrolly('fixture_scrolly_%d' % seed, seed, margins, ego2)
+
+  cropper('crop_ego_pad', ' ', (None, None), None, True)
+  cropper('crop_margins_nopad', None, (2, 3), None, True)
+  cropper('crop_margins_pad_offset', ' ', (2, 3), (1, -2), False)
+
+
+if __name__ == '__main__':
+  main()

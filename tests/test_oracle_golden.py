@@ -1,0 +1,114 @@
+"""Pin the oracle against the golden fixtures the real reference produced.
+
+CPU-only; runs everywhere (the fixtures travel with the repo, /root/reference
+does not).  Every board, reward, discount, game_over, sprite register and crop
+must match bit-for-bit.
+"""
+
+import numpy as np
+import pytest
+
+import golden_cases as gc
+import trajectory as tj
+from oracle import engine_model as em
+from oracle import games
+
+
+def _sprite_sink(chars, sink):
+  def on_frame(env, out):
+    sink.append(gc.oracle_sprite_rows(env, chars))
+  return on_frame
+
+
+@pytest.mark.parametrize('name', gc.names('scrolly_'))
+def test_scrolly(name):
+  g = gc.load(name)
+  maze, board, beneath = gc.scrolly_art(g)
+  sprites = []
+  got = tj.run_trajectory(
+      lambda: games.make_scrolly_maze(maze, board, '+', beneath),
+      g['actions'].tolist(), on_frame=_sprite_sink('Pabc', sprites))
+  tj.assert_same_trajectory(g, got, name)
+  np.testing.assert_array_equal(g['sprites'], np.array(sprites))
+
+
+@pytest.mark.parametrize('name', gc.names('warehouse_'))
+def test_warehouse(name):
+  g = gc.load(name)
+  art, wlb = gc.warehouse_art(g)
+  chars = bytes(g['sprite_chars']).decode()
+  sprites = []
+  got = tj.run_trajectory(lambda: games.make_warehouse(art, wlb),
+                          g['actions'].tolist(),
+                          on_frame=_sprite_sink(chars, sprites))
+  tj.assert_same_trajectory(g, got, name)
+  np.testing.assert_array_equal(g['sprites'], np.array(sprites))
+
+
+@pytest.mark.parametrize('name', gc.names('marauders_'))
+def test_marauders(name):
+  g = gc.load(name)
+  art = tj.u8_to_art(g['art'])
+  rng = np.random.RandomState(int(g['rng_seed'][0]))
+  sprites = []
+  got = tj.run_trajectory(lambda: games.make_marauders(art, rng),
+                          g['actions'].tolist(),
+                          on_frame=_sprite_sink('Pabcdyz', sprites))
+  tj.assert_same_trajectory(g, got, name)
+  np.testing.assert_array_equal(g['sprites'], np.array(sprites))
+
+
+@pytest.mark.parametrize('name', gc.names('fixture_walkers_'))
+def test_fixture_walkers(name):
+  g = gc.load(name)
+  kw, cfg = gc.fixture_kwargs(g)
+  chars = cfg['action_chars']
+  sprites = []
+  got = tj.run_trajectory(
+      lambda: games.make_fixture_world(**kw), g['actions'],
+      convert_action=lambda m: {ch: int(v) for ch, v in zip(chars, m)},
+      on_frame=_sprite_sink(chars, sprites))
+  tj.assert_same_trajectory(g, got, name)
+  np.testing.assert_array_equal(g['sprites'], np.array(sprites))
+
+
+@pytest.mark.parametrize('name', gc.names('fixture_scrolly_'))
+def test_fixture_scrolly(name):
+  g = gc.load(name)
+  kw, cfg = gc.fixture_kwargs(g)
+  world = games.make_fixture_world(**kw)
+  out = world.its_showtime()
+  for t in range(len(g['actions']) + 1):
+    np.testing.assert_array_equal(g['boards'][t], out[0], err_msg='t=%d' % t)
+    np.testing.assert_array_equal(g['sprites'][t],
+                                  gc.oracle_sprite_rows(world, 'Pq'))
+    np.testing.assert_array_equal(
+        g['curtains'][t],
+        np.stack([world.things['#'].curtain, world.things['@'].curtain]))
+    if t < len(g['actions']):
+      out = world.play(int(g['actions'][t]))
+
+
+@pytest.mark.parametrize('name', gc.names('crop_'))
+def test_cropper(name):
+  g = gc.load(name)
+  cfg = gc.config_of(g)
+  maze, board, beneath = gc.scrolly_art(g)
+  crop = em.ScrollingCrop(cfg['rows'], cfg['cols'], ['P'], pad_char=cfg['pad'],
+                          scroll_margins=tuple(cfg['margins']),
+                          initial_offset=cfg['offset'], saccade=cfg['saccade'])
+  crops, corners = [], []
+
+  def make():
+    w = games.make_scrolly_maze(maze, board, '+', beneath)
+    crop.set_engine(w)
+    return w
+
+  def on_frame(env, out):
+    crops.append(crop.crop(out[0]))
+    corners.append(list(crop.corner))
+
+  got = tj.run_trajectory(make, g['actions'].tolist(), on_frame=on_frame)
+  tj.assert_same_trajectory(g, got, name)
+  np.testing.assert_array_equal(g['crops'], np.stack(crops))
+  np.testing.assert_array_equal(g['corners'], np.array(corners))
