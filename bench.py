@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/sec of the batched step engine (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A "step" is one pass of the hot path (Engine.play for every env = ONE fused
+kernel launch through the C ABI) over one batch of synthetic random actions.
+Workload at every N: BASELINE.json configs[1] per GPU — scrolly_maze on seeded
+generated levels, 64x64 board over a 129x129 world, 4096 envs per GPU (weak
+scaling; envs shard across ranks with no data-path collective).
+
+Printed JSON (one line, rank 0): see the task contract.  `value` is timed on the
+device with per-step CUDA events (inputs resident in HBM, L2 flushed between
+steps outside the event pairs); `e2e` goes through `pcl_step_host` with pinned
+HOST buffers, copies inside the timed region.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BOARD = (64, 64)
+WORLD = (129, 129)
+BATCH_PER_GPU = 4096
+N_LEVELS = 32
+ACTIONS = 5                       # 0..4, no quit
+# Algorithmic bytes per env-step, reference layout:
+#   H*W*(1 backdrop + 2 pattern windows + 2 curtains + 1 board) + 64*S + 64
+A_STEP_BYTES = 64 * 64 * 6 + 64 * 4 + 64          # 24 896
+# Bytes this implementation's layout must move per env-step:
+#   backdrop 4096 + board 4096 + 2 bit-packed 64-row windows (64*2*8 B) + records r/w
+LAYOUT_STEP_BYTES = 4096 + 4096 + 2 * 64 * 8 + 2 * (4 * 32 + 2 * 32 + 64)
+
+
+def make_levels(n, seed0=1000):
+  from pycolab_b200 import levels
+  return [levels.scrolly_maze_level(seed0 + i, world_shape=WORLD, board_shape=BOARD)
+          for i in range(n)]
+
+
+# ------------------------------------------------------------- CPU baseline
+
+_ENV = {}
+
+
+def _cpu_worker(args):
+  """Step one oracle env (kept alive per process) for ~budget seconds."""
+  seed, budget = args
+  from oracle import games as ogames
+  if 'make' not in _ENV:
+    art = make_levels(1, seed0=1000 + seed % N_LEVELS)[0]
+    _ENV['make'] = lambda: ogames.make_scrolly_maze(art[0], art[1], '+', art[2])
+    _ENV['rs'] = np.random.RandomState(1234 + seed)
+    _ENV['env'] = _ENV['make']()
+    _ENV['env'].its_showtime()
+  make, rs, env = _ENV['make'], _ENV['rs'], _ENV['env']
+  steps = 0
+  t0 = time.perf_counter()
+  while True:
+    for a in rs.randint(0, ACTIONS, size=50):
+      if env.game_over:
+        env = make()
+        env.its_showtime()
+      else:
+        env.play(int(a))
+      steps += 1
+    el = time.perf_counter() - t0
+    if el >= budget:
+      _ENV['env'] = env
+      return steps, el
+
+
+def cpu_baseline(cores, budget, pool=None):
+  """Oracle port (Python/NumPy restatement of the reference's step) on `cores`
+  host processes; whole-sample env-steps/sec."""
+  if cores == 1 or pool is None:
+    results = [_cpu_worker((0, budget))]
+  else:
+    results = pool.map(_cpu_worker, [(i, budget) for i in range(cores)], chunksize=1)
+  steps = sum(r[0] for r in results)
+  secs = max(r[1] for r in results)
+  return steps / secs, steps
+
+
+# ------------------------------------------------------------------- clocks
+
+class ClockSampler(object):
+  QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+           'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+           'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, gpu_index):
+    self.gpu = gpu_index
+    self.proc = None
+    self.path = None
+
+  def start(self):
+    try:
+      fd, self.path = tempfile.mkstemp(suffix='.csv')
+      os.close(fd)
+      self.proc = subprocess.Popen(
+          ['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.QUERY,
+           '--format=csv,noheader,nounits', '-lms', '100'],
+          stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+    except OSError:
+      self.proc = None
+
+  def stop(self):
+    out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+    if self.proc is None:
+      return out
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=5)
+    except subprocess.TimeoutExpired:
+      self.proc.kill()
+    sm, smax, reasons = [], [], set()
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    for line in open(self.path):
+      f = [x.strip() for x in line.split(',')]
+      if len(f) < 9:
+        continue
+      try:
+        sm.append(float(f[1]))
+        smax.append(float(f[2]))
+      except ValueError:
+        continue
+      for name, val in zip(names, f[5:9]):
+        if val.lower().startswith('active'):
+          reasons.add(name)
+    os.unlink(self.path)
+    if sm:
+      out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)),
+                 reasons=sorted(reasons), samples=len(sm))
+    return out
+
+
+# --------------------------------------------------------------------- main
+
+def run_reference_arm(args, rank, world):
+  """The reference's CPU path for the same metric: the oracle port on all host
+  cores (the pure-Python reference itself cannot travel to the GPU box).  Each
+  "step" is a bounded time slice of the same workload on every core."""
+  if rank != 0:
+    return
+  import multiprocessing as mp
+  cores = os.cpu_count() or 1
+  K, W = args.steps, args.warmup
+  slice_s = max(0.05, min(1.0, 45.0 / max(1, K + W)))
+  t0 = time.perf_counter()
+  with mp.get_context('fork').Pool(cores) as pool:
+    for _ in range(W):
+      cpu_baseline(cores, slice_s, pool)
+    total_steps, total_secs = 0, 0.0
+    for _ in range(K):
+      rate, steps = cpu_baseline(cores, slice_s, pool)
+      total_steps += steps
+      total_secs += steps / rate
+  value = total_steps / total_secs
+  print(json.dumps({
+      'impl': 'reference', 'metric': 'env_steps_per_sec', 'value': value,
+      'unit': 'env-steps/s', 'n_gpus': args.gpus, 'steps': K,
+      'warmup': W, 'ms_per_step': 1000.0 * total_secs / max(1, K),
+      'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+      'dtype': 'u8', 'data': 'synthetic',
+      'config': workload_config(args.gpus),
+      'cpu_baseline': {'value': value, 'unit': 'env-steps/s', 'cores': cores,
+                       'kind': 'port',
+                       'sample': '%d env-steps of the same generated 64x64 levels, one '
+                                 'oracle env per host process, %d processes' % (
+                                     total_steps, cores)},
+      'e2e': {'value': value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0,
+              'd2h_bytes_per_step': 0},
+      'wall_s': time.perf_counter() - t0}))
+
+
+def workload_config(n_gpus):
+  return {'workload': 'scrolly_maze 64x64 board / 129x129 world, generated levels '
+                      '(BASELINE.json configs[1]), random actions 0-4, auto-reset',
+          'batch_per_gpu': BATCH_PER_GPU, 'global_batch': BATCH_PER_GPU * n_gpus,
+          'levels': N_LEVELS, 'parallelism': 'env-sharded x%d, no collective' % n_gpus,
+          'l2': 'flushed between steps (256 MiB write outside the timed events)'}
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=200)
+  ap.add_argument('--warmup', type=int, default=20)
+  ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+  ap.add_argument('--cpu-seconds', type=float, default=12.0)
+  ap.add_argument('--no-flush', action='store_true')
+  args = ap.parse_args()
+
+  rank = int(os.environ.get('RANK', '0'))
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+
+  if args.impl == 'reference':
+    run_reference_arm(args, rank, world)
+    return
+
+  import torch
+  import torch.distributed as dist
+  from pycolab_b200 import batched
+  from pycolab_b200.games import scrolly_maze
+
+  torch.cuda.set_device(local_rank)
+  dev = torch.device('cuda', local_rank)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+
+  B, K, W = BATCH_PER_GPU, args.steps, max(3, args.warmup)
+  arts = make_levels(N_LEVELS)
+  games = [scrolly_maze.make_game(*a) for a in arts]
+  eng = batched.BatchedEngine(games, batch=B, device=local_rank, env_offset=rank * B)
+  eng.its_showtime()
+  rs = np.random.RandomState(1234 + rank)
+  actions_np = rs.randint(0, ACTIONS, size=(W + K, B)).astype(np.int32)
+  actions = torch.from_numpy(actions_np).to(dev)
+  flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+  def barrier():
+    torch.cuda.synchronize(dev)
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize(dev)
+
+  # ---- device-resident throughput: per-step CUDA events ------------------
+  for t in range(W):
+    eng.play(actions[t])
+  barrier()
+  sampler = ClockSampler(local_rank)
+  sampler.start()
+  starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+  stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+  launches0 = eng.launch_count()
+  barrier()
+  wall0 = time.perf_counter()
+  for t in range(K):
+    if not args.no_flush:
+      flush.fill_(t & 0xff)
+    starts[t].record()
+    eng.play(actions[W + t])
+    stops[t].record()
+  barrier()
+  wall = time.perf_counter() - wall0
+  launches = eng.launch_count() - launches0
+  clocks = sampler.stop()
+  step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, stops)])
+  dev_ms = float(step_ms.sum())
+  if world > 1:
+    t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+  value = world * B * K / (dev_ms / 1000.0)
+  kernel_ms = float(np.median(step_ms))
+
+  # ---- end to end through the host-buffer C-ABI call ---------------------
+  for t in range(3):
+    eng.play_host(actions_np[t])
+  barrier()
+  e2e_steps = min(K, 100)
+  t0 = time.perf_counter()
+  for t in range(e2e_steps):
+    eng.play_host(actions_np[W + t])
+  barrier()
+  e2e_s = time.perf_counter() - t0
+  if world > 1:
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+  e2e_value = world * B * e2e_steps / e2e_s
+  errors = int(eng.error_codes().abs().max())
+
+  if rank == 0:
+    peaks = {}
+    try:
+      peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except (OSError, ValueError):
+      pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    achieved = B * A_STEP_BYTES / (kernel_ms / 1000.0) / 1e9
+    layout = B * LAYOUT_STEP_BYTES / (kernel_ms / 1000.0) / 1e9
+    cpu_value, cpu_steps = cpu_baseline(1, args.cpu_seconds)
+    print(json.dumps({
+        'metric': 'env_steps_per_sec', 'value': value, 'unit': 'env-steps/s',
+        'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': dev_ms / K,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'u8', 'data': 'synthetic', 'config': workload_config(world),
+        'clocks': clocks, 'gpu_launches': launches,
+        'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'steps': e2e_steps,
+                'h2d_bytes_per_step': B * 4,
+                'd2h_bytes_per_step': B * (BOARD[0] * eng.pitch + 4 + 1 + 4 + 1)},
+        'roofline': {
+            'kernel': 'scrolly_maze_step', 'bound': 'hbm', 'achieved': achieved,
+            'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+            'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback 6650',
+            'algorithmic_bytes_per_launch': B * A_STEP_BYTES,
+            'kernel_ms_median': kernel_ms, 'traffic': None,
+            'layout_bytes_per_launch': B * LAYOUT_STEP_BYTES,
+            'layout_achieved': layout, 'layout_frac': layout / peak},
+        'cpu_baseline': {'value': cpu_value, 'unit': 'env-steps/s', 'cores': 1,
+                         'kind': 'port',
+                         'sample': '%d env-steps of one oracle env on the same generated '
+                                   '64x64 levels' % cpu_steps},
+        'wall_s_timed_region': wall, 'env_errors': errors}))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+  main()

@@ -1,0 +1,224 @@
+/*
+ * pcl.h — C ABI of the B200 batched gridworld step engine (libpcl.so).
+ *
+ * pycolab has no FFI: its "plugin interface" for the per-step hot path is the
+ * Python object API  Engine.its_showtime() / Engine.play(actions)  returning
+ * (Observation(board, layers), reward, discount)  (reference
+ * pycolab/engine.py:520-639).  This header is what a native replacement of
+ * that path exports; INTEGRATION.md shows the ctypes binding a pycolab
+ * maintainer would add.  Conventions:
+ *
+ *   - plain C, no C++/torch types; every pointer named d_* is a DEVICE
+ *     pointer, h_* a HOST pointer; buffers are owned by the caller, the
+ *     library never frees them;
+ *   - every entry point returns 0 (PCL_OK) or a negative pcl_status and never
+ *     throws; per-environment run-time faults (the reference's RuntimeError /
+ *     scrolling.Error cases) are latched in a per-env error word readable
+ *     with pcl_error_codes();
+ *   - every launch takes the cudaStream_t (as void*) to enqueue on; nothing
+ *     synchronises except the *_host entry points;
+ *   - re-entrant per handle, no global state.
+ *
+ * Batched-state model: B independent environments ("envs"), each the
+ * equivalent of one reference Engine, live as a struct-of-arrays in HBM.
+ * One warp advances one env per launch.
+ */
+#ifndef PCL_H_
+#define PCL_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCL_ABI_VERSION 1
+
+#define PCL_MAX_SPRITES 16
+#define PCL_MAX_DRAPES 8
+#define PCL_SPRITE_WORDS 8   /* int32 words per sprite record */
+#define PCL_DRAPE_WORDS 8    /* int32 words per drape record  */
+#define PCL_PLOT_WORDS 16    /* int32 words per env plot record */
+#define PCL_MT_WORDS 625     /* MT19937: 624 state words + position */
+
+typedef enum pcl_status {
+  PCL_OK = 0,
+  PCL_ERR_INVALID = -1,      /* bad argument / malformed spec (ValueError)   */
+  PCL_ERR_UNSUPPORTED = -2,  /* spec is valid pycolab but not lowered        */
+  PCL_ERR_CUDA = -3,         /* a CUDA runtime call failed                   */
+  PCL_ERR_UNBOUND = -4,      /* pcl_bind_state has not been called           */
+  PCL_ERR_NOMEM = -5
+} pcl_status;
+
+/* Per-env latched error bits (pcl_error_codes).  Each mirrors an exception
+ * the reference would raise inside Engine.play(). */
+#define PCL_ENV_ERR_ORDER_MISMATCH   0x1  /* sprites.py:449-454, drapes.py:525-530 */
+#define PCL_ENV_ERR_SECOND_ORDER     0x2  /* scrolling.py:518-521 */
+#define PCL_ENV_ERR_EMPTY_CHOICE     0x4  /* np.random.choice([]) in marauders :253 */
+#define PCL_ENV_ERR_INDEX            0x8  /* NumPy IndexError (board look-up off the array) */
+
+/* Which game program advances the envs.  One fused kernel per program; the
+ * host "lowering" recognises the reference's entity classes and picks one. */
+typedef enum pcl_program {
+  PCL_PROG_NONE = 0,         /* no step program: pcl_render / pcl_crop only        */
+  PCL_PROG_SCROLLY_MAZE = 1, /* examples/scrolly_maze.py:212-364               */
+  PCL_PROG_WAREHOUSE = 2,    /* examples/warehouse_manager.py:139-295          */
+  PCL_PROG_MARAUDERS = 3,    /* examples/extraterrestrial_marauders.py:91-256  */
+  PCL_PROG_FIXTURE = 4       /* tests/test_things.py TestMazeWalker/TestScrolly */
+} pcl_program;
+
+/* Motion codes (prefab_parts/sprites.py:140-150). */
+enum { PCL_M_N = 0, PCL_M_NE, PCL_M_E, PCL_M_SE, PCL_M_S, PCL_M_SW, PCL_M_W,
+       PCL_M_NW, PCL_M_STAY, PCL_M_NONE = -1 };
+
+/* Action value meaning "actions=None" (the its_showtime() frame,
+ * engine.py:581). */
+#define PCL_ACTION_NONE (-1)
+
+/* Sprite record layout, int32[PCL_SPRITE_WORDS] (things.py:339-391,
+ * sprites.py:153-205). */
+enum { PCL_S_ROW = 0, PCL_S_COL, PCL_S_VROW, PCL_S_VCOL,
+       PCL_S_FLAGS,          /* bit0 visible; bits1-2 prior_visible: 0 None, 1 False, 2 True */
+       PCL_S_AUX0,           /* program-specific (e.g. patroller heading; permit mask)      */
+       PCL_S_AUX1,           /* program-specific (e.g. permit frame)                        */
+       PCL_S_AUX2 };
+/* Drape record layout, int32[PCL_DRAPE_WORDS] (drapes.py:293-376). */
+enum { PCL_D_CORNER_R = 0, PCL_D_CORNER_C, PCL_D_PRE_R, PCL_D_PRE_C,
+       PCL_D_LAST_FRAME,     /* _last_maybe_move_frame; INT32_MIN = -inf */
+       PCL_D_AUX0, PCL_D_AUX1, PCL_D_AUX2 };
+/* Plot record layout, int32[PCL_PLOT_WORDS] (plot.py:69-104,
+ * protocols/scrolling.py:198-241). */
+enum { PCL_P_FRAME = 0, PCL_P_GAME_OVER, PCL_P_ERROR, PCL_P_EPISODES,
+       PCL_P_ORDER_R, PCL_P_ORDER_C, PCL_P_ORDER_FRAME, PCL_P_EGO_MASK,
+       PCL_P_AUX0, PCL_P_AUX1, PCL_P_AUX2, PCL_P_AUX3,
+       PCL_P_CROP_R, PCL_P_CROP_C, PCL_P_CROP_INIT, PCL_P_RESERVED };
+
+/* Static description of one game (what Engine's set-up API collected:
+ * engine.py:248-518).  All envs of a handle share it. */
+typedef struct pcl_spec {
+  int32_t abi_version;           /* PCL_ABI_VERSION */
+  int32_t program;               /* pcl_program */
+  int32_t rows, cols;            /* board H x W (engine.py:202-203) */
+  int32_t pitch;                 /* bytes per board row in HBM, multiple of 16, >= cols */
+  int32_t n_sprites, n_drapes;
+  int32_t auto_reset;            /* 1: an env that is game-over is rebuilt by the next step */
+  int32_t pattern_rows, pattern_cols; /* Scrolly whole_pattern shape (drapes.py:338-343) */
+  int32_t pattern_words;         /* uint32 words per bit-packed pattern row (>= cols/32 + 2) */
+  int32_t bits_words;            /* uint32 words per bit-packed board-sized row */
+  uint8_t sprite_char[PCL_MAX_SPRITES];
+  uint8_t drape_char[PCL_MAX_DRAPES];
+  uint32_t impassable[PCL_MAX_SPRITES][4]; /* 128-bit ASCII set (sprites.py:190) */
+  int32_t sprite_confined[PCL_MAX_SPRITES];
+  int32_t sprite_egocentric[PCL_MAX_SPRITES];
+  int32_t margins[PCL_MAX_DRAPES][2];      /* Scrolly scroll_margins; -1,-1 = None */
+  uint8_t z_order[PCL_MAX_SPRITES + PCL_MAX_DRAPES]; /* initial z-order, chars */
+  int32_t n_groups;
+  int32_t group_len[PCL_MAX_SPRITES + PCL_MAX_DRAPES];
+  uint8_t group_chars[PCL_MAX_SPRITES + PCL_MAX_DRAPES]; /* update order, concatenated */
+  int32_t reserved[8];
+} pcl_spec;
+
+/* Device buffers of one handle (all caller-owned).  A "*_bstride" is the
+ * distance between consecutive envs in ELEMENTS of that array; 0 means all
+ * envs share one copy (legal only for arrays the step never writes). */
+typedef struct pcl_state {
+  /* static level data */
+  const uint8_t* d_backdrop;   int64_t backdrop_bstride;       /* u8 [*, rows, pitch] */
+  /* Scrolly patterns, bit-packed: u32 [*, pattern_rows, pattern_words], cell c
+   * of a row is bit (c & 31) of word (c >> 5). */
+  uint32_t* d_pattern[PCL_MAX_DRAPES];  int64_t pattern_bstride[PCL_MAX_DRAPES];
+  const uint32_t* d_pattern_init[PCL_MAX_DRAPES]; int64_t pattern_init_bstride[PCL_MAX_DRAPES];
+  /* board-sized bit-packed curtains for non-Scrolly drapes: u32 [*, rows, bits_words] */
+  uint32_t* d_bits[PCL_MAX_DRAPES];     int64_t bits_bstride[PCL_MAX_DRAPES];
+  const uint32_t* d_bits_init[PCL_MAX_DRAPES]; int64_t bits_init_bstride[PCL_MAX_DRAPES];
+  /* per-env registers and their reset templates */
+  int32_t* d_sprites;  const int32_t* d_sprites_init; int64_t sprites_init_bstride; /* [B, S, 8] */
+  int32_t* d_drapes;   const int32_t* d_drapes_init;  int64_t drapes_init_bstride;  /* [B, D, 8] */
+  int32_t* d_plot;     const int32_t* d_plot_init;    int64_t plot_init_bstride;    /* [B, 16]   */
+  uint32_t* d_rng;     /* MT19937 per env, u32 [B, PCL_MT_WORDS]; NULL if unused */
+} pcl_state;
+
+/* Per-step outputs = the (observation, reward, discount) triple of
+ * Engine.play() (engine.py:639) plus Engine.game_over (engine.py:657). */
+typedef struct pcl_outputs {
+  uint8_t* d_board;       /* u8 [B, rows, pitch]; Observation.board */
+  int32_t* d_reward;      /* i32 [B]; summed reward (plot.py:201-214), 0 if none */
+  uint8_t* d_has_reward;  /* u8 [B]; 0 = reference returned reward None */
+  float*   d_discount;    /* f32 [B]; 1.0 running / 0.0 terminated (plot.py:104,176) */
+  uint8_t* d_done;        /* u8 [B]; Engine.game_over after this step */
+} pcl_outputs;
+
+typedef struct pcl_handle pcl_handle;
+
+/* Validate `spec`, allocate the handle.  Replaces Engine.__init__ + set-up
+ * bookkeeping (engine.py:191-246). */
+int pcl_create(const pcl_spec* spec, int batch, int device, pcl_handle** out);
+int pcl_destroy(pcl_handle* h);
+
+/* Attach the caller's device buffers. */
+int pcl_bind_state(pcl_handle* h, const pcl_state* state);
+
+/* Engine.its_showtime() (engine.py:520-581) for every env whose d_env_mask
+ * byte is non-zero (NULL = all): restore the reset templates, then run the
+ * actions=None frame.  Envs not selected are left untouched. */
+int pcl_reset(pcl_handle* h, const uint8_t* d_env_mask, const pcl_outputs* out,
+              void* stream);
+
+/* Engine.play(actions) (engine.py:583-639) for all envs in lockstep: one fused
+ * kernel = _update_and_render + _apply_and_clear_plot.  d_actions is
+ * i32 [B, actions_per_env] (actions_per_env = 1 for the example games). */
+int pcl_step(pcl_handle* h, const int32_t* d_actions, const pcl_outputs* out,
+             void* stream);
+
+/* T consecutive pcl_step()s with d_actions i32 [T, B, actions_per_env]; the
+ * outputs hold the last step's values. */
+int pcl_run(pcl_handle* h, const int32_t* d_actions, int steps,
+            const pcl_outputs* out, void* stream);
+
+/* Host-buffer form of pcl_step: copies h_actions to the device, steps, copies
+ * the outputs back into the h_* buffers (any may be NULL = skip) and
+ * synchronises the stream.  `out` names the device staging buffers. */
+int pcl_step_host(pcl_handle* h, const int32_t* h_actions, int32_t* d_actions,
+                  const pcl_outputs* out, uint8_t* h_board, int32_t* h_reward,
+                  uint8_t* h_has_reward, float* h_discount, uint8_t* h_done,
+                  void* stream);
+
+/* Stand-alone renderer = Engine._render() + BaseObservationRenderer
+ * (engine.py:737-759, rendering.py:98-179) over reference-layout inputs:
+ * u8 backdrop [*, rows, pitch], byte curtains u8 [B, n_drapes, rows, pitch],
+ * sprite records, per-env z-order u8 [B, n_sprites + n_drapes] of chars. */
+int pcl_render(pcl_handle* h, const uint8_t* d_backdrop, int64_t backdrop_bstride,
+               const uint8_t* d_curtains, const int32_t* d_sprites,
+               const uint8_t* d_z_order, uint8_t* d_board, void* stream);
+
+/* Byte-per-cell view of drape `drape_index`'s current curtain (Drape.curtain,
+ * things.py:213-217): u8 [B, rows, pitch]. */
+int pcl_export_curtain(pcl_handle* h, int drape_index, uint8_t* d_out, void* stream);
+
+/* ScrollingCropper.crop (cropping.py:393-426): track sprite `sprite_index`,
+ * update the per-env window corner (kept in the plot record) and copy the
+ * crop_rows x crop_cols window of d_board into d_crop u8 [B, crop_rows, crop_cols]. */
+typedef struct pcl_crop_spec {
+  int32_t rows, cols;          /* window shape */
+  int32_t sprite_index;        /* entity to track (a sprite) */
+  int32_t pad_char;            /* ASCII code, or -1 for None */
+  int32_t margin_rows, margin_cols; /* resolved scroll margins (cropping.py:362-373) */
+  int32_t offset_rows, offset_cols; /* initial_offset */
+  int32_t saccade;
+} pcl_crop_spec;
+int pcl_crop(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d_board,
+             uint8_t* d_crop, void* stream);
+
+/* Copy the per-env latched error words (PCL_ENV_ERR_*) to d_out i32 [B]. */
+int pcl_error_codes(pcl_handle* h, int32_t* d_out, void* stream);
+
+/* Number of kernels this handle has launched so far. */
+int pcl_launch_count(pcl_handle* h, int64_t* out);
+
+const char* pcl_status_string(int status);
+int pcl_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* PCL_H_ */

@@ -1,0 +1,325 @@
+"""`BatchedEngine`: B independent pycolab environments stepped in lockstep on one GPU.
+
+The batched counterpart of the reference's one-`Engine`-per-env loop
+(engine.py:520-639): `its_showtime()` / `play(actions)` keep their meaning,
+vectorised over the env axis.  State lives in HBM as a struct-of-arrays
+(include/pcl.h `pcl_state`); PyTorch is used only to own the device buffers
+and the stream.  Every step is ONE fused CUDA kernel launched through the
+C ABI (`pcl_step`); there is no CPU path.
+"""
+
+import ctypes as C
+
+import numpy as np
+
+from pycolab_b200 import _lib
+from pycolab_b200 import lowering
+
+
+def _torch():
+  import torch
+  return torch
+
+
+class StepResult(object):
+  """(board, reward, has_reward, discount, done) of one batched step.
+
+  board: u8 [B, rows, cols] view into the engine-owned output buffer (valid
+  until the next step — copy to keep, as upstream rendering.py:55-63).
+  reward: i32 [B] with has_reward u8 [B] == 0 where the reference returns None.
+  discount: f32 [B].  done: u8 [B] (Engine.game_over).
+  """
+  __slots__ = ('board', 'reward', 'has_reward', 'discount', 'done')
+
+  def __init__(self, board, reward, has_reward, discount, done):
+    self.board, self.reward, self.has_reward = board, reward, has_reward
+    self.discount, self.done = discount, done
+
+  def __iter__(self):            # (observation, reward, discount) like Engine.play
+    return iter((self.board, self.reward, self.discount))
+
+
+class BatchedEngine(object):
+
+  def __init__(self, games, batch=None, device=0, auto_reset=True, rng_seed=0,
+               env_offset=0, rng_states=None):
+    """games: list of lowered games (`lowering.LoweredGame`) or set-up `Engine`s.
+    Env e uses games[e % len(games)]; with a single game the static level data
+    (backdrop, immutable patterns, reset templates) is shared by all envs.
+    env_offset: global index of this shard's env 0 (per-env RNG streams are
+    seeded rng_seed + global env index); rng_states: explicit u32 [B, 625]
+    MT19937 states (624 key words + position) instead of seeds."""
+    torch = _torch()
+    self._lib = _lib.load()
+    if not torch.cuda.is_available():
+      raise _lib.PclLibraryError('CUDA device required: pycolab_b200 has no CPU path')
+    games = [g if isinstance(g, lowering.LoweredGame) else lowering.lower(g)
+             for g in (games if isinstance(games, (list, tuple)) else [games])]
+    sig = games[0].signature()
+    for g in games[1:]:
+      if g.signature() != sig:
+        raise ValueError('all games of one BatchedEngine must share one structure')
+    self.game = g0 = games[0]
+    self.batch = B = int(batch if batch is not None else len(games))
+    self.device = torch.device('cuda', device)
+    self.auto_reset = bool(auto_reset)
+    self.rows, self.cols, self.pitch = g0.rows, g0.cols, g0.pitch
+    self.sprite_chars, self.drape_chars = g0.sprite_chars, g0.drape_chars
+    self.chars = ''.join(sorted(set(g0.sprite_chars + g0.drape_chars + g0.backdrop_chars)))
+    n = len(games)
+    shared = (n == 1)
+    dev = self.device
+
+    def tiled(arrays, dtype):
+      """Stack per-game numpy arrays into a device tensor over envs (or one)."""
+      if shared:
+        return torch.from_numpy(np.ascontiguousarray(arrays[0]).astype(dtype))[None].to(dev)
+      stacked = np.stack([np.ascontiguousarray(a).astype(dtype) for a in arrays])
+      t = torch.from_numpy(stacked).to(dev)
+      reps = (B + n - 1) // n
+      return t.repeat((reps,) + (1,) * (t.dim() - 1))[:B].contiguous()
+
+    def per_env(arrays, dtype):
+      stacked = np.stack([np.ascontiguousarray(a).astype(dtype) for a in arrays])
+      t = torch.from_numpy(stacked).to(dev)
+      reps = (B + n - 1) // n
+      return t.repeat((reps,) + (1,) * (t.dim() - 1))[:B].contiguous()
+
+    def bstride(t):
+      return 0 if t.shape[0] == 1 else t[0].numel()
+
+    self._keep = []             # every tensor the handle points at
+    st = _lib.State()
+    self.backdrop = tiled([g.backdrop for g in games], np.uint8)
+    st.d_backdrop, st.backdrop_bstride = self.backdrop.data_ptr(), bstride(self.backdrop)
+    self.patterns, self.bits = {}, {}
+    for d in sorted(g0.patterns):
+      arrays = [g.patterns[d].view(np.int32) for g in games]
+      if g0.pattern_mutable[d]:
+        init = tiled(arrays, np.int32)
+        live = per_env(arrays, np.int32)
+        st.d_pattern_init[d], st.pattern_init_bstride[d] = init.data_ptr(), bstride(init)
+        self._keep.append(init)
+      else:
+        live = tiled(arrays, np.int32)
+      self.patterns[d] = live
+      st.d_pattern[d] = live.data_ptr()
+      st.pattern_bstride[d] = bstride(live) if not g0.pattern_mutable[d] else live[0].numel()
+    for d in sorted(g0.bits):
+      arrays = [g.bits[d].view(np.int32) for g in games]
+      init = tiled(arrays, np.int32)
+      live = per_env(arrays, np.int32)
+      self.bits[d] = live
+      self._keep.append(init)
+      st.d_bits[d], st.bits_bstride[d] = live.data_ptr(), live[0].numel()
+      st.d_bits_init[d], st.bits_init_bstride[d] = init.data_ptr(), bstride(init)
+    self.sprites = per_env([g.sprites for g in games], np.int32)
+    self.drapes = per_env([g.drapes for g in games], np.int32)
+    self.plot = per_env([g.plot for g in games], np.int32)
+    # Live records start "game over" so the first pcl_reset builds every env.
+    self._sprites_init = tiled([g.sprites for g in games], np.int32)
+    self._drapes_init = tiled([g.drapes for g in games], np.int32)
+    self._plot_init = tiled([g.plot for g in games], np.int32)
+    st.d_sprites, st.d_sprites_init = self.sprites.data_ptr(), self._sprites_init.data_ptr()
+    st.sprites_init_bstride = bstride(self._sprites_init)
+    st.d_drapes, st.d_drapes_init = self.drapes.data_ptr(), self._drapes_init.data_ptr()
+    st.drapes_init_bstride = bstride(self._drapes_init)
+    st.d_plot, st.d_plot_init = self.plot.data_ptr(), self._plot_init.data_ptr()
+    st.plot_init_bstride = bstride(self._plot_init)
+    self.rng = None
+    if g0.needs_rng:
+      if rng_states is not None:
+        states = np.ascontiguousarray(rng_states, dtype=np.uint32).reshape(B, _lib.MT_WORDS)
+      else:
+        states = np.empty((B, _lib.MT_WORDS), dtype=np.uint32)
+        for e in range(B):
+          _, key, pos, _, _ = np.random.RandomState(rng_seed + env_offset + e).get_state()
+          states[e, :624] = key
+          states[e, 624] = pos
+      self.rng = torch.from_numpy(states.view(np.int32)).to(dev)
+      st.d_rng = self.rng.data_ptr()
+    self._state = st
+
+    # Outputs.
+    self._board = torch.zeros((B, self.rows, self.pitch), dtype=torch.uint8, device=dev)
+    self.reward = torch.zeros((B,), dtype=torch.int32, device=dev)
+    self.has_reward = torch.zeros((B,), dtype=torch.uint8, device=dev)
+    self.discount = torch.ones((B,), dtype=torch.float32, device=dev)
+    self.done = torch.zeros((B,), dtype=torch.uint8, device=dev)
+    self._out = _lib.Outputs(self._board.data_ptr(), self.reward.data_ptr(),
+                             self.has_reward.data_ptr(), self.discount.data_ptr(),
+                             self.done.data_ptr())
+    self._actions = torch.zeros((B,), dtype=torch.int32, device=dev)
+    self._host = None           # pinned staging for play_host()
+    self._crop_out = None
+
+    self._spec = g0.make_spec(self.auto_reset)
+    handle = C.c_void_p()
+    _lib.check(self._lib.pcl_create(C.byref(self._spec), B, self.device.index,
+                                    C.byref(handle)), 'pcl_create')
+    self._h = handle
+    _lib.check(self._lib.pcl_bind_state(self._h, C.byref(self._state)), 'pcl_bind_state')
+    self._showtime = False
+
+  # ---------------------------------------------------------------- running
+  def _stream(self):
+    return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+  @property
+  def board(self):
+    """u8 [B, rows, cols] view of the last rendered boards."""
+    return self._board[:, :, :self.cols]
+
+  def _result(self):
+    return StepResult(self.board, self.reward, self.has_reward, self.discount, self.done)
+
+  def its_showtime(self):
+    """Engine.its_showtime() for every env (engine.py:520-581)."""
+    if self._showtime:
+      raise RuntimeError('its_showtime should not be called after its_showtime() has '
+                         'been called')
+    self._showtime = True
+    _lib.check(self._lib.pcl_reset(self._h, None, C.byref(self._out), self._stream()),
+               'pcl_reset')
+    return self._result()
+
+  def reset(self, env_mask=None):
+    """Rebuild the selected envs (u8/bool [B] device tensor; None = all) and run
+    their its_showtime() frame; other envs are untouched."""
+    self._showtime = True
+    mask = None
+    if env_mask is not None:
+      mask = env_mask.to(device=self.device, dtype=_torch().uint8).contiguous()
+    _lib.check(self._lib.pcl_reset(self._h, None if mask is None else mask.data_ptr(),
+                                   C.byref(self._out), self._stream()), 'pcl_reset')
+    return self._result()
+
+  def play(self, actions):
+    """Engine.play(actions) for every env (engine.py:583-639).
+
+    actions: int32 [B] device tensor (or anything torch.as_tensor accepts).
+    With auto_reset, an env that was game-over is rebuilt instead and its
+    action is ignored; without it such envs stay frozen (upstream raises)."""
+    if not self._showtime:
+      raise RuntimeError('play() cannot be called until the Engine is placed in "play '
+                         'mode" via the its_showtime() method.')
+    torch = _torch()
+    if not (torch.is_tensor(actions) and actions.is_cuda and
+            actions.dtype == torch.int32 and actions.is_contiguous()):
+      actions = torch.as_tensor(actions, dtype=torch.int32).to(self.device).contiguous()
+    if actions.numel() != self.batch:
+      raise ValueError('expected %d actions, got %d' % (self.batch, actions.numel()))
+    _lib.check(self._lib.pcl_step(self._h, actions.data_ptr(), C.byref(self._out),
+                                  self._stream()), 'pcl_step')
+    return self._result()
+
+  def run(self, actions):
+    """T back-to-back steps; actions int32 [T, B] on the device."""
+    torch = _torch()
+    assert actions.is_cuda and actions.dtype == torch.int32 and actions.is_contiguous()
+    assert actions.dim() == 2 and actions.shape[1] == self.batch
+    _lib.check(self._lib.pcl_run(self._h, actions.data_ptr(), int(actions.shape[0]),
+                                 C.byref(self._out), self._stream()), 'pcl_run')
+    return self._result()
+
+  def play_host(self, actions, want_board=True):
+    """Host-buffer step through `pcl_step_host`: int32 [B] numpy actions in,
+    numpy (board [B, rows, pitch] padded, reward, has_reward, discount, done)
+    views of pinned host buffers out; synchronises."""
+    torch = _torch()
+    if self._host is None:
+      pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()
+      self._host = dict(
+          actions=pin((self.batch,), torch.int32),
+          board=pin((self.batch, self.rows, self.pitch), torch.uint8),
+          reward=pin((self.batch,), torch.int32), has_reward=pin((self.batch,), torch.uint8),
+          discount=pin((self.batch,), torch.float32), done=pin((self.batch,), torch.uint8))
+      self._host_np = {k: v.numpy() for k, v in self._host.items()}
+    h = self._host
+    self._host_np['actions'][:] = actions
+    _lib.check(self._lib.pcl_step_host(
+        self._h, h['actions'].data_ptr(), self._actions.data_ptr(), C.byref(self._out),
+        h['board'].data_ptr() if want_board else None, h['reward'].data_ptr(),
+        h['has_reward'].data_ptr(), h['discount'].data_ptr(), h['done'].data_ptr(),
+        self._stream()), 'pcl_step_host')
+    n = self._host_np
+    return (n['board'][:, :, :self.cols], n['reward'], n['has_reward'], n['discount'],
+            n['done'])
+
+  # ------------------------------------------------------------- accessors
+  def curtain(self, char):
+    """Drape.curtain of every env as bool [B, rows, cols] (things.py:213-217)."""
+    torch = _torch()
+    d = self.drape_chars.index(char)
+    out = torch.empty((self.batch, self.rows, self.pitch), dtype=torch.uint8,
+                      device=self.device)
+    if self.game.program == _lib.PROG_WAREHOUSE:
+      # JudgeDrape curtain = cells of boxes currently drawn as 'X'.
+      out.zero_()
+      nb = len(self.sprite_chars) - 1
+      rec = self.sprites[:, :nb]
+      on = rec[:, :, _lib.S_AUX0] != 0
+      b, s = torch.nonzero(on, as_tuple=True)
+      out[b, rec[b, s, _lib.S_ROW].long(), rec[b, s, _lib.S_COL].long()] = 1
+    else:
+      _lib.check(self._lib.pcl_export_curtain(self._h, d, out.data_ptr(), self._stream()),
+                 'pcl_export_curtain')
+    return out[:, :, :self.cols].bool()
+
+  def error_codes(self):
+    torch = _torch()
+    out = torch.empty((self.batch,), dtype=torch.int32, device=self.device)
+    _lib.check(self._lib.pcl_error_codes(self._h, out.data_ptr(), self._stream()),
+               'pcl_error_codes')
+    return out
+
+  def launch_count(self):
+    n = C.c_int64()
+    _lib.check(self._lib.pcl_launch_count(self._h, C.byref(n)), 'pcl_launch_count')
+    return n.value
+
+  def crop(self, crop_spec):
+    """ScrollingCropper.crop over the last boards: u8 [B, rows, cols]."""
+    torch = _torch()
+    shape = (self.batch, crop_spec.rows, crop_spec.cols)
+    if self._crop_out is None or tuple(self._crop_out.shape) != shape:
+      self._crop_out = torch.empty(shape, dtype=torch.uint8, device=self.device)
+    _lib.check(self._lib.pcl_crop(self._h, C.byref(crop_spec), self._board.data_ptr(),
+                                  self._crop_out.data_ptr(), self._stream()), 'pcl_crop')
+    return self._crop_out
+
+  def sprite_state(self):
+    """i32 [B, S, 8] device tensor of sprite records (PCL_S_* words)."""
+    return self.sprites
+
+  def frames(self):
+    return self.plot[:, _lib.P_FRAME]
+
+  def close(self):
+    if getattr(self, '_h', None) is not None and self._h.value:
+      self._lib.pcl_destroy(self._h)
+      self._h = C.c_void_p()
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass
+
+
+def scrolling_crop_spec(rows, cols, sprite_index, pad_char=None, scroll_margins=(2, 3),
+                        initial_offset=None, saccade=True):
+  """Resolve ScrollingCropper constructor arguments (cropping.py:313-392)."""
+  if ((scroll_margins[0] is None and rows % 2 == 0) or
+      (scroll_margins[1] is None and cols % 2 == 0)):
+    raise ValueError("A ScrollingCropper can't perform perfectly-egocentric scrolling "
+                     'with a window that has an even number of rows or columns. Either '
+                     'specify looser scroll margins or use a window with odd dimensions.')
+  m0 = rows // 2 if scroll_margins[0] is None else scroll_margins[0]
+  m1 = cols // 2 if scroll_margins[1] is None else scroll_margins[1]
+  if 2 * m0 >= rows or 2 * m1 >= cols:
+    raise ValueError("A ScrollingCropper can't use scroll margins which extend to or "
+                     'beyond the very centre of the scrolling window.')
+  off = initial_offset if initial_offset is not None else (0, 0)
+  return _lib.CropSpec(rows, cols, sprite_index, -1 if pad_char is None else ord(pad_char),
+                       m0, m1, off[0], off[1], 1 if saccade else 0)

@@ -1,0 +1,368 @@
+// api.cu — the extern "C" boundary declared in include/pcl.h.
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include <new>
+
+#include "pcl_device.cuh"
+#include "pcl_kernels.cuh"
+
+struct pcl_handle {
+  pcl_spec spec;
+  int batch;
+  int device;
+  int bound;
+  int actions_per_env;
+  pcl_state st;
+  long long launches;
+};
+
+namespace {
+
+using pcl::StepParams;
+
+#define PCL_CUDA(call)                                   \
+  do {                                                   \
+    cudaError_t e_ = (call);                             \
+    if (e_ != cudaSuccess) { return PCL_ERR_CUDA; }      \
+  } while (0)
+
+bool chars_are(const uint8_t* got, int n, const char* want) {
+  if ((int)strlen(want) != n) return false;
+  for (int i = 0; i < n; ++i) if (got[i] != (uint8_t)want[i]) return false;
+  return true;
+}
+
+// The set `want` as a 128-bit ASCII mask equals `got`?
+bool set_is(const uint32_t (&got)[4], const char* want) {
+  uint32_t m[4] = {0, 0, 0, 0};
+  for (const char* c = want; *c; ++c) m[(*c >> 5) & 3] |= 1u << (*c & 31);
+  return m[0] == got[0] && m[1] == got[1] && m[2] == got[2] && m[3] == got[3];
+}
+
+int groups_are(const pcl_spec& s, const char* flat, const int* lens, int n) {
+  if (s.n_groups != n) return 0;
+  int k = 0;
+  for (int g = 0; g < n; ++g) {
+    if (s.group_len[g] != lens[g]) return 0;
+    for (int i = 0; i < lens[g]; ++i, ++k)
+      if (s.group_chars[k] != (uint8_t)flat[k]) return 0;
+  }
+  return 1;
+}
+
+// Each program is lowered for one entity layout; anything else is a valid
+// pycolab game that this build does not accelerate.
+int validate(const pcl_spec& s) {
+  if (s.abi_version != PCL_ABI_VERSION) return PCL_ERR_INVALID;
+  if (s.rows <= 0 || s.cols <= 0 || s.pitch < s.cols || (s.pitch & 15)) return PCL_ERR_INVALID;
+  if (s.n_sprites < 0 || s.n_sprites > PCL_MAX_SPRITES) return PCL_ERR_INVALID;
+  if (s.n_drapes < 0 || s.n_drapes > PCL_MAX_DRAPES) return PCL_ERR_INVALID;
+  switch (s.program) {
+    case PCL_PROG_NONE:
+      return PCL_OK;
+    case PCL_PROG_SCROLLY_MAZE: {
+      if (!chars_are(s.sprite_char, s.n_sprites, "Pabc")) return PCL_ERR_UNSUPPORTED;
+      if (!chars_are(s.drape_char, s.n_drapes, "#@")) return PCL_ERR_UNSUPPORTED;
+      if (!chars_are(s.z_order, 6, "abc@#P")) return PCL_ERR_UNSUPPORTED;
+      const int lens[3] = {1, 4, 1};
+      if (!groups_are(s, "#abcP@", lens, 3)) return PCL_ERR_UNSUPPORTED;
+      for (int i = 0; i < 4; ++i) {
+        if (!set_is(s.impassable[i], "#")) return PCL_ERR_UNSUPPORTED;
+        if (s.sprite_confined[i]) return PCL_ERR_UNSUPPORTED;
+        if (s.sprite_egocentric[i] != (i == 0)) return PCL_ERR_UNSUPPORTED;
+      }
+      if (s.pattern_rows < s.rows || s.pattern_cols < s.cols) return PCL_ERR_INVALID;
+      if (s.pattern_words < (s.pattern_cols + 31) / 32 + 1) return PCL_ERR_INVALID;
+      for (int d = 0; d < 2; ++d) {
+        const int mr = s.margins[d][0], mc = s.margins[d][1];
+        if (mr >= 0 && (mc - 1 >= s.cols - mc || mr - 1 >= s.rows - mr)) return PCL_ERR_INVALID;
+      }
+      return PCL_OK;
+    }
+    case PCL_PROG_WAREHOUSE: {
+      const int nb = s.n_sprites - 1;
+      if (nb < 1 || nb > 10) return PCL_ERR_UNSUPPORTED;
+      if (s.sprite_char[nb] != 'P') return PCL_ERR_UNSUPPORTED;
+      if (!chars_are(s.drape_char, s.n_drapes, "X")) return PCL_ERR_UNSUPPORTED;
+      const char* order = "1234567890";
+      int k = 0;
+      for (int i = 0; i < nb; ++i) {
+        while (order[k] && order[k] != (char)s.sprite_char[i]) ++k;
+        if (!order[k]) return PCL_ERR_UNSUPPORTED;
+        ++k;
+        if (s.z_order[i] != s.sprite_char[i]) return PCL_ERR_UNSUPPORTED;
+        if (s.sprite_confined[i] || s.sprite_egocentric[i]) return PCL_ERR_UNSUPPORTED;
+      }
+      if (s.z_order[nb] != 'X' || s.z_order[nb + 1] != 'P') return PCL_ERR_UNSUPPORTED;
+      if (s.n_groups != 3 || s.group_len[0] != nb || s.group_len[1] != 1 || s.group_len[2] != 1)
+        return PCL_ERR_UNSUPPORTED;
+      for (int i = 0; i < nb; ++i)
+        if (s.group_chars[i] != s.sprite_char[i]) return PCL_ERR_UNSUPPORTED;
+      if (s.group_chars[nb] != 'X' || s.group_chars[nb + 1] != 'P') return PCL_ERR_UNSUPPORTED;
+      return PCL_OK;
+    }
+    case PCL_PROG_MARAUDERS: {
+      if (!chars_are(s.sprite_char, s.n_sprites, "Pabcdyz")) return PCL_ERR_UNSUPPORTED;
+      if (!chars_are(s.drape_char, s.n_drapes, "BX")) return PCL_ERR_UNSUPPORTED;
+      if (!chars_are(s.z_order, 9, "PBXabcdyz")) return PCL_ERR_UNSUPPORTED;
+      const int lens[1] = {9};
+      if (!groups_are(s, "PBXabcdyz", lens, 1)) return PCL_ERR_UNSUPPORTED;
+      if (s.rows > 32 || s.rows < 11 || s.cols > 64 || s.bits_words < 2)
+        return PCL_ERR_UNSUPPORTED;
+      for (int i = 0; i < 7; ++i) {
+        if (!set_is(s.impassable[i], "")) return PCL_ERR_UNSUPPORTED;
+        if (s.sprite_confined[i] != (i == 0) || s.sprite_egocentric[i]) return PCL_ERR_UNSUPPORTED;
+      }
+      return PCL_OK;
+    }
+    default:
+      return PCL_ERR_UNSUPPORTED;
+  }
+}
+
+void fill_params(const pcl_handle* h, StepParams* p) {
+  const pcl_spec& s = h->spec;
+  memset(p, 0, sizeof(*p));
+  p->B = h->batch; p->H = s.rows; p->W = s.cols; p->pitch = s.pitch;
+  p->PH = s.pattern_rows; p->PW = s.pattern_cols; p->PWW = s.pattern_words;
+  p->BW = s.bits_words;
+  p->S = s.n_sprites; p->D = s.n_drapes;
+  p->auto_reset = s.auto_reset;
+  p->actions_per_env = h->actions_per_env;
+  memcpy(p->margin, s.margins, sizeof(p->margin));
+  memcpy(p->sprite_char, s.sprite_char, sizeof(p->sprite_char));
+  memcpy(p->drape_char, s.drape_char, sizeof(p->drape_char));
+  memcpy(p->impassable, s.impassable, sizeof(p->impassable));
+  memcpy(p->confined, s.sprite_confined, sizeof(p->confined));
+  memcpy(p->egocentric, s.sprite_egocentric, sizeof(p->egocentric));
+  p->st = h->st;
+}
+
+int launch(pcl_handle* h, const StepParams& p, cudaStream_t stream) {
+  cudaError_t e;
+  switch (h->spec.program) {
+    case PCL_PROG_SCROLLY_MAZE: e = pcl::launch_scrolly_maze(p, stream); break;
+    case PCL_PROG_WAREHOUSE: e = pcl::launch_warehouse(p, stream); break;
+    case PCL_PROG_MARAUDERS: e = pcl::launch_marauders(p, stream); break;
+    default: return PCL_ERR_UNSUPPORTED;
+  }
+  h->launches += 1;
+  return e == cudaSuccess ? PCL_OK : PCL_ERR_CUDA;
+}
+
+int check_ready(const pcl_handle* h, const pcl_outputs* out) {
+  if (!h || !out) return PCL_ERR_INVALID;
+  if (!h->bound) return PCL_ERR_UNBOUND;
+  if (!out->d_board || !out->d_reward || !out->d_has_reward || !out->d_discount || !out->d_done)
+    return PCL_ERR_INVALID;
+  return PCL_OK;
+}
+
+__global__ void gather_errors(const int32_t* plot, int32_t* out, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) out[i] = plot[(int64_t)i * PCL_PLOT_WORDS + PCL_P_ERROR];
+}
+
+}  // namespace
+
+extern "C" {
+
+int pcl_abi_version(void) { return PCL_ABI_VERSION; }
+
+const char* pcl_status_string(int status) {
+  switch (status) {
+    case PCL_OK: return "ok";
+    case PCL_ERR_INVALID: return "invalid argument or malformed spec";
+    case PCL_ERR_UNSUPPORTED: return "game not lowered to a device program";
+    case PCL_ERR_CUDA: return "CUDA runtime error";
+    case PCL_ERR_UNBOUND: return "pcl_bind_state has not been called";
+    case PCL_ERR_NOMEM: return "out of memory";
+    default: return "unknown status";
+  }
+}
+
+int pcl_create(const pcl_spec* spec, int batch, int device, pcl_handle** out) {
+  if (!spec || !out || batch <= 0) return PCL_ERR_INVALID;
+  const int v = validate(*spec);
+  if (v != PCL_OK) return v;
+  if (device >= 0) PCL_CUDA(cudaSetDevice(device));
+  pcl_handle* h = new (std::nothrow) pcl_handle();
+  if (!h) return PCL_ERR_NOMEM;
+  h->spec = *spec;
+  h->batch = batch;
+  h->device = device;
+  h->bound = 0;
+  h->actions_per_env = 1;
+  h->launches = 0;
+  *out = h;
+  return PCL_OK;
+}
+
+int pcl_destroy(pcl_handle* h) {
+  delete h;
+  return PCL_OK;
+}
+
+int pcl_bind_state(pcl_handle* h, const pcl_state* st) {
+  if (!h || !st) return PCL_ERR_INVALID;
+  if (!st->d_backdrop || !st->d_sprites || !st->d_sprites_init || !st->d_plot || !st->d_plot_init)
+    return PCL_ERR_INVALID;
+  if (h->spec.n_drapes > 0 && (!st->d_drapes || !st->d_drapes_init)) return PCL_ERR_INVALID;
+  if (h->spec.program == PCL_PROG_SCROLLY_MAZE) {
+    for (int d = 0; d < 2; ++d) if (!st->d_pattern[d]) return PCL_ERR_INVALID;
+    if (!st->d_pattern_init[1] || st->pattern_bstride[1] == 0) return PCL_ERR_INVALID;
+  }
+  if (h->spec.program == PCL_PROG_MARAUDERS) {
+    for (int d = 0; d < 2; ++d)
+      if (!st->d_bits[d] || !st->d_bits_init[d] || st->bits_bstride[d] == 0) return PCL_ERR_INVALID;
+    if (!st->d_rng) return PCL_ERR_INVALID;
+  }
+  h->st = *st;
+  h->bound = 1;
+  return PCL_OK;
+}
+
+int pcl_reset(pcl_handle* h, const uint8_t* d_env_mask, const pcl_outputs* out, void* stream) {
+  const int r = check_ready(h, out);
+  if (r != PCL_OK) return r;
+  StepParams p;
+  fill_params(h, &p);
+  p.mode = pcl::MODE_RESET;
+  p.env_mask = d_env_mask;
+  p.out = *out;
+  return launch(h, p, (cudaStream_t)stream);
+}
+
+int pcl_step(pcl_handle* h, const int32_t* d_actions, const pcl_outputs* out, void* stream) {
+  const int r = check_ready(h, out);
+  if (r != PCL_OK) return r;
+  if (!d_actions) return PCL_ERR_INVALID;
+  StepParams p;
+  fill_params(h, &p);
+  p.mode = pcl::MODE_STEP;
+  p.actions = d_actions;
+  p.out = *out;
+  return launch(h, p, (cudaStream_t)stream);
+}
+
+int pcl_run(pcl_handle* h, const int32_t* d_actions, int steps, const pcl_outputs* out,
+            void* stream) {
+  const int r = check_ready(h, out);
+  if (r != PCL_OK) return r;
+  if (!d_actions || steps < 0) return PCL_ERR_INVALID;
+  StepParams p;
+  fill_params(h, &p);
+  p.mode = pcl::MODE_STEP;
+  p.out = *out;
+  for (int t = 0; t < steps; ++t) {
+    p.actions = d_actions + (int64_t)t * h->batch * h->actions_per_env;
+    const int e = launch(h, p, (cudaStream_t)stream);
+    if (e != PCL_OK) return e;
+  }
+  return PCL_OK;
+}
+
+int pcl_step_host(pcl_handle* h, const int32_t* h_actions, int32_t* d_actions,
+                  const pcl_outputs* out, uint8_t* h_board, int32_t* h_reward,
+                  uint8_t* h_has_reward, float* h_discount, uint8_t* h_done, void* stream) {
+  const int r = check_ready(h, out);
+  if (r != PCL_OK) return r;
+  if (!h_actions || !d_actions) return PCL_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t B = (size_t)h->batch;
+  PCL_CUDA(cudaMemcpyAsync(d_actions, h_actions, B * h->actions_per_env * sizeof(int32_t),
+                           cudaMemcpyHostToDevice, s));
+  const int e = pcl_step(h, d_actions, out, stream);
+  if (e != PCL_OK) return e;
+  const size_t plane = (size_t)h->spec.rows * h->spec.pitch;
+  if (h_board) PCL_CUDA(cudaMemcpyAsync(h_board, out->d_board, B * plane, cudaMemcpyDeviceToHost, s));
+  if (h_reward) PCL_CUDA(cudaMemcpyAsync(h_reward, out->d_reward, B * 4, cudaMemcpyDeviceToHost, s));
+  if (h_has_reward)
+    PCL_CUDA(cudaMemcpyAsync(h_has_reward, out->d_has_reward, B, cudaMemcpyDeviceToHost, s));
+  if (h_discount)
+    PCL_CUDA(cudaMemcpyAsync(h_discount, out->d_discount, B * 4, cudaMemcpyDeviceToHost, s));
+  if (h_done) PCL_CUDA(cudaMemcpyAsync(h_done, out->d_done, B, cudaMemcpyDeviceToHost, s));
+  PCL_CUDA(cudaStreamSynchronize(s));
+  return PCL_OK;
+}
+
+int pcl_render(pcl_handle* h, const uint8_t* d_backdrop, int64_t backdrop_bstride,
+               const uint8_t* d_curtains, const int32_t* d_sprites, const uint8_t* d_z_order,
+               uint8_t* d_board, void* stream) {
+  if (!h || !d_backdrop || !d_z_order || !d_board) return PCL_ERR_INVALID;
+  if (h->spec.n_drapes > 0 && !d_curtains) return PCL_ERR_INVALID;
+  if (h->spec.n_sprites > 0 && !d_sprites) return PCL_ERR_INVALID;
+  pcl::RenderParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = h->batch; p.H = h->spec.rows; p.W = h->spec.cols; p.pitch = h->spec.pitch;
+  p.S = h->spec.n_sprites; p.D = h->spec.n_drapes;
+  p.backdrop = d_backdrop; p.backdrop_bstride = backdrop_bstride;
+  p.curtains = d_curtains; p.sprites = d_sprites; p.z_order = d_z_order; p.board = d_board;
+  memcpy(p.sprite_char, h->spec.sprite_char, sizeof(p.sprite_char));
+  memcpy(p.drape_char, h->spec.drape_char, sizeof(p.drape_char));
+  h->launches += 1;
+  return pcl::launch_render(p, (cudaStream_t)stream) == cudaSuccess ? PCL_OK : PCL_ERR_CUDA;
+}
+
+int pcl_export_curtain(pcl_handle* h, int drape_index, uint8_t* d_out, void* stream) {
+  if (!h || !d_out || drape_index < 0 || drape_index >= h->spec.n_drapes) return PCL_ERR_INVALID;
+  if (!h->bound) return PCL_ERR_UNBOUND;
+  pcl::ExportParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = h->batch; p.H = h->spec.rows; p.W = h->spec.cols; p.pitch = h->spec.pitch;
+  p.PWW = h->spec.pattern_words; p.BW = h->spec.bits_words;
+  p.drape = drape_index; p.D = h->spec.n_drapes; p.drapes = h->st.d_drapes;
+  p.out = d_out; p.stale_slot = -1;
+  if (h->spec.program == PCL_PROG_SCROLLY_MAZE) {
+    p.scrolly = 1;
+    p.bits = h->st.d_pattern[drape_index];
+    p.bits_bstride = h->st.pattern_bstride[drape_index];
+    if (drape_index == 1) p.stale_slot = 0;
+  } else if (h->spec.program == PCL_PROG_MARAUDERS) {
+    p.scrolly = 0;
+    p.bits = h->st.d_bits[drape_index];
+    p.bits_bstride = h->st.bits_bstride[drape_index];
+  } else {
+    return PCL_ERR_UNSUPPORTED;
+  }
+  h->launches += 1;
+  return pcl::launch_export_curtain(p, (cudaStream_t)stream) == cudaSuccess ? PCL_OK : PCL_ERR_CUDA;
+}
+
+int pcl_crop(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d_board, uint8_t* d_crop,
+             void* stream) {
+  if (!h || !crop || !d_board || !d_crop) return PCL_ERR_INVALID;
+  if (!h->bound) return PCL_ERR_UNBOUND;
+  if (crop->rows <= 0 || crop->cols <= 0 || crop->sprite_index >= h->spec.n_sprites)
+    return PCL_ERR_INVALID;
+  if (crop->sprite_index >= 0 &&
+      (2 * crop->margin_rows >= crop->rows || 2 * crop->margin_cols >= crop->cols))
+    return PCL_ERR_INVALID;                                  // cropping.py:374-380
+  if (crop->pad_char < 0 && (crop->rows > h->spec.rows || crop->cols > h->spec.cols))
+    return PCL_ERR_INVALID;                                  // cropping.py:384-391
+  pcl::CropParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = h->batch; p.H = h->spec.rows; p.W = h->spec.cols; p.pitch = h->spec.pitch;
+  p.S = h->spec.n_sprites; p.crop = *crop;
+  p.sprites = h->st.d_sprites; p.plot = h->st.d_plot; p.board = d_board; p.out = d_crop;
+  h->launches += 1;
+  return pcl::launch_crop(p, (cudaStream_t)stream) == cudaSuccess ? PCL_OK : PCL_ERR_CUDA;
+}
+
+int pcl_error_codes(pcl_handle* h, int32_t* d_out, void* stream) {
+  if (!h || !d_out) return PCL_ERR_INVALID;
+  if (!h->bound) return PCL_ERR_UNBOUND;
+  gather_errors<<<(h->batch + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->st.d_plot, d_out,
+                                                                           h->batch);
+  h->launches += 1;
+  return cudaGetLastError() == cudaSuccess ? PCL_OK : PCL_ERR_CUDA;
+}
+
+int pcl_launch_count(pcl_handle* h, int64_t* out) {
+  if (!h || !out) return PCL_ERR_INVALID;
+  *out = h->launches;
+  return PCL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,296 @@
+// marauders.cu — fused step kernel for examples/extraterrestrial_marauders.py.
+//
+// Single update group ['P','B','X','a','b','c','d','y','z'] which is also the
+// z-order (extraterrestrial_marauders.py:91-101), so every entity reads the
+// PREVIOUS step's board (engine.py:729-735).  Sprite order P,a,b,c,d,y,z
+// (0..6); drapes 'B' (0) and 'X' (1) whose curtains are the primary state:
+// bit-packed rows, row r lives in lane r's registers (rows <= 32, cols <= 64).
+//
+// Registers: X drape aux0 = _dx (:140); plot aux0 / aux1 = 'last_player_shot'
+// / 'last_marauder_shot' frames (:214-215, :248-249).  The per-env MT19937
+// stream reproduces numpy.random.choice (:253): legacy RandomState draws an
+// index by masked rejection over tempered 32-bit outputs.
+#include "pcl_device.cuh"
+#include "pcl_kernels.cuh"
+
+namespace pcl {
+
+namespace {
+
+constexpr int kS = 7;
+constexpr int kWarpsPerBlock = 4;
+typedef unsigned long long u64;
+
+// ---- MT19937 (NumPy legacy RandomState core), warp-cooperative ------------
+__device__ __forceinline__ void mt_twist(uint32_t* mt, int lane) {
+  for (int base = 0; base < 624; base += 32) {
+    const int j = base + lane;
+    uint32_t v = 0;
+    if (j < 624) {
+      const int j1 = (j + 1 == 624) ? 0 : j + 1;
+      const int jm = (j + 397 >= 624) ? j + 397 - 624 : j + 397;
+      const uint32_t y = (mt[j] & 0x80000000u) | (mt[j1] & 0x7fffffffu);
+      v = mt[jm] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    __syncwarp();
+    if (j < 624) mt[j] = v;
+    __syncwarp();
+  }
+}
+__device__ __forceinline__ uint32_t mt_next(uint32_t* mt, int lane) {
+  int pos = (int)mt[624];
+  if (pos >= 624) { mt_twist(mt, lane); pos = 0; }
+  uint32_t y = mt[pos];
+  __syncwarp();
+  if (lane == 0) mt[624] = (uint32_t)(pos + 1);
+  __syncwarp();
+  y ^= (y >> 11);
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= (y >> 18);
+  return y;
+}
+// RandomState.randint(0, n) for 1 <= n <= 2^32: masked rejection; no draw when
+// n == 1.
+__device__ __forceinline__ uint32_t mt_below(uint32_t* mt, uint32_t n, int lane) {
+  const uint32_t rng = n - 1;
+  if (rng == 0) return 0;
+  uint32_t mask = rng;
+  mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+  uint32_t v;
+  do { v = mt_next(mt, lane) & mask; } while (v > rng);
+  return v;
+}
+
+__device__ __forceinline__ bool same_cell(const Sprite& a, const Sprite& b) {
+  return a.row == b.row && a.col == b.col;
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+marauders_step(const StepParams p) {
+  const int lane = threadIdx.x & 31;
+  const int env = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (env >= p.B) return;
+  const int H = p.H, W = p.W;
+
+  int32_t* g_sprites = p.st.d_sprites + (int64_t)env * kS * PCL_SPRITE_WORDS;
+  int32_t* g_drapes = p.st.d_drapes + (int64_t)env * 2 * PCL_DRAPE_WORDS;
+  int32_t* g_plot = p.st.d_plot + (int64_t)env * PCL_PLOT_WORDS;
+  uint32_t* g_bunk = p.st.d_bits[0] + (int64_t)env * p.st.bits_bstride[0];
+  uint32_t* g_mara = p.st.d_bits[1] + (int64_t)env * p.st.bits_bstride[1];
+  uint32_t* mt = p.st.d_rng + (int64_t)env * PCL_MT_WORDS;
+
+  Plot plot = load_record_rw<Plot>(g_plot);
+  bool restart;
+  if (p.mode == MODE_RESET) {
+    restart = (p.env_mask == nullptr) || (p.env_mask[env] != 0);
+    if (!restart) return;
+  } else {
+    restart = plot.game_over && p.auto_reset;
+    if (plot.game_over && !p.auto_reset) return;
+  }
+
+  Sprite sp[kS];
+  Drape bunkers, marauders;
+  u64 brow = 0, xrow = 0;          // lane r holds row r of the B / X curtain
+  int action;
+  const int BW = p.BW;
+  auto load_row = [&](const uint32_t* base) -> u64 {
+    if (lane >= H) return 0;
+    const uint32_t* row = base + lane * BW;
+    return (u64)row[0] | ((u64)row[1] << 32);
+  };
+  if (restart) {
+    const int episodes = plot.episodes, error = plot.error;
+    plot = load_record<Plot>(p.st.d_plot_init + (int64_t)env * p.st.plot_init_bstride);
+    plot.episodes = episodes + 1;
+    plot.error = error;
+    const int32_t* si = p.st.d_sprites_init + (int64_t)env * p.st.sprites_init_bstride;
+#pragma unroll
+    for (int i = 0; i < kS; ++i) sp[i] = load_record<Sprite>(si + i * PCL_SPRITE_WORDS);
+    const int32_t* di = p.st.d_drapes_init + (int64_t)env * p.st.drapes_init_bstride;
+    bunkers = load_record<Drape>(di);
+    marauders = load_record<Drape>(di + PCL_DRAPE_WORDS);
+    brow = load_row(p.st.d_bits_init[0] + (int64_t)env * p.st.bits_init_bstride[0]);
+    xrow = load_row(p.st.d_bits_init[1] + (int64_t)env * p.st.bits_init_bstride[1]);
+    action = PCL_ACTION_NONE;
+  } else {
+#pragma unroll
+    for (int i = 0; i < kS; ++i) sp[i] = load_record_rw<Sprite>(g_sprites + i * PCL_SPRITE_WORDS);
+    bunkers = load_record_rw<Drape>(g_drapes);
+    marauders = load_record_rw<Drape>(g_drapes + PCL_DRAPE_WORDS);
+    brow = load_row(g_bunk);
+    xrow = load_row(g_mara);
+    action = p.actions[(int64_t)env * p.actions_per_env];
+  }
+  Directives dir = fresh_directives();
+  plot.frame += 1;
+
+  // ---- the stale board, as far as anybody looks at it --------------------
+  // top[i]: bolt i is the visible character of its cell (layers[c] = board==c,
+  // rendering.py:177); a later bolt in z-order hides an earlier one.
+  bool top[kS];
+#pragma unroll
+  for (int i = 1; i < kS; ++i) {
+    top[i] = visible(sp[i]);
+#pragma unroll
+    for (int j = i + 1; j < kS; ++j)
+      if (visible(sp[j]) && same_cell(sp[i], sp[j])) top[i] = false;
+  }
+  // layers['X'] of the stale board: marauders not hidden under a bolt.
+  u64 seen = xrow;
+#pragma unroll
+  for (int i = 1; i < kS; ++i)
+    if (visible(sp[i]) && sp[i].row == lane) seen &= ~(1ull << sp[i].col);
+  // Old bolt cells (bolts only move in their own update, after B and X).
+  auto never_blocked = [](int, int) { return false; };
+
+  // ---- P (PlayerSprite.update :178-186)
+  if (action == 0) walker_move(sp[0], 0, PCL_M_W, plot, H, W, true, false, lane, never_blocked);
+  else if (action == 1) walker_move(sp[0], 0, PCL_M_E, plot, H, W, true, false, lane, never_blocked);
+  else if (action == 4) terminate(dir);
+
+  // ---- B (BunkerDrape.update :113-120)
+  int bunker_hitters = 0, nb = 0;
+#pragma unroll
+  for (int i = 1; i < kS; ++i) {
+    const bool mine = top[i] && sp[i].row == lane && ((brow >> sp[i].col) & 1ull);
+    const bool hit = __any_sync(PCL_FULL, mine);
+    if (mine) brow &= ~(1ull << sp[i].col);
+    if (hit) { bunker_hitters |= 1 << i; nb += 1; }
+  }
+  add_reward(dir, -nb);
+
+  // ---- X (MarauderDrape.update :142-163)
+  int marauder_hitters = 0, nx = 0;
+#pragma unroll
+  for (int i = 1; i <= 4; ++i) {
+    const bool mine = top[i] && sp[i].row == lane && ((xrow >> sp[i].col) & 1ull);
+    const bool hit = __any_sync(PCL_FULL, mine);
+    if (mine) xrow &= ~(1ull << sp[i].col);
+    if (hit) { marauder_hitters |= 1 << i; nx += 1; }
+  }
+  add_reward(dir, nx * 10);
+  {
+    const bool none_left = !__any_sync(PCL_FULL, xrow != 0);
+    const u64 row10 = __shfl_sync(PCL_FULL, xrow, 10);
+    if (none_left || (H > 10 && row10 != 0)) {
+      terminate(dir);
+    } else {
+      int count = __popcll(xrow);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(PCL_FULL, count, o);
+      // frame % max(1, count // 8.0000001): the float floor-division equals
+      // (count - 1) / 8 for every 1 <= count <= 2^20.
+      const int period = max(1, (count - 1) / 8);
+      if (plot.frame % period == 0) {
+        const u64 edge = (1ull) | (1ull << (W - 1));
+        if (__any_sync(PCL_FULL, (xrow & edge) != 0)) {
+          marauders.aux0 = -marauders.aux0;
+          const u64 up = __shfl_sync(PCL_FULL, xrow, (lane + H - 1) % H);   // np.roll(+1, axis 0)
+          xrow = lane < H ? up : 0;
+        }
+        const u64 full = (W == 64) ? ~0ull : ((1ull << W) - 1ull);
+        if (marauders.aux0 > 0) xrow = ((xrow << 1) | (xrow >> (W - 1))) & full;
+        else xrow = ((xrow >> 1) | ((xrow & 1ull) << (W - 1))) & full;
+      }
+    }
+  }
+
+  // ---- upward bolts a..d (UpwardLaserBoltSprite :198-220)
+#pragma unroll
+  for (int i = 1; i <= 4; ++i) {
+    if (visible(sp[i])) {
+      if (((bunker_hitters | marauder_hitters) >> i) & 1) walker_teleport(sp[i], H, W, -1, -1);
+      else walker_move(sp[i], i, PCL_M_N, plot, H, W, false, false, lane, never_blocked);
+    } else if (action == 2) {
+      if (plot.aux0 != plot.frame) {
+        plot.aux0 = plot.frame;
+        walker_teleport(sp[i], H, W, sp[0].row - 1, sp[0].col);
+      }
+    }
+  }
+  // ---- downward bolts y, z (DownwardLaserBoltSprite :232-256)
+#pragma unroll
+  for (int i = 5; i < kS; ++i) {
+    if (visible(sp[i])) {
+      if ((bunker_hitters >> i) & 1) {
+        walker_teleport(sp[i], H, W, -1, -1);
+      } else {
+        if (same_cell(sp[i], sp[0])) terminate(dir);
+        walker_move(sp[i], i, PCL_M_S, plot, H, W, false, false, lane, never_blocked);
+      }
+    } else if (plot.aux1 != plot.frame) {
+      plot.aux1 = plot.frame;
+      // cols = nonzero(layers['X'].sum(axis=0)); col = choice(cols)
+      u64 colmask = seen;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) colmask |= __shfl_xor_sync(PCL_FULL, colmask, o);
+      const int n = __popcll(colmask);
+      if (n == 0) {
+        plot.error |= PCL_ENV_ERR_EMPTY_CHOICE;   // the reference raises ValueError here
+      } else {
+        int k = (int)mt_below(mt, (uint32_t)n, lane);
+        u64 m = colmask;
+        for (int t = 0; t < k; ++t) m &= m - 1;   // drop the k lowest set bits
+        const int col = __ffsll((long long)m) - 1;
+        const unsigned rows_with = __ballot_sync(PCL_FULL, (seen >> col) & 1ull);
+        const int row = (31 - __clz((int)rows_with)) + 1;
+        walker_teleport(sp[i], H, W, row, col);
+      }
+    }
+  }
+
+  // ---- _apply_and_clear_plot + state write-back
+  plot.game_over = dir.game_over;
+  if (lane < H) {
+    uint32_t* rb = g_bunk + lane * BW;
+    uint32_t* rx = g_mara + lane * BW;
+    rb[0] = (uint32_t)brow; rb[1] = (uint32_t)(brow >> 32);
+    rx[0] = (uint32_t)xrow; rx[1] = (uint32_t)(xrow >> 32);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kS; ++i) store_record(g_sprites + i * PCL_SPRITE_WORDS, sp[i]);
+    store_record(g_drapes, bunkers);
+    store_record(g_drapes + PCL_DRAPE_WORDS, marauders);
+    store_record(g_plot, plot);
+    p.out.d_reward[env] = dir.reward;
+    p.out.d_has_reward[env] = (uint8_t)dir.has_reward;
+    p.out.d_discount[env] = dir.discount;
+    p.out.d_done[env] = (uint8_t)dir.game_over;
+  }
+
+  // ---- final render, z-order P B X a b c d y z
+  const uint8_t* backdrop = p.st.d_backdrop + (int64_t)env * p.st.backdrop_bstride;
+  uint8_t* board = p.out.d_board + (int64_t)env * H * p.pitch;
+  const int segs_per_row = p.pitch >> 4;
+  const int total = H * segs_per_row;
+  for (int base = 0; base < total; base += 32) {
+    const int seg = base + lane;
+    const bool active = seg < total;
+    const int r = active ? seg / segs_per_row : 0;
+    const int c0 = active ? (seg - r * segs_per_row) << 4 : 0;
+    const u64 b = __shfl_sync(PCL_FULL, brow, r);
+    const u64 x = __shfl_sync(PCL_FULL, xrow, r);
+    if (active) {
+      uint4 px = __ldg(reinterpret_cast<const uint4*>(backdrop + (int64_t)r * p.pitch + c0));
+      paint_bits(px, sprite_bit(sp[0], r, c0), p.sprite_char[0]);
+      paint_bits(px, (unsigned)(b >> c0) & 0xffffu, 'B');
+      paint_bits(px, (unsigned)(x >> c0) & 0xffffu, 'X');
+#pragma unroll
+      for (int i = 1; i < kS; ++i) paint_bits(px, sprite_bit(sp[i], r, c0), p.sprite_char[i]);
+      *reinterpret_cast<uint4*>(board + (int64_t)r * p.pitch + c0) = px;
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_marauders(const StepParams& p, cudaStream_t s) {
+  const int blocks = (p.B + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  marauders_step<<<blocks, kWarpsPerBlock * 32, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace pcl

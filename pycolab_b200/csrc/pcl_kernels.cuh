@@ -1,0 +1,68 @@
+// pcl_kernels.cuh — kernel parameter blocks + launch prototypes.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pcl.h"
+
+namespace pcl {
+
+// Everything a fused step kernel needs, by value (fits the 4 KB param space).
+struct StepParams {
+  int B, H, W, pitch;
+  int PH, PW, PWW;               // Scrolly pattern rows/cols/words-per-row
+  int BW;                        // words per bit-packed board-sized row
+  int S, D;
+  int auto_reset;
+  int mode;                      // MODE_STEP / MODE_RESET
+  int actions_per_env;
+  int margin[PCL_MAX_DRAPES][2];
+  uint8_t sprite_char[PCL_MAX_SPRITES];
+  uint8_t drape_char[PCL_MAX_DRAPES];
+  uint32_t impassable[PCL_MAX_SPRITES][4];
+  int confined[PCL_MAX_SPRITES];
+  int egocentric[PCL_MAX_SPRITES];
+  pcl_state st;
+  pcl_outputs out;
+  const int32_t* actions;        // i32 [B, actions_per_env] (MODE_STEP)
+  const uint8_t* env_mask;       // u8 [B] or NULL (MODE_RESET)
+};
+
+cudaError_t launch_scrolly_maze(const StepParams& p, cudaStream_t s);
+cudaError_t launch_warehouse(const StepParams& p, cudaStream_t s);
+cudaError_t launch_marauders(const StepParams& p, cudaStream_t s);
+cudaError_t launch_fixture(const StepParams& p, cudaStream_t s);
+
+struct RenderParams {
+  int B, H, W, pitch, S, D;
+  const uint8_t* backdrop; int64_t backdrop_bstride;
+  const uint8_t* curtains;       // u8 [B, D, H, pitch]
+  const int32_t* sprites;        // i32 [B, S, 8]
+  const uint8_t* z_order;        // u8 [B, S + D] chars
+  uint8_t sprite_char[PCL_MAX_SPRITES];
+  uint8_t drape_char[PCL_MAX_DRAPES];
+  uint8_t* board;                // u8 [B, H, pitch]
+};
+cudaError_t launch_render(const RenderParams& p, cudaStream_t s);
+
+struct ExportParams {
+  int B, H, W, pitch, PWW, BW, drape, scrolly;
+  const uint32_t* bits; int64_t bits_bstride;   // pattern (scrolly) or board bits
+  const int32_t* drapes; int D;
+  int stale_slot;                // drape aux pair holding a stale cell, or -1
+  uint8_t* out;
+};
+cudaError_t launch_export_curtain(const ExportParams& p, cudaStream_t s);
+
+struct CropParams {
+  int B, H, W, pitch, S;
+  pcl_crop_spec crop;
+  const int32_t* sprites;
+  int32_t* plot;
+  const uint8_t* board;
+  uint8_t* out;
+};
+cudaError_t launch_crop(const CropParams& p, cudaStream_t s);
+
+}  // namespace pcl

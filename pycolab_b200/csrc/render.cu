@@ -1,0 +1,205 @@
+// render.cu — the stand-alone renderer, curtain export and cropper kernels.
+//
+// render_kernel is Engine._render() + BaseObservationRenderer (engine.py:737-759,
+// rendering.py:98-179) over reference-layout inputs: one byte per cell for the
+// backdrop and for every drape curtain.  It is a pure HBM streaming kernel:
+// per env it reads (1 + D) * H * pitch bytes and writes H * pitch bytes; the
+// occlusion flatten down the z-order is done per 16-byte segment with byte-SIMD
+// rank compares so that all (1 + D) loads of a segment are issued up front and
+// no register array is indexed dynamically.
+#include "pcl_device.cuh"
+#include "pcl_kernels.cuh"
+
+namespace pcl {
+
+namespace {
+
+constexpr int kRenderThreads = 128;
+
+struct RenderShared {
+  int rank_s[PCL_MAX_SPRITES];
+  int rank_d[PCL_MAX_DRAPES];
+  int row[PCL_MAX_SPRITES], col[PCL_MAX_SPRITES], vis[PCL_MAX_SPRITES];
+};
+
+// Where `take` (0x00/0xff per byte) is set, write ch4 / rank4.
+__device__ __forceinline__ void overlay(uint32_t& px, uint32_t& rk, uint32_t cover,
+                                        uint32_t ch4, uint32_t rank4) {
+  const uint32_t take = cover & __vcmpltu4(rk, rank4);
+  px = (px & ~take) | (ch4 & take);
+  rk = (rk & ~take) | (rank4 & take);
+}
+
+__global__ void __launch_bounds__(kRenderThreads)
+render_kernel(const RenderParams p) {
+  __shared__ RenderShared sh;
+  const int env = blockIdx.x;
+  const int n = p.S + p.D;
+  // Decode this env's z-order (engine.py:751: later entries paint over earlier).
+  if (threadIdx.x < n) {
+    const uint8_t ch = p.z_order[(int64_t)env * n + threadIdx.x];
+    for (int s = 0; s < p.S; ++s) if (p.sprite_char[s] == ch) sh.rank_s[s] = threadIdx.x + 1;
+    for (int d = 0; d < p.D; ++d) if (p.drape_char[d] == ch) sh.rank_d[d] = threadIdx.x + 1;
+  }
+  if (threadIdx.x < p.S) {
+    const int32_t* rec = p.sprites + ((int64_t)env * p.S + threadIdx.x) * PCL_SPRITE_WORDS;
+    sh.row[threadIdx.x] = rec[PCL_S_ROW];
+    sh.col[threadIdx.x] = rec[PCL_S_COL];
+    sh.vis[threadIdx.x] = rec[PCL_S_FLAGS] & 1;
+  }
+  __syncthreads();
+
+  const uint8_t* backdrop = p.backdrop + (int64_t)env * p.backdrop_bstride;
+  const int64_t plane = (int64_t)p.H * p.pitch;
+  const uint8_t* curtains = p.curtains + (int64_t)env * p.D * plane;
+  uint8_t* board = p.board + (int64_t)env * plane;
+  const int segs_per_row = p.pitch >> 4;
+  const int total = p.H * segs_per_row;
+
+  for (int seg = threadIdx.x; seg < total; seg += kRenderThreads) {
+    const int r = seg / segs_per_row;
+    const int c0 = (seg - r * segs_per_row) << 4;
+    const int64_t off = (int64_t)r * p.pitch + c0;
+    uint4 px = __ldg(reinterpret_cast<const uint4*>(backdrop + off));
+    uint4 cur[PCL_MAX_DRAPES];
+#pragma unroll
+    for (int d = 0; d < PCL_MAX_DRAPES; ++d)
+      if (d < p.D) cur[d] = __ldg(reinterpret_cast<const uint4*>(curtains + d * plane + off));
+    uint4 rk = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int d = 0; d < PCL_MAX_DRAPES; ++d) {
+      if (d < p.D) {
+        const uint32_t ch4 = p.drape_char[d] * 0x01010101u;
+        const uint32_t r4 = sh.rank_d[d] * 0x01010101u;
+        overlay(px.x, rk.x, __vcmpne4(cur[d].x, 0), ch4, r4);   // rendering.py:160
+        overlay(px.y, rk.y, __vcmpne4(cur[d].y, 0), ch4, r4);
+        overlay(px.z, rk.z, __vcmpne4(cur[d].z, 0), ch4, r4);
+        overlay(px.w, rk.w, __vcmpne4(cur[d].w, 0), ch4, r4);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < PCL_MAX_SPRITES; ++s) {
+      if (s < p.S) {
+        const int dc = sh.col[s] - c0;
+        if (sh.vis[s] && sh.row[s] == r && (unsigned)dc < 16u) {     // rendering.py:139
+          const uint32_t cover = 0xffu << ((dc & 3) * 8);
+          const uint32_t ch4 = p.sprite_char[s] * 0x01010101u;
+          const uint32_t r4 = sh.rank_s[s] * 0x01010101u;
+          const int w = dc >> 2;
+          if (w == 0) overlay(px.x, rk.x, cover, ch4, r4);
+          else if (w == 1) overlay(px.y, rk.y, cover, ch4, r4);
+          else if (w == 2) overlay(px.z, rk.z, cover, ch4, r4);
+          else overlay(px.w, rk.w, cover, ch4, r4);
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(board + off) = px;
+  }
+}
+
+// Drape.curtain as bytes (things.py:213-217) from the packed device state.
+__global__ void export_curtain_kernel(const ExportParams p) {
+  const int env = blockIdx.x;
+  const int segs_per_row = p.pitch >> 4;
+  const int total = p.H * segs_per_row;
+  const int32_t* drec = p.drapes + ((int64_t)env * p.D + p.drape) * PCL_DRAPE_WORDS;
+  const int cr = p.scrolly ? drec[PCL_D_CORNER_R] : 0;
+  const int cc = p.scrolly ? drec[PCL_D_CORNER_C] : 0;
+  const int stale_r = p.stale_slot >= 0 ? drec[PCL_D_AUX0] : -1;
+  const int stale_c = p.stale_slot >= 0 ? drec[PCL_D_AUX1] : -1;
+  const int rw = p.scrolly ? p.PWW : p.BW;
+  const uint32_t* bits = p.bits + (int64_t)env * p.bits_bstride;
+  uint8_t* out = p.out + (int64_t)env * p.H * p.pitch;
+  for (int seg = threadIdx.x; seg < total; seg += blockDim.x) {
+    const int r = seg / segs_per_row;
+    const int c0 = (seg - r * segs_per_row) << 4;
+    const int ncols = min(16, p.W - c0);
+    unsigned b = bits16(bits + (int64_t)(cr + r) * rw, cc + c0) & ((1u << ncols) - 1u);
+    if (r == stale_r && (unsigned)(stale_c - c0) < 16u) b |= 1u << (stale_c - c0);
+    uint4 px = make_uint4(0, 0, 0, 0);
+    paint_bits(px, b, 1);
+    *reinterpret_cast<uint4*>(out + (int64_t)r * p.pitch + c0) = px;
+  }
+}
+
+// ScrollingCropper.crop (cropping.py:393-426) for one tracked sprite.
+__global__ void __launch_bounds__(128) crop_kernel(const CropParams p) {
+  const int lane = threadIdx.x & 31;
+  const int env = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (env >= p.B) return;
+  const pcl_crop_spec& c = p.crop;
+  int32_t* plot = p.plot + (int64_t)env * PCL_PLOT_WORDS;
+  const bool fixed = c.sprite_index < 0;                  // FixedCropper :229-310
+  const int32_t* rec = p.sprites + ((int64_t)env * p.S + (fixed ? 0 : c.sprite_index)) * PCL_SPRITE_WORDS;
+  const bool have = !fixed && (rec[PCL_S_FLAGS] & 1);     // _centroid :544-598
+  const int crow = fixed ? 0 : rec[PCL_S_ROW], ccol = fixed ? 0 : rec[PCL_S_COL];
+  int wr = fixed ? c.offset_rows : plot[PCL_P_CROP_R];
+  int wc = fixed ? c.offset_cols : plot[PCL_P_CROP_C];
+  const int init = fixed ? 1 : plot[PCL_P_CROP_INIT];
+  const bool pad = c.pad_char >= 0;
+  auto rectify = [&]() {                                  // :533-542
+    wr = max(0, wr) - max(0, wr + c.rows - p.H);
+    wc = max(0, wc) - max(0, wc + c.cols - p.W);
+  };
+  auto initialise = [&](int orow, int ocol) {             // :438-458
+    if (!have) { wr = 0; wc = 0; return; }
+    wr = crow - orow; wc = ccol - ocol;
+    if (!pad) rectify();
+  };
+  if (!init) {
+    initialise(c.rows / 2 + c.offset_rows, c.cols / 2 + c.offset_cols);
+  } else if (have) {
+    const int mr = c.margin_rows, mc = c.margin_cols;
+    bool can_v = (mr - 1 <= crow - wr) && (crow - wr <= c.rows - mr);   // :460-505
+    bool can_h = (mc - 1 <= ccol - wc) && (ccol - wc <= c.cols - mc);
+    if (!pad) {
+      if (!can_v) {
+        if (wr <= 0) can_v = crow <= mr;
+        else if (wr >= p.H - c.rows) can_v = crow >= wr + c.rows - mr;
+      } else if (!can_h) {
+        if (wc <= 0) can_h = ccol <= mc;
+        else if (wc >= p.W - c.cols) can_h = ccol >= wc + c.cols - mc;
+      }
+    }
+    if (can_v && can_h) {                                 // _pan_to :507-531
+      int dr = min(0, crow - wr - mr);
+      int dc = min(0, ccol - wc - mc);
+      if (dr == 0) dr += max(0, crow - wr - c.rows + mr + 1);
+      if (dc == 0) dc += max(0, ccol - wc - c.cols + mc + 1);
+      wr += dr; wc += dc;
+      if (!pad) rectify();
+    } else if (c.saccade) {
+      initialise(c.rows / 2, c.cols / 2);
+    }
+  }
+  __syncwarp();
+  if (lane == 0 && !fixed) { plot[PCL_P_CROP_R] = wr; plot[PCL_P_CROP_C] = wc; plot[PCL_P_CROP_INIT] = 1; }
+  // _do_crop :118-227: pad fill + window copy.
+  const uint8_t* board = p.board + (int64_t)env * p.H * p.pitch;
+  uint8_t* out = p.out + (int64_t)env * c.rows * c.cols;
+  const int cells = c.rows * c.cols;
+  for (int i = lane; i < cells; i += 32) {
+    const int r = wr + i / c.cols, cc2 = wc + i % c.cols;
+    uint8_t v = pad ? (uint8_t)c.pad_char : 0;
+    if ((unsigned)r < (unsigned)p.H && (unsigned)cc2 < (unsigned)p.W)
+      v = board[(int64_t)r * p.pitch + cc2];
+    out[i] = v;
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_render(const RenderParams& p, cudaStream_t s) {
+  render_kernel<<<p.B, kRenderThreads, 0, s>>>(p);
+  return cudaGetLastError();
+}
+cudaError_t launch_export_curtain(const ExportParams& p, cudaStream_t s) {
+  export_curtain_kernel<<<p.B, 128, 0, s>>>(p);
+  return cudaGetLastError();
+}
+cudaError_t launch_crop(const CropParams& p, cudaStream_t s) {
+  crop_kernel<<<(p.B + 3) / 4, 128, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace pcl

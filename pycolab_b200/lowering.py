@@ -1,0 +1,333 @@
+"""Lower a set-up `Engine` (Python entity objects) to a device game description.
+
+"Recognise and lower" (SURVEY.md §7 H1): game logic upstream is arbitrary Python
+in `update()` methods, which cannot run on a GPU.  The fused step kernels
+implement the logic of a fixed set of entity classes — the prefabs plus the
+concrete classes of the configured example games — and this module maps a
+finished `Engine` onto one of those device programs by class identity:
+
+  * an entity class is recognised by (defining module's last name component,
+    class name), looked up along its MRO, and only if `update` is not
+    overridden below the recognised class;
+  * the example modules may be the reference's own files
+    (`pycolab/examples/*.py`, imported through `pycolab_b200.compat`) or this
+    package's `pycolab_b200/games/*.py`;
+  * everything the constructors decided (positions, visibility, curtains,
+    patterns, margins, impassable sets, z-order, update groups) is read from
+    the live objects, so `make_game()` code runs unchanged.
+
+Anything else raises `NotLoweredError`; there is no CPU fallback.
+"""
+
+import numpy as np
+
+from pycolab_b200 import _lib
+from pycolab_b200 import things
+from pycolab_b200.errors import NotLoweredError
+from pycolab_b200.prefab_parts import drapes as prefab_drapes
+from pycolab_b200.prefab_parts import sprites as prefab_sprites
+
+# (module tail, class name) -> device role.
+LOWERED_CLASSES = {
+    ('scrolly_maze', 'PlayerSprite'): 'scrolly.player',
+    ('scrolly_maze', 'PatrollerSprite'): 'scrolly.patroller',
+    ('scrolly_maze', 'MazeDrape'): 'scrolly.maze',
+    ('scrolly_maze', 'CashDrape'): 'scrolly.cash',
+    ('warehouse_manager', 'BoxSprite'): 'warehouse.box',
+    ('warehouse_manager', 'JudgeDrape'): 'warehouse.judge',
+    ('warehouse_manager', 'PlayerSprite'): 'warehouse.player',
+    ('extraterrestrial_marauders', 'PlayerSprite'): 'marauders.player',
+    ('extraterrestrial_marauders', 'BunkerDrape'): 'marauders.bunker',
+    ('extraterrestrial_marauders', 'MarauderDrape'): 'marauders.marauder',
+    ('extraterrestrial_marauders', 'UpwardLaserBoltSprite'): 'marauders.up_bolt',
+    ('extraterrestrial_marauders', 'DownwardLaserBoltSprite'): 'marauders.down_bolt',
+}
+
+_PROGRAM_OF = {'scrolly': _lib.PROG_SCROLLY_MAZE, 'warehouse': _lib.PROG_WAREHOUSE,
+               'marauders': _lib.PROG_MARAUDERS}
+
+
+def role_of(entity):
+  """Device role of `entity`, or raise NotLoweredError."""
+  cls = type(entity)
+  for klass in cls.__mro__:
+    key = (klass.__module__.rsplit('.', 1)[-1], klass.__name__)
+    if key in LOWERED_CLASSES:
+      if cls.update is not klass.update:
+        raise NotLoweredError(
+            '{} overrides update() of the lowered class {}.{}'.format(
+                cls.__name__, *key))
+      return LOWERED_CLASSES[key]
+  raise NotLoweredError(
+      'no device program for entity class {}.{} (character {!r}); lowered classes: '
+      '{}'.format(cls.__module__, cls.__name__, getattr(entity, 'character', '?'),
+                  sorted('%s.%s' % k for k in LOWERED_CLASSES)))
+
+
+def round_up(x, m):
+  return (x + m - 1) // m * m
+
+
+def pack_rows(mask, words):
+  """bool [R, C] -> uint32 [R, words]; cell c is bit c&31 of word c>>5."""
+  mask = np.asarray(mask, dtype=bool)
+  rows, cols = mask.shape
+  assert words * 32 >= cols
+  padded = np.zeros((rows, words * 32), dtype=np.uint8)
+  padded[:, :cols] = mask
+  packed = np.packbits(padded.reshape(rows, words, 32), axis=2, bitorder='little')
+  return np.ascontiguousarray(packed).view('<u4').reshape(rows, words)
+
+
+def unpack_rows(packed, cols):
+  packed = np.ascontiguousarray(packed, dtype='<u4')
+  rows, words = packed.shape
+  bits = np.unpackbits(packed.view(np.uint8).reshape(rows, words * 4), axis=1,
+                       bitorder='little')
+  return bits[:, :cols].astype(bool)
+
+
+def char_set_mask(chars):
+  out = [0, 0, 0, 0]
+  for ch in chars:
+    code = ord(ch)
+    if code > 127:
+      raise NotLoweredError('non-ASCII impassable character {!r}'.format(ch))
+    out[code >> 5] |= 1 << (code & 31)
+  return out
+
+
+class LoweredGame(object):
+  """One level's device description: spec fields + template arrays."""
+
+  def __init__(self):
+    self.program = 0
+    self.rows = self.cols = self.pitch = 0
+    self.sprite_chars = ''
+    self.drape_chars = ''
+    self.impassable = []
+    self.confined = []
+    self.egocentric = []
+    self.margins = []
+    self.z_order = ''
+    self.groups = []
+    self.pattern_rows = self.pattern_cols = self.pattern_words = 0
+    self.bits_words = 0
+    self.backdrop = None        # u8 [H, pitch]
+    self.patterns = {}          # drape index -> u32 [PH, PWW]
+    self.pattern_mutable = {}   # drape index -> bool
+    self.bits = {}              # drape index -> u32 [H, BW]
+    self.sprites = None         # i32 [S, 8]
+    self.drapes = None          # i32 [D, 8]
+    self.plot = None            # i32 [16]
+    self.needs_rng = False
+    self.backdrop_chars = ''
+
+  def signature(self):
+    """Everything that must agree between envs sharing one handle."""
+    return (self.program, self.rows, self.cols, self.sprite_chars, self.drape_chars,
+            tuple(map(tuple, self.impassable)), tuple(self.confined),
+            tuple(self.egocentric), tuple(map(tuple, self.margins)), self.z_order,
+            tuple(self.groups), self.pattern_rows, self.pattern_cols)
+
+  def make_spec(self, auto_reset):
+    s = _lib.Spec()
+    s.abi_version = _lib.ABI_VERSION
+    s.program = self.program
+    s.rows, s.cols, s.pitch = self.rows, self.cols, self.pitch
+    s.n_sprites, s.n_drapes = len(self.sprite_chars), len(self.drape_chars)
+    s.auto_reset = 1 if auto_reset else 0
+    s.pattern_rows, s.pattern_cols = self.pattern_rows, self.pattern_cols
+    s.pattern_words, s.bits_words = self.pattern_words, self.bits_words
+    for i, ch in enumerate(self.sprite_chars):
+      s.sprite_char[i] = ord(ch)
+      for w in range(4):
+        s.impassable[i][w] = self.impassable[i][w]
+      s.sprite_confined[i] = int(self.confined[i])
+      s.sprite_egocentric[i] = int(self.egocentric[i])
+    for i, ch in enumerate(self.drape_chars):
+      s.drape_char[i] = ord(ch)
+      s.margins[i][0], s.margins[i][1] = self.margins[i]
+    for i, ch in enumerate(self.z_order):
+      s.z_order[i] = ord(ch)
+    s.n_groups = len(self.groups)
+    k = 0
+    for g, group in enumerate(self.groups):
+      s.group_len[g] = len(group)
+      for ch in group:
+        s.group_chars[k] = ord(ch)
+        k += 1
+    return s
+
+
+def _sprite_record(sprite, aux0=0, aux1=0, aux2=0):
+  if isinstance(sprite, prefab_sprites.MazeWalker):
+    vrow, vcol = sprite.virtual_position
+    prior = sprite._prior_visible
+  else:
+    vrow, vcol = sprite.position
+    prior = None
+  flags = (1 if sprite.visible else 0) | ((0 if prior is None else 2 if prior else 1) << 1)
+  return [int(sprite.position[0]), int(sprite.position[1]), int(vrow), int(vcol),
+          flags, int(aux0), int(aux1), int(aux2)]
+
+
+def _walker_meta(sprite):
+  if not isinstance(sprite, prefab_sprites.MazeWalker):
+    raise NotLoweredError('sprite {!r} is not a MazeWalker'.format(sprite.character))
+  if sprite._scrolling_group != '':
+    raise NotLoweredError('only the default scrolling group is lowered')
+  if (type(sprite)._on_board_exit is not prefab_sprites.MazeWalker._on_board_exit or
+      type(sprite)._on_board_enter is not prefab_sprites.MazeWalker._on_board_enter):
+    raise NotLoweredError('overridden MazeWalker board exit/enter hooks are not lowered')
+  return (char_set_mask(sprite.impassable), bool(sprite._confined_to_board),
+          bool(sprite._egocentric_scroller))
+
+
+def _plot_record(**words):
+  rec = [0] * _lib.PLOT_WORDS
+  rec[_lib.P_FRAME] = -1
+  rec[_lib.P_ORDER_FRAME] = _lib.NEVER
+  for name, value in words.items():
+    rec[getattr(_lib, 'P_' + name.upper())] = int(value)
+  return rec
+
+
+def _common(engine, game, program):
+  game.program = program
+  game.rows, game.cols = engine.rows, engine.cols
+  game.pitch = round_up(engine.cols, 16)
+  game.bits_words = (engine.cols + 31) // 32 + 1
+  game.z_order = ''.join(engine.z_order)
+  game.groups = [''.join(e.character for e in entities)
+                 for _, entities in sorted(engine._update_groups.items())]
+  backdrop = engine.backdrop
+  if type(backdrop).update is not things.Backdrop.update:
+    raise NotLoweredError('Backdrop subclasses with update() logic are not lowered')
+  game.backdrop = np.zeros((engine.rows, game.pitch), dtype=np.uint8)
+  game.backdrop[:, :engine.cols] = backdrop.curtain
+  game.backdrop_chars = ''.join(sorted(backdrop.palette))
+  if not engine._occlusion_in_layers:
+    raise NotLoweredError('occlusion_in_layers=False is not lowered yet')
+
+
+def _set_sprites(game, sprites, records):
+  game.sprite_chars = ''.join(s.character for s in sprites)
+  meta = [_walker_meta(s) for s in sprites]
+  game.impassable = [m[0] for m in meta]
+  game.confined = [m[1] for m in meta]
+  game.egocentric = [m[2] for m in meta]
+  game.sprites = np.array(records, dtype=np.int32).reshape(len(sprites), _lib.SPRITE_WORDS)
+
+
+def _scrolly_record(drape, aux0=0, aux1=0):
+  r, c = drape._northwest_corner
+  return [int(r), int(c), int(r), int(c), _lib.NEVER, int(aux0), int(aux1), 0]
+
+
+def _lower_scrolly_maze(engine, roles):
+  th = engine.things
+  want = {'P': 'scrolly.player', 'a': 'scrolly.patroller', 'b': 'scrolly.patroller',
+          'c': 'scrolly.patroller', '#': 'scrolly.maze', '@': 'scrolly.cash'}
+  if roles != want:
+    raise NotLoweredError('scrolly_maze program needs exactly {} (got {})'.format(want, roles))
+  game = LoweredGame()
+  _common(engine, game, _lib.PROG_SCROLLY_MAZE)
+  sprites = [th[c] for c in 'Pabc']
+  records = [_sprite_record(th['P'], aux0=0, aux1=_lib.NEVER)]
+  records += [_sprite_record(th[c], aux0=int(bool(th[c]._moving_east))) for c in 'abc']
+  _set_sprites(game, sprites, records)
+  walls, coins = th['#'], th['@']
+  for d in (walls, coins):
+    if d._scrolling_group != '':
+      raise NotLoweredError('only the default scrolling group is lowered')
+    if d.whole_pattern.shape != walls.whole_pattern.shape:
+      raise NotLoweredError('Scrolly patterns of different shapes')
+    if tuple(d._board_shape) != (engine.rows, engine.cols):
+      raise NotLoweredError('Scrolly board_shape differs from the Engine board')
+  game.drape_chars = '#@'
+  game.margins = [(-1, -1) if d._scroll_margins is None else tuple(d._scroll_margins)
+                  for d in (walls, coins)]
+  game.pattern_rows, game.pattern_cols = walls.whole_pattern.shape
+  game.pattern_words = (game.pattern_cols + 31) // 32 + 1
+  game.patterns = {0: pack_rows(walls.whole_pattern, game.pattern_words),
+                   1: pack_rows(coins.whole_pattern, game.pattern_words)}
+  game.pattern_mutable = {0: False, 1: True}
+  game.drapes = np.array([_scrolly_record(walls), _scrolly_record(coins, -1, -1)],
+                         dtype=np.int32)
+  game.plot = np.array(_plot_record(aux0=int(coins.whole_pattern.sum())), dtype=np.int32)
+  return game
+
+
+def _lower_warehouse(engine, roles):
+  th = engine.things
+  groups = [[e.character for e in ents]
+            for _, ents in sorted(engine._update_groups.items())]
+  if len(groups) != 3 or groups[1] != ['X'] or groups[2] != ['P']:
+    raise NotLoweredError('warehouse program needs update groups [boxes, [X], [P]]')
+  boxes = groups[0]
+  for ch in boxes:
+    if roles.get(ch) != 'warehouse.box':
+      raise NotLoweredError('unexpected entity {!r} in the box group'.format(ch))
+  if roles.get('X') != 'warehouse.judge' or roles.get('P') != 'warehouse.player':
+    raise NotLoweredError('warehouse program needs JudgeDrape X and PlayerSprite P')
+  game = LoweredGame()
+  _common(engine, game, _lib.PROG_WAREHOUSE)
+  sprites = [th[c] for c in boxes] + [th['P']]
+  _set_sprites(game, sprites, [_sprite_record(s) for s in sprites])
+  judge = th['X']
+  if judge.curtain.any():
+    raise NotLoweredError("a pre-filled 'X' curtain is not lowered")
+  game.drape_chars = 'X'
+  game.margins = [(-1, -1)]
+  rec = [0] * _lib.DRAPE_WORDS
+  rec[_lib.D_LAST_FRAME] = _lib.NEVER
+  rec[_lib.D_AUX0] = int(judge._last_num_boxes_on_goals)
+  game.drapes = np.array([rec], dtype=np.int32)
+  game.plot = np.array(_plot_record(), dtype=np.int32)
+  if '_' not in engine.backdrop.palette:
+    raise NotLoweredError("warehouse backdrop has no goal character '_'")
+  return game
+
+
+def _lower_marauders(engine, roles):
+  th = engine.things
+  want = {'P': 'marauders.player', 'B': 'marauders.bunker', 'X': 'marauders.marauder',
+          'a': 'marauders.up_bolt', 'b': 'marauders.up_bolt', 'c': 'marauders.up_bolt',
+          'd': 'marauders.up_bolt', 'y': 'marauders.down_bolt', 'z': 'marauders.down_bolt'}
+  if roles != want:
+    raise NotLoweredError('marauders program needs exactly {} (got {})'.format(want, roles))
+  game = LoweredGame()
+  _common(engine, game, _lib.PROG_MARAUDERS)
+  sprites = [th[c] for c in 'Pabcdyz']
+  _set_sprites(game, sprites, [_sprite_record(s) for s in sprites])
+  game.drape_chars = 'BX'
+  game.margins = [(-1, -1), (-1, -1)]
+  game.bits = {0: pack_rows(th['B'].curtain, game.bits_words),
+               1: pack_rows(th['X'].curtain, game.bits_words)}
+  recs = []
+  for ch in 'BX':
+    rec = [0] * _lib.DRAPE_WORDS
+    rec[_lib.D_LAST_FRAME] = _lib.NEVER
+    recs.append(rec)
+  recs[1][_lib.D_AUX0] = int(th['X']._dx)
+  game.drapes = np.array(recs, dtype=np.int32)
+  game.plot = np.array(_plot_record(aux0=_lib.NEVER, aux1=_lib.NEVER), dtype=np.int32)
+  game.needs_rng = True
+  return game
+
+
+def lower(engine):
+  """`Engine` (set-up finished, not yet showtime) -> `LoweredGame`."""
+  roles = {ch: role_of(ent) for ch, ent in engine.things.items()}
+  families = {role.split('.')[0] for role in roles.values()}
+  if len(families) != 1:
+    raise NotLoweredError('entities from different game programs: {}'.format(roles))
+  family = families.pop()
+  if family == 'scrolly':
+    return _lower_scrolly_maze(engine, roles)
+  if family == 'warehouse':
+    return _lower_warehouse(engine, roles)
+  if family == 'marauders':
+    return _lower_marauders(engine, roles)
+  raise NotLoweredError(family)

@@ -1,0 +1,395 @@
+"""GPU parity: the CUDA step engine vs the golden fixtures and the oracle.
+
+All of these call through the C ABI (libpcl.so via ctypes).  Bar: bit-exact
+boards (uint8), rewards (incl. None-ness), discounts, game_over and sprite
+registers.  Marked `gpu`; run on the B200 box.
+"""
+
+import numpy as np
+import pytest
+
+import golden_cases as gc
+import trajectory as tj
+from oracle import engine_model as em
+from oracle import games as ogames
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch():
+  import torch
+  return torch
+
+
+def _facade_sprites(chars, sink):
+  def on_frame(env, out):
+    rows = []
+    for ch in chars:
+      s = env.things[ch]
+      vp = s.virtual_position
+      rows.append([s.position[0], s.position[1], int(bool(s.visible)), vp[0], vp[1]])
+    sink.append(rows)
+  return on_frame
+
+
+# --------------------------------------------------------------- facade, B=1
+
+@pytest.mark.parametrize('name', gc.names('scrolly_'))
+def test_facade_scrolly_golden(name):
+  from pycolab_b200.games import scrolly_maze
+  g = gc.load(name)
+  maze, board, beneath = gc.scrolly_art(g)
+  sprites = []
+  n = min(len(g['actions']), 400)
+  got = tj.run_trajectory(lambda: scrolly_maze.make_game(maze, board, beneath),
+                          g['actions'][:n].tolist(),
+                          on_frame=_facade_sprites('Pabc', sprites))
+  want = {k: g[k][:n + 1] for k in ('boards', 'reward', 'has_reward', 'discount',
+                                    'game_over')}
+  tj.assert_same_trajectory(want, got, name)
+  np.testing.assert_array_equal(g['sprites'][:n + 1], np.array(sprites))
+
+
+@pytest.mark.parametrize('name', gc.names('warehouse_'))
+def test_facade_warehouse_golden(name):
+  from pycolab_b200.games import warehouse_manager
+  g = gc.load(name)
+  art, wlb = gc.warehouse_art(g)
+  chars = bytes(g['sprite_chars']).decode()
+  sprites = []
+  n = min(len(g['actions']), 300)
+  got = tj.run_trajectory(lambda: warehouse_manager.make_game(art, wlb),
+                          g['actions'][:n].tolist(),
+                          on_frame=_facade_sprites(chars, sprites))
+  want = {k: g[k][:n + 1] for k in ('boards', 'reward', 'has_reward', 'discount',
+                                    'game_over')}
+  tj.assert_same_trajectory(want, got, name)
+  np.testing.assert_array_equal(g['sprites'][:n + 1], np.array(sprites))
+
+
+@pytest.mark.parametrize('name', gc.names('marauders_'))
+def test_facade_marauders_golden(name):
+  from pycolab_b200.games import extraterrestrial_marauders as marauders
+  g = gc.load(name)
+  art = tj.u8_to_art(g['art'])
+  np.random.seed(int(g['rng_seed'][0]))     # facade mirrors the global NumPy RNG
+  sprites = []
+  n = min(len(g['actions']), 500)
+  got = tj.run_trajectory(lambda: marauders.make_game(art), g['actions'][:n].tolist(),
+                          on_frame=_facade_sprites('Pabcdyz', sprites))
+  want = {k: g[k][:n + 1] for k in ('boards', 'reward', 'has_reward', 'discount',
+                                    'game_over')}
+  tj.assert_same_trajectory(want, got, name)
+  np.testing.assert_array_equal(g['sprites'][:n + 1], np.array(sprites))
+
+
+# ------------------------------------------------- batched engine vs oracle
+
+def _batched_vs_oracle(make_facade_game, make_oracle, actions, n_levels=1,
+                       rng_seed=None, check_curtains=()):
+  """Step a BatchedEngine (auto-reset) and B oracle worlds in lockstep.
+
+  actions: int array [T, B].  make_* take the level index (env % n_levels)."""
+  from pycolab_b200 import batched
+  T, B = actions.shape
+  games = [make_facade_game(i) for i in range(n_levels)]
+  eng = batched.BatchedEngine(games, batch=B, rng_seed=rng_seed or 0)
+  worlds = [make_oracle(e) for e in range(B)]
+  outs = [w.its_showtime() for w in worlds]
+  res = eng.its_showtime()
+  torch = _torch()
+  acts = torch.from_numpy(actions.astype(np.int32)).cuda()
+  for t in range(T + 1):
+    torch.cuda.synchronize()
+    boards = res.board.cpu().numpy()
+    reward, has = res.reward.cpu().numpy(), res.has_reward.cpu().numpy()
+    disc, done = res.discount.cpu().numpy(), res.done.cpu().numpy()
+    for e in range(B):
+      np.testing.assert_array_equal(boards[e], outs[e][0], err_msg='t=%d env=%d' % (t, e))
+      want_r = outs[e][1]
+      assert (int(has[e]), int(reward[e])) == (
+          (0, 0) if want_r is None else (1, int(want_r))), (t, e)
+      assert float(disc[e]) == float(outs[e][2]), (t, e)
+      assert bool(done[e]) == worlds[e].game_over, (t, e)
+    for ch in check_curtains:
+      cur = eng.curtain(ch).cpu().numpy()
+      for e in range(B):
+        np.testing.assert_array_equal(cur[e], worlds[e].things[ch].curtain,
+                                      err_msg='curtain %s t=%d env=%d' % (ch, t, e))
+    if t == T:
+      break
+    res = eng.play(acts[t])
+    for e in range(B):
+      if worlds[e].game_over:               # the auto-reset rule
+        worlds[e] = make_oracle(e)
+        outs[e] = worlds[e].its_showtime()
+      else:
+        outs[e] = worlds[e].play(int(actions[t, e]))
+  assert int(eng.error_codes().max()) == 0
+  return eng
+
+
+def test_batched_scrolly_stock():
+  from pycolab_b200.games import scrolly_maze
+  g = gc.load('scrolly_stock_L0')
+  maze, board, beneath = gc.scrolly_art(g)
+  rs = np.random.RandomState(42)
+  actions = rs.randint(0, 6, size=(250, 24))
+  actions[rs.random_sample(actions.shape) < 0.9] %= 5     # mostly no quits
+  _batched_vs_oracle(lambda i: scrolly_maze.make_game(maze, board, beneath),
+                     lambda e: ogames.make_scrolly_maze(maze, board, '+', beneath),
+                     actions, check_curtains='#@')
+
+
+def test_batched_scrolly_generated_multi_level():
+  from pycolab_b200 import levels
+  from pycolab_b200.games import scrolly_maze
+  arts = [levels.scrolly_maze_level(10 + i) for i in range(3)]
+  rs = np.random.RandomState(43)
+  actions = rs.choice([0, 1, 2, 3, 4], size=(120, 9), p=[.3, .15, .3, .15, .1])
+  _batched_vs_oracle(lambda i: scrolly_maze.make_game(*arts[i]),
+                     lambda e: ogames.make_scrolly_maze(arts[e % 3][0], arts[e % 3][1],
+                                                        '+', arts[e % 3][2]),
+                     actions, n_levels=3)
+
+
+def test_batched_warehouse():
+  from pycolab_b200 import levels
+  from pycolab_b200.games import warehouse_manager
+  arts = [levels.warehouse_level(20 + i, shape=(24, 31), num_boxes=4 + i, num_goals=6 + i)
+          for i in range(2)]
+  # structure (number of boxes) must agree inside one engine: use level 0 twice
+  arts = [arts[0], levels.warehouse_level(77, shape=(24, 31), num_boxes=4, num_goals=6)]
+  rs = np.random.RandomState(44)
+  actions = rs.randint(0, 6, size=(300, 16))
+  actions[rs.random_sample(actions.shape) < 0.95] %= 5
+  _batched_vs_oracle(lambda i: warehouse_manager.make_game(arts[i]),
+                     lambda e: ogames.make_warehouse(arts[e % 2]),
+                     actions, n_levels=2, check_curtains='X')
+
+
+def test_batched_warehouse_80():
+  from pycolab_b200 import levels
+  from pycolab_b200.games import warehouse_manager
+  art = levels.warehouse_level(3)
+  rs = np.random.RandomState(45)
+  actions = rs.randint(0, 4, size=(150, 8))
+  _batched_vs_oracle(lambda i: warehouse_manager.make_game(art),
+                     lambda e: ogames.make_warehouse(art), actions)
+
+
+def test_batched_marauders():
+  from pycolab_b200 import levels
+  from pycolab_b200.games import extraterrestrial_marauders as marauders
+  art = levels.marauders_level()
+  rs = np.random.RandomState(46)
+  B = 12
+  actions = rs.randint(0, 4, size=(400, B))
+  rngs = [np.random.RandomState(900 + e) for e in range(B)]
+  _batched_vs_oracle(lambda i: marauders.make_game(art),
+                     lambda e: ogames.make_marauders(art, rngs[e]),
+                     actions, rng_seed=900, check_curtains='BX')
+
+
+# ------------------------------------------------------------------ cropper
+
+@pytest.mark.parametrize('name', gc.names('crop_'))
+def test_crop_golden(name):
+  from pycolab_b200 import cropping
+  from pycolab_b200.games import scrolly_maze
+  g = gc.load(name)
+  cfg = gc.config_of(g)
+  maze, board, beneath = gc.scrolly_art(g)
+  crop = cropping.ScrollingCropper(
+      cfg['rows'], cfg['cols'], ['P'], pad_char=cfg['pad'],
+      scroll_margins=tuple(cfg['margins']),
+      initial_offset=None if cfg['offset'] is None else tuple(cfg['offset']),
+      saccade=cfg['saccade'])
+  crops = []
+
+  def make():
+    eng = scrolly_maze.make_game(maze, board, beneath)
+    crop.set_engine(eng)
+    return eng
+
+  n = 150
+  got = tj.run_trajectory(make, g['actions'][:n].tolist(),
+                          on_frame=lambda env, out: crops.append(crop.crop(out[0]).board))
+  want = {k: g[k][:n + 1] for k in ('boards', 'reward', 'has_reward', 'discount',
+                                    'game_over')}
+  tj.assert_same_trajectory(want, got, name)
+  np.testing.assert_array_equal(g['crops'][:n + 1], np.stack(crops))
+
+
+def test_batched_crop_vs_oracle():
+  from pycolab_b200 import batched, levels
+  from pycolab_b200.games import scrolly_maze
+  art = levels.scrolly_maze_level(31)
+  B, T = 16, 80
+  eng = batched.BatchedEngine([scrolly_maze.make_game(*art)], batch=B)
+  spec = batched.scrolling_crop_spec(9, 9, 0, pad_char=' ', scroll_margins=(None, None))
+  worlds = [ogames.make_scrolly_maze(art[0], art[1], '+', art[2]) for _ in range(B)]
+  crops = [em.ScrollingCrop(9, 9, ['P'], pad_char=' ', scroll_margins=(None, None))
+           for _ in range(B)]
+  outs = []
+  for w, c in zip(worlds, crops):
+    c.set_engine(w)
+    outs.append(w.its_showtime())
+  eng.its_showtime()
+  rs = np.random.RandomState(5)
+  actions = rs.randint(0, 5, size=(T, B)).astype(np.int32)
+  torch = _torch()
+  for t in range(T + 1):
+    got = eng.crop(spec).cpu().numpy()
+    for e in range(B):
+      np.testing.assert_array_equal(got[e], crops[e].crop(outs[e][0]),
+                                    err_msg='t=%d env=%d' % (t, e))
+    if t == T:
+      break
+    eng.play(torch.from_numpy(actions[t]).cuda())
+    for e in range(B):
+      if worlds[e].game_over:
+        worlds[e] = ogames.make_scrolly_maze(art[0], art[1], '+', art[2])
+        crops[e].set_engine(worlds[e])
+        outs[e] = worlds[e].its_showtime()
+      else:
+        outs[e] = worlds[e].play(int(actions[t, e]))
+
+
+# ------------------------------------------------------- stand-alone render
+
+@pytest.mark.parametrize('shape,S,D', [((10, 30), 4, 2), ((64, 64), 4, 2),
+                                       ((16, 39), 7, 2), ((80, 80), 11, 1),
+                                       ((5, 7), 0, 1), ((9, 33), 16, 8)])
+def test_render_kernel_vs_oracle(shape, S, D):
+  """pcl_render on random reference-layout inputs vs oracle.render."""
+  import ctypes as C
+  from pycolab_b200 import _lib
+  torch = _torch()
+  lib = _lib.load()
+  H, W = shape
+  pitch = (W + 15) // 16 * 16
+  B = 37
+  rs = np.random.RandomState(H * 100 + W)
+  schars = 'ABCDEFGHIJKLMNOP'[:S]
+  dchars = 'stuvwxyz'[:D]
+  spec = _lib.Spec()
+  spec.abi_version, spec.program = _lib.ABI_VERSION, _lib.PROG_NONE
+  spec.rows, spec.cols, spec.pitch, spec.n_sprites, spec.n_drapes = H, W, pitch, S, D
+  for i, c in enumerate(schars):
+    spec.sprite_char[i] = ord(c)
+  for i, c in enumerate(dchars):
+    spec.drape_char[i] = ord(c)
+  h = C.c_void_p()
+  _lib.check(lib.pcl_create(C.byref(spec), B, 0, C.byref(h)), 'pcl_create')
+  backdrop = np.zeros((B, H, pitch), np.uint8)
+  backdrop[:, :, :W] = rs.choice([32, 46, 35], size=(B, H, W))
+  curtains = np.zeros((B, max(D, 1), H, pitch), np.uint8)
+  curtains[:, :D, :, :W] = rs.random_sample((B, D, H, W)) < 0.3
+  sprites = np.zeros((B, max(S, 1), 8), np.int32)
+  sprites[:, :, 0] = rs.randint(0, H, size=(B, max(S, 1)))
+  sprites[:, :, 1] = rs.randint(0, W, size=(B, max(S, 1)))
+  sprites[:, :, 4] = rs.randint(0, 2, size=(B, max(S, 1)))
+  z = np.zeros((B, max(S + D, 1)), np.uint8)
+  for b in range(B):
+    z[b, :S + D] = rs.permutation([ord(c) for c in schars + dchars])
+  dev = lambda a: torch.from_numpy(a).cuda()
+  t_bd, t_cur, t_sp, t_z = dev(backdrop), dev(curtains), dev(sprites), dev(z)
+  out = torch.zeros((B, H, pitch), dtype=torch.uint8, device='cuda')
+  stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+  _lib.check(lib.pcl_render(h, t_bd.data_ptr(), H * pitch, t_cur.data_ptr(),
+                            t_sp.data_ptr(), t_z.data_ptr(), out.data_ptr(), stream),
+             'pcl_render')
+  torch.cuda.synchronize()
+  got = out.cpu().numpy()
+  lib.pcl_destroy(h)
+
+  class Ent(object):
+    pass
+  for b in range(B):
+    things = {}
+    for i, c in enumerate(schars):
+      e = Ent()
+      e.is_sprite, e.row, e.col = True, int(sprites[b, i, 0]), int(sprites[b, i, 1])
+      e.visible = bool(sprites[b, i, 4])
+      things[c] = e
+    for i, c in enumerate(dchars):
+      e = Ent()
+      e.is_sprite, e.curtain = False, curtains[b, i, :, :W].astype(bool)
+      things[c] = e
+    want = em.render(H, W, backdrop[b, :, :W], [chr(c) for c in z[b, :S + D]], things)
+    np.testing.assert_array_equal(got[b, :, :W], want, err_msg='env %d' % b)
+    assert not got[b, :, W:].any()
+
+
+def test_renderer_class_api():
+  """BaseObservationRenderer's paint protocol (rendering.py:98-184) on the GPU."""
+  from pycolab_b200 import rendering
+  r = rendering.BaseObservationRenderer(4, 5, 'ab.# ')
+  r.clear()
+  bd = np.full((4, 5), ord('.'), np.uint8)
+  r.paint_all_of(bd)
+  mask = np.zeros((4, 5), bool)
+  mask[1, :] = True
+  r.paint_drape('#', mask)
+  r.paint_sprite('a', (1, 2))
+  r.paint_sprite('b', (3, 4))
+  obs = r.render()
+  want = bd.copy()
+  want[1, :] = ord('#')
+  want[1, 2] = ord('a')
+  want[3, 4] = ord('b')
+  np.testing.assert_array_equal(obs.board, want)
+  np.testing.assert_array_equal(obs.layers['#'], want == ord('#'))
+  with pytest.raises(ValueError):
+    r.paint_sprite('Z', (0, 0))
+
+
+# ------------------------------------------------- host-buffer entry point
+
+def test_step_host_matches_device_path():
+  from pycolab_b200 import batched, levels
+  from pycolab_b200.games import scrolly_maze
+  art = levels.scrolly_maze_level(3, world_shape=(65, 65), board_shape=(32, 32))
+  a = batched.BatchedEngine([scrolly_maze.make_game(*art)], batch=32)
+  b = batched.BatchedEngine([scrolly_maze.make_game(*art)], batch=32)
+  a.its_showtime()
+  b.its_showtime()
+  torch = _torch()
+  rs = np.random.RandomState(9)
+  for t in range(40):
+    act = rs.randint(0, 5, size=32).astype(np.int32)
+    ra = a.play(torch.from_numpy(act).cuda())
+    board, reward, has, disc, done = b.play_host(act)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(ra.board.cpu().numpy(), board)
+    np.testing.assert_array_equal(ra.reward.cpu().numpy(), reward)
+    np.testing.assert_array_equal(ra.done.cpu().numpy(), done)
+  assert a.launch_count() >= 41
+
+
+def test_large_batch_invariants():
+  """BASELINE configs[1] size: properties that need no oracle at full size."""
+  from pycolab_b200 import batched, levels
+  from pycolab_b200.games import scrolly_maze
+  torch = _torch()
+  art = levels.scrolly_maze_level(0)
+  B = 4096
+  eng = batched.BatchedEngine([scrolly_maze.make_game(*art)], batch=B)
+  eng.its_showtime()
+  first = eng.board.clone()
+  # Identical envs + identical actions stay identical (lockstep determinism).
+  rs = np.random.RandomState(1)
+  total_reward = torch.zeros(B, dtype=torch.int64, device='cuda')
+  for t in range(50):
+    a = int(rs.randint(0, 5))
+    res = eng.play(torch.full((B,), a, dtype=torch.int32, device='cuda'))
+    total_reward += res.reward.long()
+    assert bool((res.board == res.board[0:1]).all())
+  # Exactly one 'P' per board while it is on the board, boards only hold legal chars.
+  legal = torch.tensor([ord(c) for c in ' .#@Pabc'], device='cuda', dtype=torch.uint8)
+  assert bool(torch.isin(eng.board, legal).all())
+  assert int((eng.board == ord('P')).sum()) == B
+  assert bool((total_reward % 100 == 0).all())
+  assert int(eng.error_codes().abs().max()) == 0
+  assert first.shape == (B, 64, 64)

@@ -1,0 +1,325 @@
+"""CPU tests of the host side: C-ABI library surface, facade set-up API,
+lowering, compat loading of the reference's example modules."""
+
+import os
+import re
+
+import numpy as np
+import pytest
+
+import golden_cases as gc
+import refdriver
+import trajectory as tj
+from oracle import games as ogames
+from pycolab_b200 import _lib
+from pycolab_b200 import ascii_art
+from pycolab_b200 import engine as engine_mod
+from pycolab_b200 import levels
+from pycolab_b200 import lowering
+from pycolab_b200 import things
+from pycolab_b200.errors import DeviceOnlyError, NotLoweredError
+from pycolab_b200.games import extraterrestrial_marauders as g_marauders
+from pycolab_b200.games import scrolly_maze as g_scrolly
+from pycolab_b200.games import warehouse_manager as g_warehouse
+from pycolab_b200.prefab_parts import sprites as prefab_sprites
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------ C-ABI library
+
+def _header_functions():
+  text = open(os.path.join(ROOT, 'include', 'pcl.h')).read()
+  text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+  return sorted(set(re.findall(r'\b(pcl_[a-z_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+  import ctypes
+  assert os.path.exists(_lib.LIB_PATH), 'build libpcl.so first (__graft_entry__.build)'
+  lib = ctypes.CDLL(_lib.LIB_PATH)
+  declared = _header_functions()
+  assert len(declared) >= 14
+  for name in declared:
+    assert hasattr(lib, name), name
+  assert sorted(_lib.SYMBOLS) == declared
+
+
+def test_binding_loads_and_reports_abi():
+  lib = _lib.load()
+  assert lib.pcl_abi_version() == _lib.ABI_VERSION
+  assert _lib.status_string(_lib.ERR_UNSUPPORTED) == 'game not lowered to a device program'
+
+
+def test_spec_struct_matches_header_size():
+  # pcl_spec: 12 int32 + 16 + 8 bytes + 16*4 u32 + 16 + 16 i32 + 8*2 i32 + 24 bytes
+  # + 1 i32 + 24 i32 + 24 bytes + 8 i32.
+  import ctypes
+  expected = 12 * 4 + 16 + 8 + 16 * 16 + 16 * 4 + 16 * 4 + 16 * 4 + 24 + 4 + 24 * 4 + 24 + 8 * 4
+  assert ctypes.sizeof(_lib.Spec) == expected
+
+
+def test_create_rejects_bad_specs_without_gpu():
+  import ctypes as C
+  lib = _lib.load()
+  h = C.c_void_p()
+  spec = _lib.Spec()
+  assert lib.pcl_create(C.byref(spec), 4, -1, C.byref(h)) == _lib.ERR_INVALID  # abi 0
+  spec.abi_version = _lib.ABI_VERSION
+  spec.rows, spec.cols, spec.pitch = 10, 30, 30                              # pitch % 16
+  assert lib.pcl_create(C.byref(spec), 4, -1, C.byref(h)) == _lib.ERR_INVALID
+  spec.pitch = 32
+  spec.program = 99
+  assert lib.pcl_create(C.byref(spec), 4, -1, C.byref(h)) == _lib.ERR_UNSUPPORTED
+  spec.program = _lib.PROG_NONE
+  assert lib.pcl_create(C.byref(spec), 4, -1, C.byref(h)) == _lib.OK
+  out = _lib.Outputs()
+  assert lib.pcl_step(h, None, C.byref(out), None) == _lib.ERR_UNBOUND
+  assert lib.pcl_destroy(h) == _lib.OK
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+  monkeypatch.setattr(_lib, '_lib', None)
+  monkeypatch.setattr(_lib, 'LIB_PATH', '/nonexistent/libpcl.so')
+  with pytest.raises(_lib.PclLibraryError):
+    _lib.load()
+
+
+def test_no_cpu_path():
+  import torch
+  if torch.cuda.is_available():
+    pytest.skip('GPU present')
+  from pycolab_b200 import batched
+  art = levels.scrolly_maze_level(0, world_shape=(33, 33), board_shape=(16, 16))
+  with pytest.raises(_lib.PclLibraryError):
+    batched.BatchedEngine([g_scrolly.make_game(*art)], batch=2)
+  with pytest.raises(_lib.PclLibraryError):
+    g_scrolly.make_game(*art).its_showtime()
+
+
+# ----------------------------------------------------------------- lowering
+
+def test_pack_rows_round_trip():
+  rs = np.random.RandomState(0)
+  for cols in (1, 31, 32, 33, 64, 89, 129):
+    mask = rs.random_sample((7, cols)) < 0.4
+    words = (cols + 31) // 32 + 1
+    packed = lowering.pack_rows(mask, words)
+    assert packed.shape == (7, words) and packed.dtype == np.uint32
+    np.testing.assert_array_equal(lowering.unpack_rows(packed, cols), mask)
+    assert not packed[:, -1].any()
+    c = cols - 1
+    assert bool((packed[3, c >> 5] >> (c & 31)) & 1) == bool(mask[3, c])
+
+
+def _check_sprites(game, world, chars):
+  for i, ch in enumerate(chars):
+    w, rec = world.things[ch], game.sprites[i]
+    assert tuple(rec[:4]) == (w.row, w.col, w.vrow, w.vcol), ch
+    assert bool(rec[_lib.S_FLAGS] & 1) == bool(w.visible), ch
+    prior = (rec[_lib.S_FLAGS] >> 1) & 3
+    assert {0: None, 1: False, 2: True}[prior] == w.prior_visible, ch
+
+
+@pytest.mark.parametrize('name', ['scrolly_stock_L0', 'scrolly_stock_L2', 'scrolly_gen64_s0'])
+def test_lower_scrolly_matches_oracle_initial_state(name):
+  g = gc.load(name)
+  maze, board, beneath = gc.scrolly_art(g)
+  game = lowering.lower(g_scrolly.make_game(maze, board, beneath))
+  world = ogames.make_scrolly_maze(maze, board, '+', beneath)
+  assert game.program == _lib.PROG_SCROLLY_MAZE
+  assert (game.rows, game.cols) == (world.rows, world.cols)
+  assert game.pitch % 16 == 0 and game.pitch >= game.cols
+  assert game.sprite_chars == 'Pabc' and game.drape_chars == '#@'
+  assert game.z_order == 'abc@#P' and game.groups == ['#', 'abcP', '@']
+  _check_sprites(game, world, 'Pabc')
+  for d, ch in enumerate('#@'):
+    np.testing.assert_array_equal(
+        lowering.unpack_rows(game.patterns[d], game.pattern_cols), world.things[ch].pattern)
+    assert tuple(game.drapes[d][:2]) == world.things[ch].corner
+    assert game.margins[d] == (2, 3)
+  assert game.plot[_lib.P_AUX0] == world.things['@'].pattern.sum()
+  assert game.plot[_lib.P_FRAME] == -1
+  np.testing.assert_array_equal(game.backdrop[:, :game.cols], world.backdrop)
+  assert [int(game.sprites[i][_lib.S_AUX0]) for i in (1, 2, 3)] == [
+      int(world.things[c].aux['moving_east']) for c in 'abc']
+  assert game.egocentric == [True, False, False, False]
+
+
+@pytest.mark.parametrize('name', ['warehouse_stock_L0', 'warehouse_stock_L1',
+                                  'warehouse_gen80_s3'])
+def test_lower_warehouse_matches_oracle_initial_state(name):
+  g = gc.load(name)
+  art, wlb = gc.warehouse_art(g)
+  game = lowering.lower(g_warehouse.make_game(art, wlb))
+  world = ogames.make_warehouse(art, wlb)
+  chars = bytes(g['sprite_chars']).decode()
+  assert game.program == _lib.PROG_WAREHOUSE and game.sprite_chars == chars
+  _check_sprites(game, world, chars)
+  np.testing.assert_array_equal(game.backdrop[:, :game.cols], world.backdrop)
+  for i, ch in enumerate(chars):
+    want = lowering.char_set_mask(chr(c) for c in world.things[ch].impassable)
+    assert game.impassable[i] == want
+
+
+def test_lower_marauders_matches_oracle_initial_state():
+  art = levels.marauders_level()
+  game = lowering.lower(g_marauders.make_game(art))
+  world = ogames.make_marauders(art, np.random.RandomState(0))
+  assert game.program == _lib.PROG_MARAUDERS and game.needs_rng
+  _check_sprites(game, world, 'Pabcdyz')
+  for d, ch in enumerate('BX'):
+    np.testing.assert_array_equal(lowering.unpack_rows(game.bits[d], game.cols),
+                                  world.things[ch].curtain)
+  assert game.drapes[1][_lib.D_AUX0] == -1
+  assert game.confined == [True] + [False] * 6
+  # bolts start hidden off-board with their visibility stashed (sprites.py:223-249)
+  assert all(game.sprites[i][_lib.S_FLAGS] == 4 for i in range(1, 7))
+
+
+def test_unknown_entity_class_is_refused():
+  class Wanderer(prefab_sprites.MazeWalker):
+    def __init__(self, corner, position, character):
+      super(Wanderer, self).__init__(corner, position, character, impassable='#')
+
+    def update(self, actions, board, layers, backdrop, things, the_plot):
+      self._north(board, the_plot)
+
+  game = ascii_art.ascii_art_to_game(['#####', '# w #', '#####'], ' ', {'w': Wanderer})
+  with pytest.raises(NotLoweredError):
+    lowering.lower(game)
+  with pytest.raises(NotLoweredError):
+    game.its_showtime()
+  with pytest.raises(DeviceOnlyError):
+    game.things['w']._north(None, None)
+
+
+def test_overriding_update_of_a_lowered_class_is_refused():
+  class Cheater(g_scrolly.PlayerSprite):
+    def update(self, actions, board, layers, backdrop, things, the_plot):
+      pass
+  assert lowering.role_of.__name__ == 'role_of'
+  corner = things.Sprite.Position(5, 5)
+  with pytest.raises(NotLoweredError):
+    lowering.role_of(Cheater(corner, things.Sprite.Position(1, 1), 'P', (1, 1)))
+
+
+# ----------------------------------------------- facade set-up API behaviour
+
+def test_engine_setup_errors_match_reference_contract():
+  eng = engine_mod.Engine(3, 4)
+  with pytest.raises(TypeError):
+    eng.add_sprite('a', (0, 0), object)
+  with pytest.raises(ValueError):
+    eng.add_sprite('a', (5, 0), g_warehouse.PlayerSprite)
+  eng.add_sprite('a', (1, 1), g_warehouse.PlayerSprite)
+  with pytest.raises(RuntimeError):
+    eng.add_sprite('a', (1, 2), g_warehouse.PlayerSprite)
+  with pytest.raises(ValueError):
+    eng.add_sprite('ab', (1, 2), g_warehouse.PlayerSprite)
+  with pytest.raises(ValueError):
+    eng.set_z_order('ab')
+  with pytest.raises(RuntimeError):
+    eng.play(0)
+  eng.set_prefilled_backdrop(' #', np.full((3, 4), 32, np.uint8), things.Backdrop)
+  with pytest.raises(RuntimeError):
+    eng.set_backdrop(' ', things.Backdrop)
+  assert eng.backdrop.palette.hash == ord('#')
+  assert eng.backdrop.palette[' '] == 32
+  with pytest.raises(AttributeError):
+    eng.backdrop.palette.at
+
+
+def test_ascii_art_errors():
+  with pytest.raises(TypeError):
+    ascii_art.ascii_art_to_uint8_nparray([['a', 'b'], ['c', 'd']])
+  with pytest.raises(ValueError):
+    ascii_art.ascii_art_to_uint8_nparray(['ab', 'c'])
+  with pytest.raises(ValueError):
+    ascii_art.ascii_art_to_game(['P '], ' ', {'P': g_warehouse.PlayerSprite},
+                                update_schedule=[['Q']])
+  with pytest.raises(ValueError):
+    ascii_art.ascii_art_to_game(['PP'], ' ', {'P': g_warehouse.PlayerSprite})
+  with pytest.raises(TypeError):
+    ascii_art.Partial(int)
+
+
+def test_maze_walker_constructor_contract():
+  corner = things.Sprite.Position(4, 4)
+  class Plain(prefab_sprites.MazeWalker):
+    def update(self, *args):
+      pass
+  with pytest.raises(ValueError):
+    Plain(corner, things.Sprite.Position(0, 0), 'x', 'x#')
+  with pytest.raises(TypeError):
+    Plain(corner, things.Sprite.Position(0, 0), 'x', [1, 2])
+  bolt = g_marauders.UpwardLaserBoltSprite(corner, things.Sprite.Position(2, 2), 'a')
+  assert bolt.position == (0, 0) and not bolt.visible and not bolt.on_the_board
+  assert bolt.virtual_position == (-1, -1) and bolt._prior_visible is True
+  bolt._teleport((3, 1))
+  assert bolt.position == (3, 1) and bolt.visible
+
+
+# --------------------------------- the reference's own example files, unchanged
+
+needs_ref = pytest.mark.skipif(not refdriver.available(),
+                               reason='/root/reference not present')
+
+
+@pytest.fixture
+def compat_examples():
+  import sys
+  from pycolab_b200 import compat
+  saved = {k: v for k, v in sys.modules.items()
+           if k == 'pycolab' or k.startswith('pycolab.')}
+  compat.uninstall()
+  compat.install()
+  base = os.path.join(refdriver.REFERENCE_ROOT, 'pycolab', 'examples')
+  yield lambda name: compat.load_example(os.path.join(base, name + '.py'))
+  compat.uninstall()
+  sys.modules.update(saved)
+
+
+def _same_lowering(a, b):
+  assert a.signature() == b.signature()
+  for name in ('backdrop', 'sprites', 'drapes', 'plot'):
+    np.testing.assert_array_equal(getattr(a, name), getattr(b, name), err_msg=name)
+  for d in a.patterns:
+    np.testing.assert_array_equal(a.patterns[d], b.patterns[d])
+  for d in a.bits:
+    np.testing.assert_array_equal(a.bits[d], b.bits[d])
+
+
+@needs_ref
+def test_reference_scrolly_maze_example_loads_and_lowers(compat_examples):
+  mod = compat_examples('scrolly_maze')
+  assert mod.PlayerSprite.__mro__[1] is prefab_sprites.MazeWalker
+  for level in (0, 1, 2):
+    theirs = lowering.lower(mod.make_game(level))
+    ours = lowering.lower(g_scrolly.make_game(
+        mod.MAZES_ART[level], mod.STAR_ART, mod.MAZES_WHAT_LIES_BENEATH[level]))
+    _same_lowering(theirs, ours)
+
+
+@needs_ref
+def test_reference_warehouse_example_loads_and_lowers(compat_examples):
+  mod = compat_examples('warehouse_manager')
+  for level in (0, 1, 2):
+    theirs = lowering.lower(mod.make_game(level))
+    ours = lowering.lower(g_warehouse.make_game(
+        mod.WAREHOUSES_ART[level], mod.WAREHOUSES_WHAT_LIES_BENEATH[level]))
+    _same_lowering(theirs, ours)
+
+
+@needs_ref
+def test_reference_marauders_example_loads_and_lowers(compat_examples):
+  mod = compat_examples('extraterrestrial_marauders')
+  _same_lowering(lowering.lower(mod.make_game()),
+                 lowering.lower(g_marauders.make_game(levels.marauders_level())))
+
+
+@needs_ref
+def test_reference_example_outside_the_lowered_set_is_refused(compat_examples):
+  mod = compat_examples('better_scrolly_maze')
+  with pytest.raises(NotLoweredError):
+    lowering.lower(mod.make_game(0))
