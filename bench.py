@@ -94,7 +94,8 @@ def cpu_baseline(cores, budget, pool=None):
 # ------------------------------------------------------------------- clocks
 
 class ClockSampler(object):
-  QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+  """nvidia-smi clock / throttle-reason samples during the loaded window."""
+  QUERY = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
            'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
@@ -102,6 +103,7 @@ class ClockSampler(object):
     self.gpu = gpu_index
     self.proc = None
     self.path = None
+    self.begin = self.end = None
 
   def start(self):
     try:
@@ -109,12 +111,19 @@ class ClockSampler(object):
       os.close(fd)
       self.proc = subprocess.Popen(
           ['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.QUERY,
-           '--format=csv,noheader,nounits', '-lms', '100'],
+           '--format=csv,noheader,nounits', '-lms', '20'],
           stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
     except OSError:
       self.proc = None
 
+  def mark_begin(self):
+    self.begin = time.time()
+
+  def mark_end(self):
+    self.end = time.time()
+
   def stop(self):
+    import datetime
     out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
     if self.proc is None:
       return out
@@ -123,24 +132,30 @@ class ClockSampler(object):
       self.proc.wait(timeout=5)
     except subprocess.TimeoutExpired:
       self.proc.kill()
-    sm, smax, reasons = [], [], set()
     names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    rows = []
     for line in open(self.path):
       f = [x.strip() for x in line.split(',')]
       if len(f) < 9:
         continue
       try:
-        sm.append(float(f[1]))
-        smax.append(float(f[2]))
+        ts = datetime.datetime.strptime(f[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+        rows.append((ts, float(f[1]), float(f[2]),
+                     [n for n, v in zip(names, f[5:9]) if v.lower().startswith('active')]))
       except ValueError:
         continue
-      for name, val in zip(names, f[5:9]):
-        if val.lower().startswith('active'):
-          reasons.add(name)
     os.unlink(self.path)
-    if sm:
-      out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)),
-                 reasons=sorted(reasons), samples=len(sm))
+    inside = [r for r in rows if self.begin is not None and self.end is not None
+              and self.begin - 0.02 <= r[0] <= self.end + 0.02]
+    window = 'loaded window'
+    if not inside:                      # window shorter than the sampling period
+      inside = [r for r in rows if self.begin is None or r[0] >= self.begin - 0.25]
+      window = 'nearest samples (loaded window shorter than the sampling period)'
+    if inside:
+      out.update(sm_mhz=float(np.median([r[1] for r in inside])),
+                 sm_max_mhz=float(max(r[2] for r in inside)),
+                 reasons=sorted({n for r in inside for n in r[3]}),
+                 samples=len(inside), window=window)
     return out
 
 
@@ -194,8 +209,8 @@ def workload_config(n_gpus):
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
-  ap.add_argument('--steps', type=int, default=200)
-  ap.add_argument('--warmup', type=int, default=20)
+  ap.add_argument('--steps', type=int, default=1000)
+  ap.add_argument('--warmup', type=int, default=50)
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--cpu-seconds', type=float, default=12.0)
   ap.add_argument('--no-flush', action='store_true')
@@ -219,6 +234,8 @@ def main():
   if world > 1:
     dist.init_process_group('nccl', device_id=dev)
 
+  sampler = ClockSampler(local_rank)
+  sampler.start()
   B, K, W = BATCH_PER_GPU, args.steps, max(3, args.warmup)
   arts = make_levels(N_LEVELS)
   games = [scrolly_maze.make_game(*a) for a in arts]
@@ -236,11 +253,10 @@ def main():
     torch.cuda.synchronize(dev)
 
   # ---- device-resident throughput: per-step CUDA events ------------------
+  sampler.mark_begin()
   for t in range(W):
     eng.play(actions[t])
   barrier()
-  sampler = ClockSampler(local_rank)
-  sampler.start()
   starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
   stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
   launches0 = eng.launch_count()
@@ -255,7 +271,6 @@ def main():
   barrier()
   wall = time.perf_counter() - wall0
   launches = eng.launch_count() - launches0
-  clocks = sampler.stop()
   step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, stops)])
   dev_ms = float(step_ms.sum())
   if world > 1:
@@ -280,6 +295,8 @@ def main():
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
   e2e_value = world * B * e2e_steps / e2e_s
+  sampler.mark_end()
+  clocks = sampler.stop()
   errors = int(eng.error_codes().abs().max())
 
   if rank == 0:
