@@ -32,6 +32,7 @@ BOARD = (64, 64)
 WORLD = (129, 129)
 BATCH_PER_GPU = 4096
 N_LEVELS = 32
+ROTATION = 6                      # independent batches stepped round-robin (> L2)
 ACTIONS = 5                       # 0..4, no quit
 # Algorithmic bytes per env-step, reference layout:
 #   H*W*(1 backdrop + 2 pattern windows + 2 curtains + 1 board) + 64*S + 64
@@ -198,12 +199,66 @@ def run_reference_arm(args, rank, world):
       'wall_s': time.perf_counter() - t0}))
 
 
+def render_microbench(engines, n=60):
+  """Mean device time per launch of the stand-alone renderer (`pcl_render`,
+  Engine._render + BaseObservationRenderer in the reference's byte layout):
+  backdrop + 2 byte curtains + sprites -> board, rotating over the R engines'
+  states (working set > L2), n launches back to back between one event pair."""
+  import ctypes as C
+  import torch
+  from pycolab_b200 import _lib
+  lib = _lib.load()
+  sets = []
+  for eng in engines:
+    B, H, pitch = eng.batch, eng.rows, eng.pitch
+    dev = eng.device
+    curtains = torch.zeros((B, 2, H, pitch), dtype=torch.uint8, device=dev)
+    curtains[:, 0, :, :eng.cols] = eng.curtain('#')
+    curtains[:, 1, :, :eng.cols] = eng.curtain('@')
+    backdrop = eng.backdrop.expand(B, H, pitch).contiguous()
+    z = torch.tensor([ord(c) for c in eng.game.z_order], dtype=torch.uint8, device=dev)
+    z = z[None].repeat(B, 1).contiguous()
+    out = torch.zeros((B, H, pitch), dtype=torch.uint8, device=dev)
+    sets.append((eng, backdrop, curtains, z, out))
+  stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+  def launch(i):
+    eng, backdrop, curtains, z, out = sets[i % len(sets)]
+    _lib.check(lib.pcl_render(eng._h, backdrop.data_ptr(), eng.rows * eng.pitch,
+                              curtains.data_ptr(), eng.sprites.data_ptr(), z.data_ptr(),
+                              out.data_ptr(), stream), 'pcl_render')
+  for i in range(2 * len(sets)):
+    launch(i)
+  torch.cuda.synchronize(dev)
+  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  a.record()
+  for i in range(n):
+    launch(i)
+  b.record()
+  torch.cuda.synchronize(dev)
+  for eng, _, _, _, out in sets:
+    assert bool((out[:, :, :eng.cols] == eng.board).all()), 'pcl_render != step kernel board'
+  return float(a.elapsed_time(b)) / n
+
+
+def render_roofline(ms, B, eng, peak):
+  # A_render = H*W*(2 + D) + 12*S  (SURVEY.md §8d): 16 432 B per env at 64x64, D=2, S=4.
+  a_render = eng.rows * eng.cols * 4 + 12 * 4
+  achieved = B * a_render / (ms / 1000.0) / 1e9
+  return {'kernel': 'render_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': peak,
+          'unit': 'GB/s', 'frac': achieved / peak, 'kernel_ms_mean': ms,
+          'algorithmic_bytes_per_launch': B * a_render, 'traffic': None,
+          'checked': 'output equals the fused step kernel\'s board'}
+
+
 def workload_config(n_gpus):
   return {'workload': 'scrolly_maze 64x64 board / 129x129 world, generated levels '
                       '(BASELINE.json configs[1]), random actions 0-4, auto-reset',
           'batch_per_gpu': BATCH_PER_GPU, 'global_batch': BATCH_PER_GPU * n_gpus,
           'levels': N_LEVELS, 'parallelism': 'env-sharded x%d, no collective' % n_gpus,
-          'l2': 'flushed between steps (256 MiB write outside the timed events)'}
+          'l2': '%d independent %d-env batches stepped round-robin; working set '
+                '(~%d MB) exceeds the 126 MB L2, so no flush is needed' % (
+                    ROTATION, BATCH_PER_GPU, ROTATION * 60)}
 
 
 def main():
@@ -213,7 +268,7 @@ def main():
   ap.add_argument('--warmup', type=int, default=50)
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--cpu-seconds', type=float, default=12.0)
-  ap.add_argument('--no-flush', action='store_true')
+  ap.add_argument('--no-rotate', action='store_true')
   args = ap.parse_args()
 
   rank = int(os.environ.get('RANK', '0'))
@@ -237,14 +292,21 @@ def main():
   sampler = ClockSampler(local_rank)
   sampler.start()
   B, K, W = BATCH_PER_GPU, args.steps, max(3, args.warmup)
+  R = 1 if args.no_rotate else ROTATION
   arts = make_levels(N_LEVELS)
   games = [scrolly_maze.make_game(*a) for a in arts]
-  eng = batched.BatchedEngine(games, batch=B, device=local_rank, env_offset=rank * B)
-  eng.its_showtime()
+  from pycolab_b200 import lowering
+  lowered = [lowering.lower(g) for g in games]
+  # R independent batches of B envs, stepped round-robin: the combined working
+  # set (R x ~60 MB) exceeds the 126 MB L2, so every step streams from HBM.
+  engines = [batched.BatchedEngine(lowered, batch=B, device=local_rank,
+                                   env_offset=(rank * R + r) * B) for r in range(R)]
+  for e in engines:
+    e.its_showtime()
+  eng = engines[0]
   rs = np.random.RandomState(1234 + rank)
   actions_np = rs.randint(0, ACTIONS, size=(W + K, B)).astype(np.int32)
   actions = torch.from_numpy(actions_np).to(dev)
-  flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
   def barrier():
     torch.cuda.synchronize(dev)
@@ -252,42 +314,52 @@ def main():
       dist.barrier()
     torch.cuda.synchronize(dev)
 
-  # ---- device-resident throughput: per-step CUDA events ------------------
+  # ---- device-resident throughput: K back-to-back steps, one event pair ----
   sampler.mark_begin()
-  for t in range(W):
-    eng.play(actions[t])
+  for t in range(W * R):
+    engines[t % R].play(actions[t % W])
   barrier()
-  starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-  stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-  launches0 = eng.launch_count()
+  start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  launches0 = sum(e.launch_count() for e in engines)
   barrier()
   wall0 = time.perf_counter()
+  start.record()
   for t in range(K):
-    if not args.no_flush:
-      flush.fill_(t & 0xff)
-    starts[t].record()
-    eng.play(actions[W + t])
-    stops[t].record()
+    engines[t % R].play(actions[W + t])
+  stop.record()
   barrier()
   wall = time.perf_counter() - wall0
-  launches = eng.launch_count() - launches0
-  step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, stops)])
-  dev_ms = float(step_ms.sum())
+  launches = sum(e.launch_count() for e in engines) - launches0
+  dev_ms = float(start.elapsed_time(stop))
   if world > 1:
     t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
   value = world * B * K / (dev_ms / 1000.0)
-  kernel_ms = float(np.median(step_ms))
+  kernel_ms = dev_ms / K
+
+  # Per-launch event timing with an explicit L2 flush before each launch, for
+  # comparison (each event pair adds a few microseconds of launch/drain latency).
+  flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+  ev_ms = []
+  for t in range(min(K, 50)):
+    flush.fill_(t & 0xff)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    eng.play(actions[W + t])
+    b.record()
+    torch.cuda.synchronize(dev)
+    ev_ms.append(a.elapsed_time(b))
+  kernel_ms_flushed_events = float(np.median(ev_ms))
 
   # ---- end to end through the host-buffer C-ABI call ---------------------
-  for t in range(3):
-    eng.play_host(actions_np[t])
+  for t in range(3 * R):
+    engines[t % R].play_host(actions_np[t % W])
   barrier()
   e2e_steps = min(K, 100)
   t0 = time.perf_counter()
   for t in range(e2e_steps):
-    eng.play_host(actions_np[W + t])
+    engines[t % R].play_host(actions_np[W + t])
   barrier()
   e2e_s = time.perf_counter() - t0
   if world > 1:
@@ -295,9 +367,10 @@ def main():
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
   e2e_value = world * B * e2e_steps / e2e_s
+  render_ms = render_microbench(engines, n=60) if rank == 0 else None
   sampler.mark_end()
   clocks = sampler.stop()
-  errors = int(eng.error_codes().abs().max())
+  errors = max(int(e.error_codes().abs().max()) for e in engines)
 
   if rank == 0:
     peaks = {}
@@ -306,6 +379,11 @@ def main():
     except (OSError, ValueError):
       pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
+    traffic = {}
+    try:
+      traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+    except (OSError, ValueError):
+      pass
     achieved = B * A_STEP_BYTES / (kernel_ms / 1000.0) / 1e9
     layout = B * LAYOUT_STEP_BYTES / (kernel_ms / 1000.0) / 1e9
     cpu_value, cpu_steps = cpu_baseline(1, args.cpu_seconds)
@@ -323,13 +401,18 @@ def main():
             'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
             'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback 6650',
             'algorithmic_bytes_per_launch': B * A_STEP_BYTES,
-            'kernel_ms_median': kernel_ms, 'traffic': None,
+            'kernel_ms_mean': kernel_ms,
+            'kernel_ms_flushed_event_pairs_median': kernel_ms_flushed_events,
+            'traffic': traffic.get('scrolly_maze_step', {}).get('bytes'),
+            'traffic_source': traffic.get('scrolly_maze_step', {}).get('source'),
             'layout_bytes_per_launch': B * LAYOUT_STEP_BYTES,
             'layout_achieved': layout, 'layout_frac': layout / peak},
         'cpu_baseline': {'value': cpu_value, 'unit': 'env-steps/s', 'cores': 1,
                          'kind': 'port',
                          'sample': '%d env-steps of one oracle env on the same generated '
                                    '64x64 levels' % cpu_steps},
+        'render_roofline': dict(render_roofline(render_ms, B, eng, peak),
+                                traffic=traffic.get('render_kernel', {}).get('bytes')),
         'wall_s_timed_region': wall, 'env_errors': errors}))
   if world > 1:
     dist.destroy_process_group()

@@ -103,7 +103,7 @@ typedef struct pcl_spec {
   int32_t n_sprites, n_drapes;
   int32_t auto_reset;            /* 1: an env that is game-over is rebuilt by the next step */
   int32_t pattern_rows, pattern_cols; /* Scrolly whole_pattern shape (drapes.py:338-343) */
-  int32_t pattern_words;         /* uint32 words per bit-packed pattern row (>= cols/32 + 2) */
+  int32_t pattern_words;         /* uint32 words per bit-packed pattern row: >= ceil(cols/32) + 2 (zero padded) */
   int32_t bits_words;            /* uint32 words per bit-packed board-sized row */
   uint8_t sprite_char[PCL_MAX_SPRITES];
   uint8_t drape_char[PCL_MAX_DRAPES];

@@ -108,15 +108,10 @@ __device__ __forceinline__ void walker_teleport(Sprite& s, int H, int W, int vr,
 __constant__ int kMotionDr[9] = {-1, -1, 0, 1, 1, 1, 0, -1, 0};
 __constant__ int kMotionDc[9] = {0, 1, 1, 1, 0, -1, -1, -1, 0};
 
-__device__ __forceinline__ int motion_dr(int m) {
-  // N NE E SE S SW W NW STAY
-  return (m == PCL_M_N || m == PCL_M_NE || m == PCL_M_NW) ? -1
-       : (m == PCL_M_S || m == PCL_M_SE || m == PCL_M_SW) ? 1 : 0;
-}
-__device__ __forceinline__ int motion_dc(int m) {
-  return (m == PCL_M_E || m == PCL_M_NE || m == PCL_M_SE) ? 1
-       : (m == PCL_M_W || m == PCL_M_NW || m == PCL_M_SW) ? -1 : 0;
-}
+// (drow, dcol) of a motion code, two bits per code packed in a constant:
+// N NE E SE S SW W NW STAY -> drow+1 = 0 0 1 2 2 2 1 0 1, dcol+1 = 1 2 2 2 1 0 0 0 1.
+__device__ __forceinline__ int motion_dr(int m) { return ((0x11A90 >> (2 * m)) & 3) - 1; }
+__device__ __forceinline__ int motion_dc(int m) { return ((0x101A9 >> (2 * m)) & 3) - 1; }
 
 // 3x3 neighbourhood "blocked" mask around the walker's VIRTUAL position: bit
 // (dr+1)*3 + (dc+1).  Lane k < 9 evaluates one neighbour with `cell_blocked(r,

@@ -14,15 +14,19 @@ namespace pcl {
 
 namespace {
 
-constexpr int kRenderThreads = 128;
+constexpr int kRenderThreads = 256;
 
+template <int MAXD, int MAXS>
 struct RenderShared {
-  int rank_s[PCL_MAX_SPRITES];
-  int rank_d[PCL_MAX_DRAPES];
-  int row[PCL_MAX_SPRITES], col[PCL_MAX_SPRITES], vis[PCL_MAX_SPRITES];
+  uint32_t rank_d[MAXD];          // z rank of each drape, replicated in 4 bytes
+  uint32_t rank_s[MAXS];
+  int seg[MAXS];                  // 16-byte segment holding each visible sprite, or -1
+  int word[MAXS];                 // which 32-bit word of the segment
+  uint32_t cover[MAXS];           // 0xff at the sprite's byte
 };
 
-// Where `take` (0x00/0xff per byte) is set, write ch4 / rank4.
+// Where `cover` (0x00/0xff per byte) is set and the rank is higher, write
+// ch4 / rank4 (later z-order entries paint over earlier ones, engine.py:751).
 __device__ __forceinline__ void overlay(uint32_t& px, uint32_t& rk, uint32_t cover,
                                         uint32_t ch4, uint32_t rank4) {
   const uint32_t take = cover & __vcmpltu4(rk, rank4);
@@ -30,47 +34,58 @@ __device__ __forceinline__ void overlay(uint32_t& px, uint32_t& rk, uint32_t cov
   rk = (rk & ~take) | (rank4 & take);
 }
 
+template <int MAXD, int MAXS>
 __global__ void __launch_bounds__(kRenderThreads)
 render_kernel(const RenderParams p) {
-  __shared__ RenderShared sh;
+  __shared__ RenderShared<MAXD, MAXS> sh;
   const int env = blockIdx.x;
   const int n = p.S + p.D;
-  // Decode this env's z-order (engine.py:751: later entries paint over earlier).
-  if (threadIdx.x < n) {
-    const uint8_t ch = p.z_order[(int64_t)env * n + threadIdx.x];
-    for (int s = 0; s < p.S; ++s) if (p.sprite_char[s] == ch) sh.rank_s[s] = threadIdx.x + 1;
-    for (int d = 0; d < p.D; ++d) if (p.drape_char[d] == ch) sh.rank_d[d] = threadIdx.x + 1;
-  }
-  if (threadIdx.x < p.S) {
-    const int32_t* rec = p.sprites + ((int64_t)env * p.S + threadIdx.x) * PCL_SPRITE_WORDS;
-    sh.row[threadIdx.x] = rec[PCL_S_ROW];
-    sh.col[threadIdx.x] = rec[PCL_S_COL];
-    sh.vis[threadIdx.x] = rec[PCL_S_FLAGS] & 1;
-  }
-  __syncthreads();
-
+  const int segs_per_row = p.pitch >> 4;
   const uint8_t* backdrop = p.backdrop + (int64_t)env * p.backdrop_bstride;
   const int64_t plane = (int64_t)p.H * p.pitch;
   const uint8_t* curtains = p.curtains + (int64_t)env * p.D * plane;
   uint8_t* board = p.board + (int64_t)env * plane;
-  const int segs_per_row = p.pitch >> 4;
   const int total = p.H * segs_per_row;
 
-  for (int seg = threadIdx.x; seg < total; seg += kRenderThreads) {
-    const int r = seg / segs_per_row;
-    const int c0 = (seg - r * segs_per_row) << 4;
-    const int64_t off = (int64_t)r * p.pitch + c0;
-    uint4 px = __ldg(reinterpret_cast<const uint4*>(backdrop + off));
-    uint4 cur[PCL_MAX_DRAPES];
+  // Issue the tile loads of the first segment before anything else: they do not
+  // depend on the z-order / sprite decode below, so both round trips overlap.
+  int seg = threadIdx.x;
+  uint4 px = make_uint4(0, 0, 0, 0);
+  uint4 cur[MAXD];
+  if (seg < total) {
+    const int64_t off = (int64_t)seg << 4;
+    px = __ldg(reinterpret_cast<const uint4*>(backdrop + off));
 #pragma unroll
-    for (int d = 0; d < PCL_MAX_DRAPES; ++d)
+    for (int d = 0; d < MAXD; ++d)
       if (d < p.D) cur[d] = __ldg(reinterpret_cast<const uint4*>(curtains + d * plane + off));
+  }
+
+  // Decode this env's z-order and sprite cells once per block.
+  if (threadIdx.x < n) {
+    const uint8_t ch = p.z_order[(int64_t)env * n + threadIdx.x];
+    const uint32_t rank4 = (threadIdx.x + 1) * 0x01010101u;
+#pragma unroll
+    for (int s = 0; s < MAXS; ++s) if (s < p.S && p.sprite_char[s] == ch) sh.rank_s[s] = rank4;
+#pragma unroll
+    for (int d = 0; d < MAXD; ++d) if (d < p.D && p.drape_char[d] == ch) sh.rank_d[d] = rank4;
+  }
+  if (threadIdx.x < p.S) {
+    const int32_t* rec = p.sprites + ((int64_t)env * p.S + threadIdx.x) * PCL_SPRITE_WORDS;
+    const int row = rec[PCL_S_ROW], col = rec[PCL_S_COL];
+    const bool vis = rec[PCL_S_FLAGS] & 1;                     // engine.py:754
+    sh.seg[threadIdx.x] = vis ? row * segs_per_row + (col >> 4) : -1;
+    sh.word[threadIdx.x] = (col & 15) >> 2;
+    sh.cover[threadIdx.x] = 0xffu << ((col & 3) * 8);
+  }
+  __syncthreads();
+
+  while (seg < total) {
     uint4 rk = make_uint4(0, 0, 0, 0);
 #pragma unroll
-    for (int d = 0; d < PCL_MAX_DRAPES; ++d) {
+    for (int d = 0; d < MAXD; ++d) {
       if (d < p.D) {
         const uint32_t ch4 = p.drape_char[d] * 0x01010101u;
-        const uint32_t r4 = sh.rank_d[d] * 0x01010101u;
+        const uint32_t r4 = sh.rank_d[d];
         overlay(px.x, rk.x, __vcmpne4(cur[d].x, 0), ch4, r4);   // rendering.py:160
         overlay(px.y, rk.y, __vcmpne4(cur[d].y, 0), ch4, r4);
         overlay(px.z, rk.z, __vcmpne4(cur[d].z, 0), ch4, r4);
@@ -78,22 +93,26 @@ render_kernel(const RenderParams p) {
       }
     }
 #pragma unroll
-    for (int s = 0; s < PCL_MAX_SPRITES; ++s) {
-      if (s < p.S) {
-        const int dc = sh.col[s] - c0;
-        if (sh.vis[s] && sh.row[s] == r && (unsigned)dc < 16u) {     // rendering.py:139
-          const uint32_t cover = 0xffu << ((dc & 3) * 8);
-          const uint32_t ch4 = p.sprite_char[s] * 0x01010101u;
-          const uint32_t r4 = sh.rank_s[s] * 0x01010101u;
-          const int w = dc >> 2;
-          if (w == 0) overlay(px.x, rk.x, cover, ch4, r4);
-          else if (w == 1) overlay(px.y, rk.y, cover, ch4, r4);
-          else if (w == 2) overlay(px.z, rk.z, cover, ch4, r4);
-          else overlay(px.w, rk.w, cover, ch4, r4);
-        }
+    for (int s = 0; s < MAXS; ++s) {
+      if (s < p.S && sh.seg[s] == seg) {                         // rendering.py:139
+        const uint32_t ch4 = p.sprite_char[s] * 0x01010101u;
+        const uint32_t r4 = sh.rank_s[s], cover = sh.cover[s];
+        const int w = sh.word[s];
+        if (w == 0) overlay(px.x, rk.x, cover, ch4, r4);
+        else if (w == 1) overlay(px.y, rk.y, cover, ch4, r4);
+        else if (w == 2) overlay(px.z, rk.z, cover, ch4, r4);
+        else overlay(px.w, rk.w, cover, ch4, r4);
       }
     }
-    *reinterpret_cast<uint4*>(board + off) = px;
+    *reinterpret_cast<uint4*>(board + ((int64_t)seg << 4)) = px;
+    seg += kRenderThreads;
+    if (seg < total) {
+      const int64_t off = (int64_t)seg << 4;
+      px = __ldg(reinterpret_cast<const uint4*>(backdrop + off));
+#pragma unroll
+      for (int d = 0; d < MAXD; ++d)
+        if (d < p.D) cur[d] = __ldg(reinterpret_cast<const uint4*>(curtains + d * plane + off));
+    }
   }
 }
 
@@ -190,7 +209,12 @@ __global__ void __launch_bounds__(128) crop_kernel(const CropParams p) {
 }  // namespace
 
 cudaError_t launch_render(const RenderParams& p, cudaStream_t s) {
-  render_kernel<<<p.B, kRenderThreads, 0, s>>>(p);
+  // Loop bounds are compile-time so the per-segment code stays small.
+  if (p.D <= 2 && p.S <= 4) render_kernel<2, 4><<<p.B, kRenderThreads, 0, s>>>(p);
+  else if (p.D <= 2 && p.S <= 8) render_kernel<2, 8><<<p.B, kRenderThreads, 0, s>>>(p);
+  else if (p.D <= 2) render_kernel<2, 16><<<p.B, kRenderThreads, 0, s>>>(p);
+  else if (p.S <= 4) render_kernel<8, 4><<<p.B, kRenderThreads, 0, s>>>(p);
+  else render_kernel<8, 16><<<p.B, kRenderThreads, 0, s>>>(p);
   return cudaGetLastError();
 }
 cudaError_t launch_export_curtain(const ExportParams& p, cudaStream_t s) {

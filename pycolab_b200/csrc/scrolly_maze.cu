@@ -9,8 +9,25 @@
 // read between groups are the <= 9 neighbours of a MazeWalker, tested against
 // impassable = '#', and in z-order 'abc@#P' a cell shows '#' iff the wall
 // curtain covers it and the (previously rendered) player is not standing on
-// it.  Those few look-ups are answered straight from the bit-packed wall
-// pattern, one lane per neighbour.
+// it.
+//
+// Memory schedule (one warp per env, everything staged through shared memory):
+//   1. records (sprites/drapes/plot, 64 words) -> smem with two coalesced loads;
+//      only the fields this game uses are pulled into registers;
+//   2. group 0 ('#' MazeDrape) is pure register arithmetic and fixes BOTH
+//      final window corners (the '@' drape can only obey an order, never issue
+//      one: by the time it runs, the player's permit is already for frame+1);
+//   3. one batch of loads is issued for everything else the step will read:
+//        - cp.async: the backdrop tile and the two 64-row windows of the
+//          bit-packed patterns (3 words per row) -> smem, no registers held;
+//        - plain loads: a 5x5 patch of wall bits around each of the 4 walkers
+//          (covers every cell any _check_motion of this step can consult,
+//          wherever the scroll order moves the walker first) and the 3x3 patch
+//          of coin bits around the player, one cell per lane, 4 per lane;
+//   4. groups 1 and 2 run on registers + ballots of those bits;
+//   5. the paint loop composes 16-byte board segments from smem and streams
+//      them out with uint4 stores; records go back with two coalesced stores.
+// So a step costs ~two dependent DRAM round trips (records, then everything).
 //
 // Sprite order P,a,b,c (indices 0..3); drape order '#','@' (0, 1).
 // Registers: patroller aux0 = moving_east; P aux0/aux1 = scroll permit mask /
@@ -26,63 +43,136 @@ namespace {
 
 constexpr int kS = 4;
 constexpr int kWarpsPerBlock = 4;
+constexpr int kRecWords = 64;     // 4 sprites * 8 + 2 drapes * 8 + plot 16
 
 __device__ __forceinline__ int action_to_motion(int a) {   // scrolly_maze.py:262-271
   return a == 0 ? PCL_M_N : a == 1 ? PCL_M_S : a == 2 ? PCL_M_W
        : a == 3 ? PCL_M_E : a == 4 ? PCL_M_STAY : PCL_M_NONE;
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::
+               "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::
+               "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// 16 window bits starting at bit `off` (< 80) of a 3-word staged row.
+__device__ __forceinline__ unsigned window16(const uint32_t* row3, int off) {
+  const int w = off >> 5, sh = off & 31;
+  const uint32_t lo = row3[w];
+  const uint32_t hi = row3[w < 2 ? w + 1 : 2];
+  return __funnelshift_r(lo, hi, sh) & 0xffffu;
+}
+
+__device__ __forceinline__ size_t warp_smem_bytes(int H, int pitch) {
+  return kRecWords * 4 + (size_t)H * pitch + 2 * (((size_t)H * 12 + 15) & ~(size_t)15);
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 7)
 scrolly_maze_step(const StepParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  // Byte-permute selectors for 4 cells at once: index = wall nibble << 4 | coin
+  // nibble; selector nibble k picks byte 5 ('#') if wall_k, else byte 4 ('@') if
+  // coin_k, else byte k of the backdrop word (z-order ... '@' '#' ...).
+  __shared__ uint16_t s_sel[256];
+  for (int idx = threadIdx.x; idx < 256; idx += blockDim.x) {
+    unsigned sel = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned nib = ((idx >> (4 + k)) & 1) ? 5u : ((idx >> k) & 1) ? 4u : (unsigned)k;
+      sel |= nib << (4 * k);
+    }
+    s_sel[idx] = (uint16_t)sel;
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int env = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int warp = threadIdx.x >> 5;
+  const int env = blockIdx.x * kWarpsPerBlock + warp;
   if (env >= p.B) return;
-  const int H = p.H, W = p.W;
+  const int H = p.H, W = p.W, PWW = p.PWW;
+
+  uint8_t* my = smem_raw + warp * warp_smem_bytes(H, p.pitch);
+  int32_t* rec = reinterpret_cast<int32_t*>(my);
+  uint8_t* s_bd = my + kRecWords * 4;
+  uint32_t* s_wall = reinterpret_cast<uint32_t*>(s_bd + (size_t)H * p.pitch);
+  uint32_t* s_coin = s_wall + ((H * 3 + 3) & ~3);
 
   int32_t* g_sprites = p.st.d_sprites + (int64_t)env * kS * PCL_SPRITE_WORDS;
   int32_t* g_drapes = p.st.d_drapes + (int64_t)env * 2 * PCL_DRAPE_WORDS;
   int32_t* g_plot = p.st.d_plot + (int64_t)env * PCL_PLOT_WORDS;
   const uint32_t* wall_pat = p.st.d_pattern[0] + (int64_t)env * p.st.pattern_bstride[0];
   uint32_t* coin_pat = p.st.d_pattern[1] + (int64_t)env * p.st.pattern_bstride[1];
+  const uint8_t* backdrop = p.st.d_backdrop + (int64_t)env * p.st.backdrop_bstride;
 
-  Plot plot = load_record_rw<Plot>(g_plot);
-
-  // ---- which envs run, and do they restart?  (engine.py:520-581, 619-624)
-  bool restart;
+  // ---- 1. records -> smem (coalesced) ------------------------------------
+  rec[lane] = g_sprites[lane];
+  rec[32 + lane] = lane < 16 ? g_drapes[lane] : g_plot[lane - 16];
+  __syncwarp();
+  const int was_over = rec[48 + PCL_P_GAME_OVER];
+  bool restart;                              // engine.py:520-581, 619-624
   if (p.mode == MODE_RESET) {
     restart = (p.env_mask == nullptr) || (p.env_mask[env] != 0);
     if (!restart) return;
   } else {
-    restart = plot.game_over && p.auto_reset;
-    if (plot.game_over && !p.auto_reset) return;   // reference raises; env stays frozen
+    restart = was_over && p.auto_reset;
+    if (was_over && !p.auto_reset) return;   // reference raises; env stays frozen
   }
-
-  Sprite sp[kS];
-  Drape walls, coins;
   int action;
   if (restart) {
-    const int episodes = plot.episodes, error = plot.error;
-    plot = load_record<Plot>(p.st.d_plot_init + (int64_t)env * p.st.plot_init_bstride);
-    plot.episodes = episodes + 1;
-    plot.error = error;
+    const int episodes = rec[48 + PCL_P_EPISODES], error = rec[48 + PCL_P_ERROR];
+    __syncwarp();
     const int32_t* si = p.st.d_sprites_init + (int64_t)env * p.st.sprites_init_bstride;
-#pragma unroll
-    for (int i = 0; i < kS; ++i) sp[i] = load_record<Sprite>(si + i * PCL_SPRITE_WORDS);
     const int32_t* di = p.st.d_drapes_init + (int64_t)env * p.st.drapes_init_bstride;
-    walls = load_record<Drape>(di);
-    coins = load_record<Drape>(di + PCL_DRAPE_WORDS);
+    const int32_t* pi = p.st.d_plot_init + (int64_t)env * p.st.plot_init_bstride;
+    rec[lane] = __ldg(si + lane);
+    rec[32 + lane] = lane < 16 ? __ldg(di + lane) : __ldg(pi + lane - 16);
     // Fresh coins: restore the mutable pattern (one Engine per episode).
     const uint32_t* src = p.st.d_pattern_init[1] + (int64_t)env * p.st.pattern_init_bstride[1];
-    const int n = p.PH * p.PWW;
+    const int n = p.PH * PWW;
     for (int i = lane; i < n; i += 32) coin_pat[i] = __ldg(src + i);
+    __syncwarp();
+    if (lane == 0) { rec[48 + PCL_P_EPISODES] = episodes + 1; rec[48 + PCL_P_ERROR] = error; }
     __syncwarp();
     action = PCL_ACTION_NONE;
   } else {
-#pragma unroll
-    for (int i = 0; i < kS; ++i) sp[i] = load_record_rw<Sprite>(g_sprites + i * PCL_SPRITE_WORDS);
-    walls = load_record_rw<Drape>(g_drapes);
-    coins = load_record_rw<Drape>(g_drapes + PCL_DRAPE_WORDS);
     action = p.actions[(int64_t)env * p.actions_per_env];
+  }
+
+  // ---- only the fields this game uses live in registers ------------------
+  Sprite sp[kS];
+#pragma unroll
+  for (int i = 0; i < kS; ++i) {
+    const int32_t* r = rec + i * PCL_SPRITE_WORDS;
+    sp[i].row = r[PCL_S_ROW]; sp[i].col = r[PCL_S_COL];
+    sp[i].vrow = r[PCL_S_VROW]; sp[i].vcol = r[PCL_S_VCOL];
+    sp[i].flags = r[PCL_S_FLAGS]; sp[i].aux0 = r[PCL_S_AUX0];
+    sp[i].aux1 = (i == 0) ? r[PCL_S_AUX1] : 0; sp[i].aux2 = 0;
+  }
+  Drape walls, coins;
+  {
+    const int32_t* r = rec + 32;
+    walls.corner_r = r[PCL_D_CORNER_R]; walls.corner_c = r[PCL_D_CORNER_C];
+    walls.pre_r = r[PCL_D_PRE_R]; walls.pre_c = r[PCL_D_PRE_C];
+    walls.last_frame = r[PCL_D_LAST_FRAME];
+    r += PCL_DRAPE_WORDS;
+    coins.corner_r = r[PCL_D_CORNER_R]; coins.corner_c = r[PCL_D_CORNER_C];
+    coins.pre_r = r[PCL_D_PRE_R]; coins.pre_c = r[PCL_D_PRE_C];
+    coins.last_frame = r[PCL_D_LAST_FRAME];
+    coins.aux0 = r[PCL_D_AUX0]; coins.aux1 = r[PCL_D_AUX1];
+  }
+  Plot plot;
+  {
+    const int32_t* r = rec + 48;
+    plot.frame = r[PCL_P_FRAME]; plot.error = r[PCL_P_ERROR];
+    plot.order_r = r[PCL_P_ORDER_R]; plot.order_c = r[PCL_P_ORDER_C];
+    plot.order_frame = r[PCL_P_ORDER_FRAME]; plot.ego_mask = r[PCL_P_EGO_MASK];
+    plot.aux0 = r[PCL_P_AUX0];
   }
 
   const ScrollyCfg wcfg = scrolly_cfg(H, W, p.PH, p.PW, p.margin[0][0], p.margin[0][1]);
@@ -92,57 +182,124 @@ scrolly_maze_step(const StepParams p) {
 
   plot.frame += 1;                                           // engine.py:716
 
-  // ---- update group 0: '#' MazeDrape (scrolly_maze.py:308-329)
+  // ---- 2. update group 0: '#' MazeDrape (scrolly_maze.py:308-329) --------
   if (motion != PCL_M_NONE) scrolly_move(walls, wcfg, motion, plot, sp);
+  const bool ordered = plot.order_frame == plot.frame;
+  const int wr = walls.corner_r, wc = walls.corner_c;
+  // Where the '@' window will be after it obeys the same order (checked below).
+  const int cr_pred = coins.corner_r + (ordered && motion != PCL_M_NONE ? plot.order_r : 0);
+  const int cc_pred = coins.corner_c + (ordered && motion != PCL_M_NONE ? plot.order_c : 0);
+
+  // ---- 3. one batch of loads ---------------------------------------------
+  {
+    const int n16 = (H * p.pitch) >> 4;
+    for (int i = lane; i < n16; i += 32) cp_async16(s_bd + i * 16, backdrop + i * 16);
+    const int nrow = H * 3;
+    const int ww0 = wc >> 5, cw0 = cc_pred >> 5;
+    for (int i = lane; i < nrow; i += 32) {
+      const int r = i / 3, k = i - r * 3;
+      cp_async4(s_wall + i, wall_pat + (int64_t)(wr + r) * PWW + ww0 + k);
+      cp_async4(s_coin + i, coin_pat + (int64_t)(cr_pred + r) * PWW + cw0 + k);
+    }
+  }
+  // Walker start positions: every look-up below is relative to these.
+  int vr0[kS], vc0[kS];
+#pragma unroll
+  for (int i = 0; i < kS; ++i) { vr0[i] = sp[i].vrow; vc0[i] = sp[i].vcol; }
+  scrolly_touch_prescroll(coins, plot);      // '@' has not moved yet this frame
+  unsigned patch[4];                         // 128 look-up bits, one per (lane, round)
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int j = q * 32 + lane;
+    bool bit = false;
+    if (j < 100) {                           // wall patch of walker j / 25
+      const int i = j / 25, k = j - i * 25;
+      int vr = vr0[0], vc = vc0[0];
+#pragma unroll
+      for (int t = 1; t < kS; ++t) if (i == t) { vr = vr0[t]; vc = vc0[t]; }
+      const int pr = wr + vr + k / 5 - 2, pc = wc + vc + k % 5 - 2;
+      if ((unsigned)pr < (unsigned)p.PH && (unsigned)pc < (unsigned)p.PW)
+        bit = bit_at(wall_pat + (int64_t)pr * PWW, pc);
+    } else if (j < 110) {                    // coin patch around the player
+      const int k = j - 100;
+      int r = k < 9 ? vr0[0] + k / 3 - 1 : 0, c = k < 9 ? vc0[0] + k % 3 - 1 : 0;
+      if (on_board(r, c, H, W))
+        bit = bit_at(coin_pat + (int64_t)(coins.pre_r + r) * PWW, coins.pre_c + c);
+    }
+    patch[q] = __ballot_sync(PCL_FULL, bit);
+  }
+  unsigned wall5[kS];                        // 25-bit 5x5 patches
+  wall5[0] = patch[0] & 0x1ffffffu;
+  wall5[1] = __funnelshift_r(patch[0], patch[1], 25) & 0x1ffffffu;
+  wall5[2] = __funnelshift_r(patch[1], patch[2], 18) & 0x1ffffffu;
+  wall5[3] = __funnelshift_r(patch[2], patch[3], 11) & 0x1ffffffu;
+  const unsigned coin9 = (patch[3] >> 4) & 0x3ffu;     // 3x3 + the (0,0) cell
 
   // Board of render #1 as far as MazeWalkers care: is cell (r, c) a '#'?
   // P is still painted where the previous render put it.
   const bool p_vis = visible(sp[0]);
   const int p_row = sp[0].row, p_col = sp[0].col;
-  const int wr = walls.corner_r, wc = walls.corner_c;
-  auto is_wall = [&](int r, int c) -> bool {
-    if (p_vis && r == p_row && c == p_col) return false;
-    return bit_at(wall_pat + (int64_t)(wr + r) * p.PWW, wc + c);
-  };
 
-  // ---- update group 1: patrollers a, b, c then P
+  // ---- 4a. update group 1: patrollers a, b, c then P ---------------------
   const int p_vrow = sp[0].vrow, p_vcol = sp[0].vcol;   // P moves after them
 #pragma unroll
-  for (int i = 1; i < kS; ++i) {                             // PatrollerSprite :284-305
-    if (plot.frame % 2) {
-      walker_move(sp[i], i, PCL_M_STAY, plot, H, W, false, false, lane, is_wall);
-    } else {
-      scrolly_touch_prescroll(walls, plot);
-      int pr = sp[i].vrow + walls.pre_r;
-      int pc = sp[i].vcol + walls.pre_c + (sp[i].aux0 ? 1 : -1);
-      // NumPy indexing: negatives wrap once, anything else is an IndexError.
-      if (pr < 0) pr += p.PH;
-      if (pc < 0) pc += p.PW;
-      bool next_to_wall = false;
-      if ((unsigned)pr < (unsigned)p.PH && (unsigned)pc < (unsigned)p.PW)
-        next_to_wall = bit_at(wall_pat + (int64_t)pr * p.PWW, pc);
-      else
-        plot.error |= PCL_ENV_ERR_INDEX;
-      if (next_to_wall) sp[i].aux0 = !sp[i].aux0;
-      walker_move(sp[i], i, sp[i].aux0 ? PCL_M_E : PCL_M_W, plot, H, W, false, false,
-                  lane, is_wall);
-      if (sp[i].vrow == p_vrow && sp[i].vcol == p_vcol) terminate(dir);
+  for (int i = 0; i < kS; ++i) {
+    const int idx = (i + 1) & 3;             // order a, b, c, P = 1, 2, 3, 0
+    const unsigned field = wall5[idx];
+    const int r0 = vr0[idx], c0 = vc0[idx];
+    auto is_wall = [&](int r, int c) -> bool {
+      if (p_vis && r == p_row && c == p_col) return false;
+      const int dr = r - r0 + 2, dc = c - c0 + 2;
+      if ((unsigned)dr > 4u || (unsigned)dc > 4u) return false;   // cannot happen
+      return (field >> (dr * 5 + dc)) & 1u;
+    };
+    if (idx != 0) {                          // PatrollerSprite :284-305
+      if (plot.frame % 2) {
+        walker_move(sp[idx], idx, PCL_M_STAY, plot, H, W, false, false, lane, is_wall);
+      } else {
+        scrolly_touch_prescroll(walls, plot);
+        const int step = sp[idx].aux0 ? 1 : -1;
+        int pr = r0 + walls.pre_r, pc = c0 + walls.pre_c + step;
+        bool next_to_wall = false;
+        if ((unsigned)pr < (unsigned)p.PH && (unsigned)pc < (unsigned)p.PW) {
+          // Same cell seen from the post-scroll corner: inside the 5x5 patch.
+          const int dr = pr - wr - r0 + 2, dc = pc - wc - c0 + 2;
+          next_to_wall = (field >> (dr * 5 + dc)) & 1u;
+        } else {
+          // NumPy indexing: negatives wrap once, anything else is an IndexError.
+          if (pr < 0) pr += p.PH;
+          if (pc < 0) pc += p.PW;
+          if ((unsigned)pr < (unsigned)p.PH && (unsigned)pc < (unsigned)p.PW)
+            next_to_wall = bit_at(wall_pat + (int64_t)pr * PWW, pc);
+          else
+            plot.error |= PCL_ENV_ERR_INDEX;
+        }
+        if (next_to_wall) sp[idx].aux0 = !sp[idx].aux0;
+        walker_move(sp[idx], idx, sp[idx].aux0 ? PCL_M_E : PCL_M_W, plot, H, W, false,
+                    false, lane, is_wall);
+        if (sp[idx].vrow == p_vrow && sp[idx].vcol == p_vcol) terminate(dir);
+      }
+    } else if (motion != PCL_M_NONE) {       // PlayerSprite :258-271
+      walker_move(sp[0], 0, motion, plot, H, W, false, true, lane, is_wall);
     }
   }
-  if (motion != PCL_M_NONE)                                  // PlayerSprite :258-271
-    walker_move(sp[0], 0, motion, plot, H, W, false, true, lane, is_wall);
 
-  // ---- update group 2: '@' CashDrape (scrolly_maze.py:341-364)
-  scrolly_touch_prescroll(coins, plot);
+  // ---- 4b. update group 2: '@' CashDrape (scrolly_maze.py:341-364) -------
+  int picked_r = -1, picked_c = -1;          // pattern cell cleared this frame
   {
+    const int dr = sp[0].row - vr0[0], dc = sp[0].col - vc0[0];
+    bool coin;
     const int pr = coins.pre_r + sp[0].row, pc = coins.pre_c + sp[0].col;
-    uint32_t* word = coin_pat + (int64_t)pr * p.PWW + (pc >> 5);
-    const uint32_t w = *word;
-    if ((w >> (pc & 31)) & 1u) {
+    if (sp[0].row == 0 && sp[0].col == 0 && !on_board(sp[0].vrow, sp[0].vcol, H, W))
+      coin = (coin9 >> 9) & 1u;              // off-board player sits at (0, 0)
+    else if ((unsigned)(dr + 1) <= 2u && (unsigned)(dc + 1) <= 2u)
+      coin = (coin9 >> ((dr + 1) * 3 + dc + 1)) & 1u;
+    else
+      coin = bit_at(coin_pat + (int64_t)pr * PWW, pc);   // cannot happen
+    if (coin) {
       add_reward(dir, 100);
-      __syncwarp();
-      if (lane == 0) *word = w & ~(1u << (pc & 31));
-      __syncwarp();
+      if (lane == 0) coin_pat[(int64_t)pr * PWW + (pc >> 5)] &= ~(1u << (pc & 31));
+      picked_r = pr; picked_c = pc;
       plot.aux0 -= 1;
       if (plot.aux0 == 0) terminate(dir);
       coins.aux0 = sp[0].row; coins.aux1 = sp[0].col;   // stale until next refresh
@@ -156,41 +313,86 @@ scrolly_maze_step(const StepParams p) {
   }
 
   // ---- _apply_and_clear_plot (engine.py:761-847); no z-order changes here.
-  plot.game_over = dir.game_over;
+  cp_async_wait_all();
+  __syncwarp();
   if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < kS; ++i) store_record(g_sprites + i * PCL_SPRITE_WORDS, sp[i]);
-    store_record(g_drapes, walls);
-    store_record(g_drapes + PCL_DRAPE_WORDS, coins);
-    store_record(g_plot, plot);
+    for (int i = 0; i < kS; ++i) {
+      int32_t* r = rec + i * PCL_SPRITE_WORDS;
+      r[PCL_S_ROW] = sp[i].row; r[PCL_S_COL] = sp[i].col;
+      r[PCL_S_VROW] = sp[i].vrow; r[PCL_S_VCOL] = sp[i].vcol;
+      r[PCL_S_FLAGS] = sp[i].flags; r[PCL_S_AUX0] = sp[i].aux0;
+      if (i == 0) r[PCL_S_AUX1] = sp[i].aux1;
+    }
+    int32_t* r = rec + 32;
+    r[PCL_D_CORNER_R] = walls.corner_r; r[PCL_D_CORNER_C] = walls.corner_c;
+    r[PCL_D_PRE_R] = walls.pre_r; r[PCL_D_PRE_C] = walls.pre_c;
+    r[PCL_D_LAST_FRAME] = walls.last_frame;
+    r += PCL_DRAPE_WORDS;
+    r[PCL_D_CORNER_R] = coins.corner_r; r[PCL_D_CORNER_C] = coins.corner_c;
+    r[PCL_D_PRE_R] = coins.pre_r; r[PCL_D_PRE_C] = coins.pre_c;
+    r[PCL_D_LAST_FRAME] = coins.last_frame;
+    r[PCL_D_AUX0] = coins.aux0; r[PCL_D_AUX1] = coins.aux1;
+    r = rec + 48;
+    r[PCL_P_FRAME] = plot.frame; r[PCL_P_GAME_OVER] = dir.game_over;
+    r[PCL_P_ERROR] = plot.error;
+    r[PCL_P_ORDER_R] = plot.order_r; r[PCL_P_ORDER_C] = plot.order_c;
+    r[PCL_P_ORDER_FRAME] = plot.order_frame; r[PCL_P_EGO_MASK] = plot.ego_mask;
+    r[PCL_P_AUX0] = plot.aux0;
     p.out.d_reward[env] = dir.reward;
     p.out.d_has_reward[env] = (uint8_t)dir.has_reward;
     p.out.d_discount[env] = dir.discount;
     p.out.d_done[env] = (uint8_t)dir.game_over;
+    // The coin window was staged before the pick-up: clear the bit there too.
+    if (picked_r >= 0) {
+      const int r2 = picked_r - cr_pred, b = picked_c - ((cc_pred >> 5) << 5);
+      if ((unsigned)r2 < (unsigned)H && (unsigned)b < 96u)
+        s_coin[r2 * 3 + (b >> 5)] &= ~(1u << (b & 31));
+    }
   }
+  const int cr = coins.corner_r, cc = coins.corner_c;
+  if (cr != cr_pred || cc != cc_pred) {      // '@' issued its own order: restage
+    __syncwarp();
+    const int nrow = H * 3, cw0 = cc >> 5;
+    for (int i = lane; i < nrow; i += 32) {
+      const int r = i / 3, k = i - r * 3;
+      s_coin[i] = coin_pat[(int64_t)(cr + r) * PWW + cw0 + k];
+    }
+  }
+  __syncwarp();
+  g_sprites[lane] = rec[lane];
+  if (lane < 16) g_drapes[lane] = rec[32 + lane];
+  else g_plot[lane - 16] = rec[32 + lane];
 
-  // ---- final render, z-order a b c @ # P (engine.py:737-759)
-  const uint8_t* backdrop = p.st.d_backdrop + (int64_t)env * p.st.backdrop_bstride;
+  // ---- 5. final render, z-order a b c @ # P (engine.py:737-759) ----------
   uint8_t* board = p.out.d_board + (int64_t)env * H * p.pitch;
   const int segs_per_row = p.pitch >> 4;
   const int total = H * segs_per_row;
-  const int cr = coins.corner_r, cc = coins.corner_c;
-  const int wr2 = walls.corner_r, wc2 = walls.corner_c;
+  const int wsh = wc & 31, csh = cc & 31;
   const int stale_r = coins.aux0, stale_c = coins.aux1;
   for (int seg = lane; seg < total; seg += 32) {
     const int r = seg / segs_per_row;
     const int c0 = (seg - r * segs_per_row) << 4;
     const int ncols = min(16, W - c0);
     const unsigned valid = (1u << ncols) - 1u;
-    uint4 px = __ldg(reinterpret_cast<const uint4*>(backdrop + (int64_t)r * p.pitch + c0));
-    unsigned coin_bits = bits16(coin_pat + (int64_t)(cr + r) * p.PWW, cc + c0) & valid;
-    const unsigned wall_bits = bits16(wall_pat + (int64_t)(wr2 + r) * p.PWW, wc2 + c0) & valid;
+    uint4 px = *reinterpret_cast<const uint4*>(s_bd + (size_t)r * p.pitch + c0);
+    unsigned coin_bits = window16(s_coin + r * 3, csh + c0) & valid;
+    const unsigned wall_bits = window16(s_wall + r * 3, wsh + c0) & valid;
     if (r == stale_r && (unsigned)(stale_c - c0) < 16u) coin_bits |= 1u << (stale_c - c0);
 #pragma unroll
-    for (int i = 1; i < kS; ++i) paint_bits(px, sprite_bit(sp[i], r, c0), p.sprite_char[i]);
-    paint_bits(px, coin_bits, '@');
-    paint_bits(px, wall_bits, '#');
-    paint_bits(px, sprite_bit(sp[0], r, c0), p.sprite_char[0]);
+    for (int i = 1; i < kS; ++i) {           // a, b, c lie under both drapes
+      const unsigned m = sprite_bit(sp[i], r, c0);
+      if (m) paint_bits(px, m, p.sprite_char[i]);
+    }
+    const unsigned drape_chars = ('#' << 8) | '@';         // bytes 4 and 5 of the permute
+    px.x = __byte_perm(px.x, drape_chars, s_sel[((wall_bits & 0xfu) << 4) | (coin_bits & 0xfu)]);
+    px.y = __byte_perm(px.y, drape_chars, s_sel[(wall_bits & 0xf0u) | ((coin_bits >> 4) & 0xfu)]);
+    px.z = __byte_perm(px.z, drape_chars,
+                       s_sel[((wall_bits >> 4) & 0xf0u) | ((coin_bits >> 8) & 0xfu)]);
+    px.w = __byte_perm(px.w, drape_chars,
+                       s_sel[((wall_bits >> 8) & 0xf0u) | ((coin_bits >> 12) & 0xfu)]);
+    const unsigned m = sprite_bit(sp[0], r, c0);
+    if (m) paint_bits(px, m, p.sprite_char[0]);
     *reinterpret_cast<uint4*>(board + (int64_t)r * p.pitch + c0) = px;
   }
 }
@@ -198,8 +400,19 @@ scrolly_maze_step(const StepParams p) {
 }  // namespace
 
 cudaError_t launch_scrolly_maze(const StepParams& p, cudaStream_t s) {
+  if (p.W > 64) return cudaErrorInvalidValue;       // 3-word window rows
   const int blocks = (p.B + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  scrolly_maze_step<<<blocks, kWarpsPerBlock * 32, 0, s>>>(p);
+  const size_t per_warp = kRecWords * 4 + (size_t)p.H * p.pitch +
+                          2 * (((size_t)p.H * 12 + 15) & ~(size_t)15);
+  const size_t smem = per_warp * kWarpsPerBlock;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(scrolly_maze_step,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  scrolly_maze_step<<<blocks, kWarpsPerBlock * 32, smem, s>>>(p);
   return cudaGetLastError();
 }
 

@@ -249,7 +249,7 @@ def _lower_scrolly_maze(engine, roles):
   game.margins = [(-1, -1) if d._scroll_margins is None else tuple(d._scroll_margins)
                   for d in (walls, coins)]
   game.pattern_rows, game.pattern_cols = walls.whole_pattern.shape
-  game.pattern_words = (game.pattern_cols + 31) // 32 + 1
+  game.pattern_words = (game.pattern_cols + 31) // 32 + 2
   game.patterns = {0: pack_rows(walls.whole_pattern, game.pattern_words),
                    1: pack_rows(coins.whole_pattern, game.pattern_words)}
   game.pattern_mutable = {0: False, 1: True}
