@@ -56,6 +56,7 @@ typedef enum pcl_status {
 #define PCL_ENV_ERR_SECOND_ORDER     0x2  /* scrolling.py:518-521 */
 #define PCL_ENV_ERR_EMPTY_CHOICE     0x4  /* np.random.choice([]) in marauders :253 */
 #define PCL_ENV_ERR_INDEX            0x8  /* NumPy IndexError (board look-up off the array) */
+#define PCL_ENV_ERR_BAD_Z            0x10 /* change_z_order names a missing entity, engine.py:802-812 */
 
 /* Which game program advances the envs.  One fused kernel per program; the
  * host "lowering" recognises the reference's entity classes and picks one. */
@@ -115,6 +116,7 @@ typedef struct pcl_spec {
   int32_t n_groups;
   int32_t group_len[PCL_MAX_SPRITES + PCL_MAX_DRAPES];
   uint8_t group_chars[PCL_MAX_SPRITES + PCL_MAX_DRAPES]; /* update order, concatenated */
+  int32_t drape_kind[PCL_MAX_DRAPES];      /* 0 = plain bool curtain (d_bits), 1 = Scrolly (d_pattern) */
   int32_t reserved[8];
 } pcl_spec;
 
@@ -136,6 +138,9 @@ typedef struct pcl_state {
   int32_t* d_drapes;   const int32_t* d_drapes_init;  int64_t drapes_init_bstride;  /* [B, D, 8] */
   int32_t* d_plot;     const int32_t* d_plot_init;    int64_t plot_init_bstride;    /* [B, 16]   */
   uint32_t* d_rng;     /* MT19937 per env, u32 [B, PCL_MT_WORDS]; NULL if unused */
+  /* per-env z-order (chars, back to front) for programs whose entities issue
+   * Plot.change_z_order (engine.py:796-835): u8 [B, n_sprites + n_drapes]; NULL = spec z_order */
+  uint8_t* d_z_order;  const uint8_t* d_z_order_init; int64_t z_order_init_bstride;
 } pcl_state;
 
 /* Per-step outputs = the (observation, reward, discount) triple of
@@ -166,7 +171,10 @@ int pcl_reset(pcl_handle* h, const uint8_t* d_env_mask, const pcl_outputs* out,
 
 /* Engine.play(actions) (engine.py:583-639) for all envs in lockstep: one fused
  * kernel = _update_and_render + _apply_and_clear_plot.  d_actions is
- * i32 [B, actions_per_env] (actions_per_env = 1 for the example games). */
+ * i32 [B, actions_per_env]: actions_per_env = 1 for the example games;
+ * PCL_PROG_FIXTURE takes n_sprites + n_drapes + 4 words per env: one motion code
+ * per entity in update order, then reward (INT32_MIN = none), terminate (0/1),
+ * z_move_this (char or -1), z_in_front_of (char, 0 = None). */
 int pcl_step(pcl_handle* h, const int32_t* d_actions, const pcl_outputs* out,
              void* stream);
 

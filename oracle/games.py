@@ -348,3 +348,12 @@ def fixture_program(world, ch, actions):
     em.walker_move(ent, world.board, world.plot, motion)
   elif isinstance(ent, em.Scrolly):
     em.scrolly_move(ent, world, motion)
+  # Plot directives injected with test_things.post_update upstream
+  # (test_things.py:85-104): keys '_reward', '_terminate', '_z' = (this, that).
+  if isinstance(actions, dict) and ch == world.groups[-1][-1]:
+    if actions.get('_reward') is not None:
+      world.plot.add_reward(actions['_reward'])
+    if actions.get('_terminate'):
+      world.plot.terminate_episode()
+    if actions.get('_z') is not None:
+      world.plot.change_z_order(*actions['_z'])

@@ -26,6 +26,7 @@ ENV_ERR_ORDER_MISMATCH = 0x1
 ENV_ERR_SECOND_ORDER = 0x2
 ENV_ERR_EMPTY_CHOICE = 0x4
 ENV_ERR_INDEX = 0x8
+ENV_ERR_BAD_Z = 0x10
 
 PROG_NONE, PROG_SCROLLY_MAZE, PROG_WAREHOUSE, PROG_MARAUDERS, PROG_FIXTURE = 0, 1, 2, 3, 4
 
@@ -68,6 +69,7 @@ class Spec(C.Structure):
       ('n_groups', C.c_int32),
       ('group_len', C.c_int32 * _N),
       ('group_chars', C.c_uint8 * _N),
+      ('drape_kind', C.c_int32 * MAX_DRAPES),
       ('reserved', C.c_int32 * 8),
   ]
 
@@ -86,6 +88,8 @@ class State(C.Structure):
       ('drapes_init_bstride', C.c_int64),
       ('d_plot', C.c_void_p), ('d_plot_init', C.c_void_p), ('plot_init_bstride', C.c_int64),
       ('d_rng', C.c_void_p),
+      ('d_z_order', C.c_void_p), ('d_z_order_init', C.c_void_p),
+      ('z_order_init_bstride', C.c_int64),
   ]
 
 

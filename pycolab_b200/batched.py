@@ -126,6 +126,15 @@ class BatchedEngine(object):
     st.drapes_init_bstride = bstride(self._drapes_init)
     st.d_plot, st.d_plot_init = self.plot.data_ptr(), self._plot_init.data_ptr()
     st.plot_init_bstride = bstride(self._plot_init)
+    self.z_order = None
+    if g0.dynamic_z:
+      zs = [np.frombuffer(g.z_order.encode('ascii'), dtype=np.uint8) for g in games]
+      self.z_order = per_env(zs, np.uint8)
+      self._z_init = tiled(zs, np.uint8)
+      st.d_z_order, st.d_z_order_init = self.z_order.data_ptr(), self._z_init.data_ptr()
+      st.z_order_init_bstride = bstride(self._z_init)
+    self.actions_per_env = (len(g0.sprite_chars) + len(g0.drape_chars) + 4
+                            if g0.program == _lib.PROG_FIXTURE else 1)
     self.rng = None
     if g0.needs_rng:
       if rng_states is not None:
@@ -149,7 +158,7 @@ class BatchedEngine(object):
     self._out = _lib.Outputs(self._board.data_ptr(), self.reward.data_ptr(),
                              self.has_reward.data_ptr(), self.discount.data_ptr(),
                              self.done.data_ptr())
-    self._actions = torch.zeros((B,), dtype=torch.int32, device=dev)
+    self._actions = torch.zeros((B * self.actions_per_env,), dtype=torch.int32, device=dev)
     self._host = None           # pinned staging for play_host()
     self._crop_out = None
 
@@ -207,8 +216,9 @@ class BatchedEngine(object):
     if not (torch.is_tensor(actions) and actions.is_cuda and
             actions.dtype == torch.int32 and actions.is_contiguous()):
       actions = torch.as_tensor(actions, dtype=torch.int32).to(self.device).contiguous()
-    if actions.numel() != self.batch:
-      raise ValueError('expected %d actions, got %d' % (self.batch, actions.numel()))
+    if actions.numel() != self.batch * self.actions_per_env:
+      raise ValueError('expected %d action words, got %d' % (
+          self.batch * self.actions_per_env, actions.numel()))
     _lib.check(self._lib.pcl_step(self._h, actions.data_ptr(), C.byref(self._out),
                                   self._stream()), 'pcl_step')
     return self._result()
@@ -217,7 +227,7 @@ class BatchedEngine(object):
     """T back-to-back steps; actions int32 [T, B] on the device."""
     torch = _torch()
     assert actions.is_cuda and actions.dtype == torch.int32 and actions.is_contiguous()
-    assert actions.dim() == 2 and actions.shape[1] == self.batch
+    assert actions.dim() >= 2 and actions[0].numel() == self.batch * self.actions_per_env
     _lib.check(self._lib.pcl_run(self._h, actions.data_ptr(), int(actions.shape[0]),
                                  C.byref(self._out), self._stream()), 'pcl_run')
     return self._result()
@@ -230,13 +240,13 @@ class BatchedEngine(object):
     if self._host is None:
       pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()
       self._host = dict(
-          actions=pin((self.batch,), torch.int32),
+          actions=pin((self.batch * self.actions_per_env,), torch.int32),
           board=pin((self.batch, self.rows, self.pitch), torch.uint8),
           reward=pin((self.batch,), torch.int32), has_reward=pin((self.batch,), torch.uint8),
           discount=pin((self.batch,), torch.float32), done=pin((self.batch,), torch.uint8))
       self._host_np = {k: v.numpy() for k, v in self._host.items()}
     h = self._host
-    self._host_np['actions'][:] = actions
+    self._host_np['actions'][:] = np.asarray(actions, dtype=np.int32).reshape(-1)
     _lib.check(self._lib.pcl_step_host(
         self._h, h['actions'].data_ptr(), self._actions.data_ptr(), C.byref(self._out),
         h['board'].data_ptr() if want_board else None, h['reward'].data_ptr(),

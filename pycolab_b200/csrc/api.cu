@@ -117,6 +117,33 @@ int validate(const pcl_spec& s) {
       }
       return PCL_OK;
     }
+    case PCL_PROG_FIXTURE: {
+      // Any MazeWalker / Scrolly / plain-drape mix; entities and z-order must
+      // be consistent permutations of each other.
+      const int n = s.n_sprites + s.n_drapes;
+      if (n < 1) return PCL_ERR_INVALID;
+      int total = 0;
+      for (int g = 0; g < s.n_groups; ++g) total += s.group_len[g];
+      if (s.n_groups < 1 || total != n) return PCL_ERR_INVALID;
+      for (int i = 0; i < n; ++i) {
+        int in_z = 0, in_groups = 0;
+        const uint8_t ch = i < s.n_sprites ? s.sprite_char[i] : s.drape_char[i - s.n_sprites];
+        for (int k = 0; k < n; ++k) {
+          in_z += s.z_order[k] == ch;
+          in_groups += s.group_chars[k] == ch;
+        }
+        if (in_z != 1 || in_groups != 1 || ch == 0 || ch > 127) return PCL_ERR_INVALID;
+      }
+      for (int d = 0; d < s.n_drapes; ++d) {
+        if (!s.drape_kind[d]) continue;
+        if (s.pattern_rows < s.rows || s.pattern_cols < s.cols) return PCL_ERR_INVALID;
+        if (s.pattern_words < (s.pattern_cols + 31) / 32 + 2) return PCL_ERR_INVALID;
+        const int mr = s.margins[d][0], mc = s.margins[d][1];
+        if (mr >= 0 && (mc - 1 >= s.cols - mc || mr - 1 >= s.rows - mr)) return PCL_ERR_INVALID;
+      }
+      if (s.bits_words < (s.cols + 31) / 32 + 1) return PCL_ERR_INVALID;
+      return PCL_OK;
+    }
     default:
       return PCL_ERR_UNSUPPORTED;
   }
@@ -137,6 +164,10 @@ void fill_params(const pcl_handle* h, StepParams* p) {
   memcpy(p->impassable, s.impassable, sizeof(p->impassable));
   memcpy(p->confined, s.sprite_confined, sizeof(p->confined));
   memcpy(p->egocentric, s.sprite_egocentric, sizeof(p->egocentric));
+  memcpy(p->drape_kind, s.drape_kind, sizeof(p->drape_kind));
+  p->n_groups = s.n_groups;
+  memcpy(p->group_len, s.group_len, sizeof(p->group_len));
+  memcpy(p->group_chars, s.group_chars, sizeof(p->group_chars));
   p->st = h->st;
 }
 
@@ -146,6 +177,7 @@ int launch(pcl_handle* h, const StepParams& p, cudaStream_t stream) {
     case PCL_PROG_SCROLLY_MAZE: e = pcl::launch_scrolly_maze(p, stream); break;
     case PCL_PROG_WAREHOUSE: e = pcl::launch_warehouse(p, stream); break;
     case PCL_PROG_MARAUDERS: e = pcl::launch_marauders(p, stream); break;
+    case PCL_PROG_FIXTURE: e = pcl::launch_fixture(p, stream); break;
     default: return PCL_ERR_UNSUPPORTED;
   }
   h->launches += 1;
@@ -194,7 +226,7 @@ int pcl_create(const pcl_spec* spec, int batch, int device, pcl_handle** out) {
   h->batch = batch;
   h->device = device;
   h->bound = 0;
-  h->actions_per_env = 1;
+  h->actions_per_env = spec->program == PCL_PROG_FIXTURE ? spec->n_sprites + spec->n_drapes + 4 : 1;
   h->launches = 0;
   *out = h;
   return PCL_OK;
@@ -218,6 +250,12 @@ int pcl_bind_state(pcl_handle* h, const pcl_state* st) {
     for (int d = 0; d < 2; ++d)
       if (!st->d_bits[d] || !st->d_bits_init[d] || st->bits_bstride[d] == 0) return PCL_ERR_INVALID;
     if (!st->d_rng) return PCL_ERR_INVALID;
+  }
+  if (h->spec.program == PCL_PROG_FIXTURE) {
+    if (!st->d_z_order || !st->d_z_order_init) return PCL_ERR_INVALID;
+    for (int d = 0; d < h->spec.n_drapes; ++d) {
+      if (h->spec.drape_kind[d] ? !st->d_pattern[d] : !st->d_bits[d]) return PCL_ERR_INVALID;
+    }
   }
   h->st = *st;
   h->bound = 1;
@@ -320,10 +358,15 @@ int pcl_export_curtain(pcl_handle* h, int drape_index, uint8_t* d_out, void* str
     p.bits = h->st.d_pattern[drape_index];
     p.bits_bstride = h->st.pattern_bstride[drape_index];
     if (drape_index == 1) p.stale_slot = 0;
-  } else if (h->spec.program == PCL_PROG_MARAUDERS) {
+  } else if (h->spec.program == PCL_PROG_MARAUDERS ||
+             (h->spec.program == PCL_PROG_FIXTURE && !h->spec.drape_kind[drape_index])) {
     p.scrolly = 0;
     p.bits = h->st.d_bits[drape_index];
     p.bits_bstride = h->st.bits_bstride[drape_index];
+  } else if (h->spec.program == PCL_PROG_FIXTURE) {
+    p.scrolly = 1;
+    p.bits = h->st.d_pattern[drape_index];
+    p.bits_bstride = h->st.pattern_bstride[drape_index];
   } else {
     return PCL_ERR_UNSUPPORTED;
   }

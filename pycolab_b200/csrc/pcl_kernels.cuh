@@ -23,6 +23,10 @@ struct StepParams {
   uint32_t impassable[PCL_MAX_SPRITES][4];
   int confined[PCL_MAX_SPRITES];
   int egocentric[PCL_MAX_SPRITES];
+  int drape_kind[PCL_MAX_DRAPES];
+  int n_groups;
+  int group_len[PCL_MAX_SPRITES + PCL_MAX_DRAPES];
+  uint8_t group_chars[PCL_MAX_SPRITES + PCL_MAX_DRAPES];
   pcl_state st;
   pcl_outputs out;
   const int32_t* actions;        // i32 [B, actions_per_env] (MODE_STEP)

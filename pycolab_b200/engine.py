@@ -142,8 +142,26 @@ class Engine(object):
     if self._game_over:
       raise RuntimeError('play() was called after the episode handled by this Engine '
                          'has terminated.')
+    if self._batched.game.program == _lib.PROG_FIXTURE:
+      return self._wrap(self._batched.play([self._fixture_row(actions)]))
     action = _lib.ACTION_NONE if actions is None else int(actions)
     return self._wrap(self._batched.play([action]))
+
+  _MOTION_NAMES = ('n', 'ne', 'e', 'se', 's', 'sw', 'w', 'nw')
+
+  def _fixture_row(self, actions):
+    """General-program action row from the fixture conventions
+    (tests/test_things.py:219-250): a direction string for everybody, or
+    {char: direction}; unknown / missing = stay.  Directive keys '_reward',
+    '_terminate', '_z' stand in for post_update code injection."""
+    from pycolab_b200.games import fixtures
+    code = lambda d: self._MOTION_NAMES.index(d) if d in self._MOTION_NAMES else 8
+    order = ''.join(self._batched.game.groups)
+    if isinstance(actions, dict):
+      motions = {ch: code(actions.get(ch)) for ch in order}
+      return fixtures.action_rows(self._batched.game, motions, actions.get('_reward'),
+                                  bool(actions.get('_terminate')), actions.get('_z'))
+    return fixtures.action_rows(self._batched.game, {ch: code(actions) for ch in order})
 
   def _wrap(self, result):
     import torch
@@ -163,6 +181,9 @@ class Engine(object):
                          'egocentric entity was to carry out in the same game iteration')
     if errors & _lib.ENV_ERR_EMPTY_CHOICE:
       raise ValueError("'a' cannot be empty unless no samples are taken")
+    if errors & _lib.ENV_ERR_BAD_Z:
+      raise RuntimeError('A z-order change directive named a Sprite or Drape that does '
+                         'not exist')
     if errors & _lib.ENV_ERR_INDEX:
       raise IndexError('a board look-up fell off the array')
     self._board = rendering.Observation(
@@ -175,6 +196,10 @@ class Engine(object):
     sprites = b.sprites[0].cpu().numpy()
     drapes = b.drapes[0].cpu().numpy()
     self._the_plot._frame = int(b.plot[0, _lib.P_FRAME])
+    if b.z_order is not None:             # Plot.change_z_order happened on the device
+      order = [chr(c) for c in b.z_order[0].cpu().numpy()]
+      self._sprites_and_drapes = collections.OrderedDict(
+          (ch, self._sprites_and_drapes[ch]) for ch in order)
     for i, ch in enumerate(b.sprite_chars):
       ent, rec = self._sprites_and_drapes[ch], sprites[i]
       ent._position = things.Sprite.Position(int(rec[_lib.S_ROW]), int(rec[_lib.S_COL]))

@@ -1,0 +1,77 @@
+"""General-purpose entities: plain MazeWalkers, Scrollys and static drapes.
+
+Counterparts of the reference's test fixtures (`pycolab/tests/test_things.py`:
+`TestMazeWalker` :203-250, `TestScrolly` :253-295, `TestDrape` :178-200): each
+entity simply performs the motion named by its action slot every frame
+(`_stay` when none is given).  Their per-step logic is the general device
+program csrc/fixture.cu (`PCL_PROG_FIXTURE`), which also accepts Plot
+directives (reward, termination, z-order change) as extra action words — the
+device stand-in for `test_things.post_update` code injection.
+
+`make_game` mirrors `oracle.games.make_fixture_world`, so one description
+builds the reference fixture game, the oracle world and the device game.
+"""
+
+import numpy as np
+
+from pycolab_b200 import ascii_art
+from pycolab_b200 import things as plab_things
+from pycolab_b200.prefab_parts import drapes as prefab_drapes
+from pycolab_b200.prefab_parts import sprites as prefab_sprites
+
+NO_REWARD = -(2 ** 31)
+
+
+class FixtureMazeWalker(prefab_sprites.MazeWalker):
+  def update(self, actions, board, layers, backdrop, things, the_plot):
+    raise NotImplementedError('runs on the device: csrc/fixture.cu')
+
+
+class FixtureScrolly(prefab_drapes.Scrolly):
+  def update(self, actions, board, layers, backdrop, things, the_plot):
+    raise NotImplementedError('runs on the device: csrc/fixture.cu')
+
+
+class FixtureDrape(plab_things.Drape):
+  def update(self, actions, board, layers, backdrop, things, the_plot):
+    raise NotImplementedError('runs on the device: csrc/fixture.cu')
+
+
+def make_game(art, what_lies_beneath, walkers, scrollys=None, drapes='',
+              update_schedule=None, z_order=None):
+  """walkers: {char: dict(impassable, confined, egocentric)}; scrollys:
+  {char: dict(pattern, corner, margins)}; drapes: chars of static drapes."""
+  scrollys = scrollys or {}
+  shape = (len(art), len(art[0]))
+  sprites = {
+      ch: ascii_art.Partial(FixtureMazeWalker, impassable=kw.get('impassable', ''),
+                            confined_to_board=kw.get('confined', False),
+                            egocentric_scroller=kw.get('egocentric', False))
+      for ch, kw in walkers.items()}
+  dr = {
+      ch: ascii_art.Partial(FixtureScrolly, board_shape=shape,
+                            whole_pattern=np.array(kw['pattern'], dtype=bool),
+                            board_northwest_corner=tuple(kw['corner']),
+                            scroll_margins=kw.get('margins', (2, 3)))
+      for ch, kw in scrollys.items()}
+  for ch in drapes:
+    dr[ch] = FixtureDrape
+  chars = list(walkers) + list(scrollys) + list(drapes)
+  if update_schedule is None:
+    update_schedule = [chars]
+  return ascii_art.ascii_art_to_game(art, what_lies_beneath, sprites, dr,
+                                     update_schedule=update_schedule, z_order=z_order)
+
+
+def action_rows(game_or_lowered, motions, reward=None, terminate=False, z=None):
+  """One device action row: motions {char: code} (missing = stay) in update
+  order, then the directive words."""
+  order = ''.join(game_or_lowered.groups)
+  row = [int(motions.get(ch, 8)) for ch in order]
+  row.append(NO_REWARD if reward is None else int(reward))
+  row.append(1 if terminate else 0)
+  if z is None:
+    row += [-1, 0]
+  else:
+    row += [ord(z[0]), 0 if z[1] is None else ord(z[1])]
+  return row

@@ -41,6 +41,13 @@ LOWERED_CLASSES = {
     ('extraterrestrial_marauders', 'MarauderDrape'): 'marauders.marauder',
     ('extraterrestrial_marauders', 'UpwardLaserBoltSprite'): 'marauders.up_bolt',
     ('extraterrestrial_marauders', 'DownwardLaserBoltSprite'): 'marauders.down_bolt',
+    # General entities: the reference's test fixtures and this package's twins.
+    ('test_things', 'TestMazeWalker'): 'fixture.walker',
+    ('test_things', 'TestScrolly'): 'fixture.scrolly',
+    ('test_things', 'TestDrape'): 'fixture.drape',
+    ('fixtures', 'FixtureMazeWalker'): 'fixture.walker',
+    ('fixtures', 'FixtureScrolly'): 'fixture.scrolly',
+    ('fixtures', 'FixtureDrape'): 'fixture.drape',
 }
 
 _PROGRAM_OF = {'scrolly': _lib.PROG_SCROLLY_MAZE, 'warehouse': _lib.PROG_WAREHOUSE,
@@ -122,6 +129,8 @@ class LoweredGame(object):
     self.plot = None            # i32 [16]
     self.needs_rng = False
     self.backdrop_chars = ''
+    self.drape_kind = None      # per drape: 1 = Scrolly (fixture program only)
+    self.dynamic_z = False      # per-env z-order array (Plot.change_z_order)
 
   def signature(self):
     """Everything that must agree between envs sharing one handle."""
@@ -148,6 +157,8 @@ class LoweredGame(object):
     for i, ch in enumerate(self.drape_chars):
       s.drape_char[i] = ord(ch)
       s.margins[i][0], s.margins[i][1] = self.margins[i]
+      if self.drape_kind is not None:
+        s.drape_kind[i] = self.drape_kind[i]
     for i, ch in enumerate(self.z_order):
       s.z_order[i] = ord(ch)
     s.n_groups = len(self.groups)
@@ -317,6 +328,52 @@ def _lower_marauders(engine, roles):
   return game
 
 
+def _lower_fixture(engine, roles):
+  th = engine.things
+  game = LoweredGame()
+  _common(engine, game, _lib.PROG_FIXTURE)
+  order = ''.join(game.groups)
+  sprite_chars = [c for c in order if roles[c] == 'fixture.walker']
+  drape_chars = [c for c in order if roles[c] != 'fixture.walker']
+  if len(sprite_chars) > _lib.MAX_SPRITES or len(drape_chars) > _lib.MAX_DRAPES:
+    raise NotLoweredError('too many entities for the general device program')
+  sprites = [th[c] for c in sprite_chars]
+  _set_sprites(game, sprites, [_sprite_record(s, aux0=0, aux1=_lib.NEVER) for s in sprites])
+  game.drape_chars = ''.join(drape_chars)
+  game.drape_kind, game.margins, recs = [], [], []
+  shape = None
+  for d, ch in enumerate(drape_chars):
+    ent = th[ch]
+    if roles[ch] == 'fixture.scrolly':
+      if ent._scrolling_group != '':
+        raise NotLoweredError('only the default scrolling group is lowered')
+      if shape not in (None, ent.whole_pattern.shape):
+        raise NotLoweredError('Scrolly patterns of different shapes')
+      shape = ent.whole_pattern.shape
+      game.drape_kind.append(1)
+      game.margins.append((-1, -1) if ent._scroll_margins is None
+                          else tuple(ent._scroll_margins))
+      recs.append(_scrolly_record(ent))
+    else:
+      game.drape_kind.append(0)
+      game.margins.append((-1, -1))
+      rec = [0] * _lib.DRAPE_WORDS
+      rec[_lib.D_LAST_FRAME] = _lib.NEVER
+      recs.append(rec)
+      game.bits[d] = pack_rows(ent.curtain, game.bits_words)
+  if shape is not None:
+    game.pattern_rows, game.pattern_cols = shape
+    game.pattern_words = (shape[1] + 31) // 32 + 2
+    for d, ch in enumerate(drape_chars):
+      if game.drape_kind[d]:
+        game.patterns[d] = pack_rows(th[ch].whole_pattern, game.pattern_words)
+        game.pattern_mutable[d] = False
+  game.drapes = np.array(recs, dtype=np.int32).reshape(len(drape_chars), _lib.DRAPE_WORDS)
+  game.plot = np.array(_plot_record(), dtype=np.int32)
+  game.dynamic_z = True
+  return game
+
+
 def lower(engine):
   """`Engine` (set-up finished, not yet showtime) -> `LoweredGame`."""
   roles = {ch: role_of(ent) for ch, ent in engine.things.items()}
@@ -330,4 +387,6 @@ def lower(engine):
     return _lower_warehouse(engine, roles)
   if family == 'marauders':
     return _lower_marauders(engine, roles)
+  if family == 'fixture':
+    return _lower_fixture(engine, roles)
   raise NotLoweredError(family)

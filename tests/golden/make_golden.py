@@ -173,6 +173,71 @@ def fixture_scrolly(name, seed, margins, second_ego, T=400):
        curtains=np.stack(curtains).astype(np.uint8))
 
 
+def fixture_directives(name, seed, T=250):
+  """Walkers + a static drape with Plot directives injected through
+  test_things.post_update: rewards, z-order changes, a final termination."""
+  tt = refdriver._import()['test_things']
+  rs = np.random.RandomState(5000 + seed)
+  H, W = 7, 9
+  art = np.full((H, W), ord(' '), dtype=np.uint8)
+  art[rs.random_sample((H, W)) < 0.2] = ord('#')
+  art[2:5, 3:6] = ord('%')                      # static drape region
+  for ch, (r, c) in zip('abc', [(1, 1), (5, 7), (3, 4)]):
+    art[r, c] = ord(ch)
+  art_l = tj.u8_to_art(art)
+  walkers = {'a': dict(impassable='#', confined=True),
+             'b': dict(impassable='#c', confined=False),
+             'c': dict(impassable='', confined=True)}
+  schedule = [['a', '%'], ['b', 'c']]
+  order = 'a%bc'
+  z_order = ''.join(rs.permutation(list(order)))
+  engine = refdriver.ref_fixture(art_l, ' ', walkers, drapes='%',
+                                 update_schedule=schedule, z_order=z_order)
+  out = engine.its_showtime()
+  boards = [tj.board_of(out[0]).copy()]
+  reward, has_reward, discount, over = [0], [0], [float(out[2])], [0]
+  rows, z_orders = [], [list(map(ord, engine.z_order))]
+  for t in range(T):
+    motions = {ch: int(rs.randint(0, 9)) for ch in 'abc'}
+    r = int(rs.randint(-5, 50)) if rs.random_sample() < 0.3 else None
+    z = None
+    if rs.random_sample() < 0.25:
+      this = order[int(rs.randint(4))]
+      that = None if rs.random_sample() < 0.3 else order[int(rs.randint(4))]
+      if that != this:
+        z = (this, that)
+    term = (t == T - 1)
+
+    def inject(actions, board, layers, backdrop, things, the_plot, r=r, z=z, term=term):
+      if r is not None:
+        the_plot.add_reward(r)
+      if term:
+        the_plot.terminate_episode()
+      if z is not None:
+        the_plot.change_z_order(*z)
+    tt.post_update(engine, 'c', inject)
+    out = engine.play(refdriver.fixture_actions_to_ref(motions))
+    row = [motions.get(ch, 8) for ch in order]
+    row += [-(2 ** 31) if r is None else r, int(term)]
+    row += [-1, 0] if z is None else [ord(z[0]), 0 if z[1] is None else ord(z[1])]
+    rows.append(row)
+    boards.append(tj.board_of(out[0]).copy())
+    reward.append(0 if out[1] is None else int(out[1]))
+    has_reward.append(0 if out[1] is None else 1)
+    discount.append(float(out[2]))
+    over.append(int(engine.game_over))
+    z_orders.append(list(map(ord, engine.z_order)))
+  cfg = dict(walkers=walkers, scrollys={}, drapes='%', schedule=schedule,
+             z_order=z_order, what_lies_beneath=' ', action_chars=order)
+  save(name, art=art, config=np.frombuffer(json.dumps(cfg).encode(), np.uint8),
+       actions=np.array(rows, dtype=np.int64), boards=np.stack(boards),
+       reward=np.array(reward, dtype=np.int64),
+       has_reward=np.array(has_reward, dtype=np.uint8),
+       discount=np.array(discount, dtype=np.float64),
+       game_over=np.array(over, dtype=np.uint8),
+       z_orders=np.array(z_orders, dtype=np.uint8))
+
+
 def cropper(name, pad, margins, offset, saccade, T=300):
   cropping = refdriver._import()['cropping']
   maze, board, beneath = levels.scrolly_maze_level(5, world_shape=(65, 65),
@@ -240,6 +305,9 @@ def main():
   for seed, margins, ego2 in ((0, (2, 3), 0), (1, None, 1), (2, (1, 1), 0),
                               (3, None, 0), (4, (2, 2), 1), (5, (1, 2), 1)):
     fixture_scrolly('fixture_scrolly_%d' % seed, seed, margins, ego2)
+
+  for seed in range(3):
+    fixture_directives('fixture_directives_%d' % seed, seed)
 
   cropper('crop_ego_pad', ' ', (None, None), None, True)
   cropper('crop_margins_nopad', None, (2, 3), None, True)

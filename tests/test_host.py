@@ -53,9 +53,9 @@ def test_binding_loads_and_reports_abi():
 
 def test_spec_struct_matches_header_size():
   # pcl_spec: 12 int32 + 16 + 8 bytes + 16*4 u32 + 16 + 16 i32 + 8*2 i32 + 24 bytes
-  # + 1 i32 + 24 i32 + 24 bytes + 8 i32.
+  # + 1 i32 + 24 i32 + 24 bytes + 8 i32 drape_kind + 8 i32.
   import ctypes
-  expected = 12 * 4 + 16 + 8 + 16 * 16 + 16 * 4 + 16 * 4 + 16 * 4 + 24 + 4 + 24 * 4 + 24 + 8 * 4
+  expected = 12 * 4 + 16 + 8 + 16 * 16 + 16 * 4 + 16 * 4 + 16 * 4 + 24 + 4 + 24 * 4 + 24 + 8 * 4 + 8 * 4
   assert ctypes.sizeof(_lib.Spec) == expected
 
 
@@ -323,3 +323,34 @@ def test_reference_example_outside_the_lowered_set_is_refused(compat_examples):
   mod = compat_examples('better_scrolly_maze')
   with pytest.raises(NotLoweredError):
     lowering.lower(mod.make_game(0))
+
+
+@needs_ref
+def test_reference_test_fixtures_load_and_lower(compat_examples):
+  """The reference's own tests/test_things.py fixtures lower to the general
+  device program, identically to this package's games/fixtures.py."""
+  import sys
+  from pycolab_b200 import compat
+  from pycolab_b200.games import fixtures
+  tt = compat.load_example(os.path.join(refdriver.REFERENCE_ROOT, 'pycolab', 'tests',
+                                        'test_things.py'))
+  g = gc.load('fixture_scrolly_0')
+  kw, cfg = gc.fixture_kwargs(g)
+  aa = sys.modules['pycolab.ascii_art']
+  shape = (len(kw['art']), len(kw['art'][0]))
+  sprites = {ch: aa.Partial(tt.TestMazeWalker, impassable=w.get('impassable', ''),
+                            confined_to_board=w.get('confined', False),
+                            egocentric_scroller=w.get('egocentric', False))
+             for ch, w in kw['walkers'].items()}
+  drapes = {ch: aa.Partial(tt.TestScrolly, board_shape=shape, whole_pattern=s['pattern'],
+                           board_northwest_corner=s['corner'], scroll_margins=s['margins'])
+            for ch, s in kw['scrollys'].items()}
+  theirs = aa.ascii_art_to_game(kw['art'], ' ', sprites, drapes,
+                                update_schedule=kw['update_schedule'],
+                                z_order=kw['z_order'])
+  ours = fixtures.make_game(kw['art'], ' ', kw['walkers'], kw['scrollys'], '',
+                            kw['update_schedule'], kw['z_order'])
+  a, b = lowering.lower(theirs), lowering.lower(ours)
+  assert a.program == _lib.PROG_FIXTURE and a.dynamic_z
+  assert a.drape_kind == [1, 1] and a.egocentric == b.egocentric
+  _same_lowering(a, b)

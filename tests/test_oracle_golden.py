@@ -89,6 +89,37 @@ def test_fixture_scrolly(name):
       out = world.play(int(g['actions'][t]))
 
 
+def directive_actions(row, order):
+  """Device action row -> the oracle fixture program's action dict."""
+  n = len(order)
+  act = {ch: int(m) for ch, m in zip(order, row[:n])}
+  if row[n] != -(2 ** 31):
+    act['_reward'] = int(row[n])
+  if row[n + 1]:
+    act['_terminate'] = True
+  if row[n + 2] >= 0:
+    act['_z'] = (chr(int(row[n + 2])), None if row[n + 3] == 0 else chr(int(row[n + 3])))
+  return act
+
+
+@pytest.mark.parametrize('name', gc.names('fixture_directives_'))
+def test_fixture_directives(name):
+  g = gc.load(name)
+  kw, cfg = gc.fixture_kwargs(g)
+  world = games.make_fixture_world(**kw)
+  out = world.its_showtime()
+  order = cfg['action_chars']
+  for t in range(len(g['actions']) + 1):
+    np.testing.assert_array_equal(g['boards'][t], out[0], err_msg='t=%d' % t)
+    assert (int(g['has_reward'][t]), int(g['reward'][t])) == (
+        (0, 0) if out[1] is None else (1, int(out[1]))), t
+    assert float(g['discount'][t]) == float(out[2])
+    assert bool(g['game_over'][t]) == world.game_over
+    assert [chr(c) for c in g['z_orders'][t]] == world.z_order
+    if t < len(g['actions']):
+      out = world.play(directive_actions(g['actions'][t], order))
+
+
 @pytest.mark.parametrize('name', gc.names('crop_'))
 def test_cropper(name):
   g = gc.load(name)
