@@ -12,7 +12,13 @@
 // Boards the entities read (engine.py:698-735): the boxes see the PREVIOUS
 // step's final board (nothing has been re-rendered yet), the player sees the
 // render after the judge ran.  Both are evaluated per cell on demand from the
-// registers, one lane per looked-up cell.
+// records + the backdrop tile.
+//
+// Memory schedule (one warp per env): records -> smem with coalesced loads; the
+// whole backdrop tile -> smem with cp.async (it is both the board's base layer
+// and the only thing the look-ups need); all game logic then runs out of
+// shared memory with one lane per box; the board is the staged tile streamed
+// back out with uint4 stores plus <= 11 single-byte patches for the sprites.
 #include "pcl_device.cuh"
 #include "pcl_kernels.cuh"
 
@@ -22,181 +28,238 @@ namespace {
 
 constexpr int kMaxS = 11;           // up to ten boxes + P
 constexpr int kWarpsPerBlock = 4;
+constexpr int kRecWords = 128;      // 11 * 8 sprite words + 8 drape + 16 plot, padded
 
-__device__ __forceinline__ bool in_set(const uint32_t (&set)[4], int code) {
+__device__ __forceinline__ bool in_set(const uint32_t* set, int code) {
   return (set[(code >> 5) & 3] >> (code & 31)) & 1u;
 }
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::
+               "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+__device__ __forceinline__ int motion_of_action(int a) {    // :214-226, :288-295
+  return a == 0 ? PCL_M_N : a == 1 ? PCL_M_S : a == 2 ? PCL_M_W : PCL_M_E;
+}
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 8)
 warehouse_step(const StepParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
   const int lane = threadIdx.x & 31;
-  const int env = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int warp = threadIdx.x >> 5;
+  const int env = blockIdx.x * kWarpsPerBlock + warp;
   if (env >= p.B) return;
-  const int H = p.H, W = p.W, S = p.S, NB = p.S - 1;
+  const int H = p.H, W = p.W, S = p.S, NB = p.S - 1, pitch = p.pitch;
+  const size_t tile = (size_t)H * pitch;
+  uint8_t* my = smem_raw + warp * (kRecWords * 4 + tile);
+  int32_t* rec = reinterpret_cast<int32_t*>(my);          // [0, 88) sprites, [96, 104) drape, [112, 128) plot
+  uint8_t* s_bd = my + kRecWords * 4;
+  int32_t* r_judge = rec + 96;
+  int32_t* r_plot = rec + 112;
 
   int32_t* g_sprites = p.st.d_sprites + (int64_t)env * S * PCL_SPRITE_WORDS;
   int32_t* g_drapes = p.st.d_drapes + (int64_t)env * PCL_DRAPE_WORDS;
   int32_t* g_plot = p.st.d_plot + (int64_t)env * PCL_PLOT_WORDS;
   const uint8_t* backdrop = p.st.d_backdrop + (int64_t)env * p.st.backdrop_bstride;
 
-  Plot plot = load_record_rw<Plot>(g_plot);
+  // ---- the backdrop tile does not depend on anything: start it first
+  {
+    const int n16 = (int)(tile >> 4);
+    for (int i = lane; i < n16; i += 32) cp_async16(s_bd + i * 16, backdrop + i * 16);
+  }
+  // ---- records -> smem
+  const int was_over = g_plot[PCL_P_GAME_OVER];
   bool restart;
   if (p.mode == MODE_RESET) {
     restart = (p.env_mask == nullptr) || (p.env_mask[env] != 0);
-    if (!restart) return;
+    if (!restart) { cp_async_wait_all(); return; }
   } else {
-    restart = plot.game_over && p.auto_reset;
-    if (plot.game_over && !p.auto_reset) return;
+    restart = was_over && p.auto_reset;
+    if (was_over && !p.auto_reset) { cp_async_wait_all(); return; }
   }
+  {
+    const int32_t* ss = restart ? p.st.d_sprites_init + (int64_t)env * p.st.sprites_init_bstride
+                                : g_sprites;
+    const int32_t* sd = restart ? p.st.d_drapes_init + (int64_t)env * p.st.drapes_init_bstride
+                                : g_drapes;
+    const int32_t* sp = restart ? p.st.d_plot_init + (int64_t)env * p.st.plot_init_bstride
+                                : g_plot;
+    const int episodes = g_plot[PCL_P_EPISODES], error = g_plot[PCL_P_ERROR];
+    for (int i = lane; i < S * PCL_SPRITE_WORDS; i += 32) rec[i] = ss[i];
+    if (lane < PCL_DRAPE_WORDS) r_judge[lane] = sd[lane];
+    if (lane >= 16) r_plot[lane - 16] = sp[lane - 16];
+    __syncwarp();
+    if (restart && lane == 0) { r_plot[PCL_P_EPISODES] = episodes + 1; r_plot[PCL_P_ERROR] = error; }
+  }
+  const int action = restart ? PCL_ACTION_NONE : p.actions[(int64_t)env * p.actions_per_env];
+  cp_async_wait_all();
+  __syncwarp();
 
-  Sprite sp[kMaxS];
-  Drape judge;
-  int action;
-  if (restart) {
-    const int episodes = plot.episodes, error = plot.error;
-    plot = load_record<Plot>(p.st.d_plot_init + (int64_t)env * p.st.plot_init_bstride);
-    plot.episodes = episodes + 1;
-    plot.error = error;
-    const int32_t* si = p.st.d_sprites_init + (int64_t)env * p.st.sprites_init_bstride;
-#pragma unroll
-    for (int i = 0; i < kMaxS; ++i)
-      if (i < S) sp[i] = load_record<Sprite>(si + i * PCL_SPRITE_WORDS);
-    judge = load_record<Drape>(p.st.d_drapes_init + (int64_t)env * p.st.drapes_init_bstride);
-    action = PCL_ACTION_NONE;
-  } else {
-#pragma unroll
-    for (int i = 0; i < kMaxS; ++i)
-      if (i < S) sp[i] = load_record_rw<Sprite>(g_sprites + i * PCL_SPRITE_WORDS);
-    judge = load_record_rw<Drape>(g_drapes);
-    action = p.actions[(int64_t)env * p.actions_per_env];
-  }
+  Plot plot;
+  plot.frame = r_plot[PCL_P_FRAME] + 1;                    // engine.py:716
+  plot.error = r_plot[PCL_P_ERROR];
+  plot.order_frame = PCL_NEVER; plot.order_r = 0; plot.order_c = 0; plot.ego_mask = 0;
   Directives dir = fresh_directives();
-  plot.frame += 1;
 
-  // Snapshot = the board every box reads (previous final render).
-  int old_row[kMaxS], old_col[kMaxS], old_x[kMaxS];
-#pragma unroll
-  for (int i = 0; i < kMaxS; ++i) {
-    old_row[i] = i < S ? sp[i].row : -1;
-    old_col[i] = i < S ? sp[i].col : -1;
-    old_x[i] = i < S ? sp[i].aux0 : 0;
+  // Player as of the previous render; box i's record sits in lane i.
+  Sprite player;
+  {
+    const int32_t* r = rec + NB * PCL_SPRITE_WORDS;
+    player.row = r[PCL_S_ROW]; player.col = r[PCL_S_COL];
+    player.vrow = r[PCL_S_VROW]; player.vcol = r[PCL_S_VCOL];
+    player.flags = r[PCL_S_FLAGS]; player.aux0 = player.aux1 = player.aux2 = 0;
   }
-  Sprite player = sp[0];           // P lives in slot NB; pick it with unrolled selects
-#pragma unroll
-  for (int i = 1; i < kMaxS; ++i) if (i == NB) player = sp[i];
   const bool pl_vis = visible(player);
   const int pl_row = player.row, pl_col = player.col;
-
-  // Character shown by the stale board at (r, c).
-  auto stale_cell = [&](int r, int c) -> int {
-    if (pl_vis && r == pl_row && c == pl_col) return p.sprite_char[NB];
-    int code = backdrop[(int64_t)r * p.pitch + c];
+  // Sprite characters -> smem (rec words 88..95 are padding); static indices only,
+  // so the parameter block is never copied to local memory.
+  uint8_t* s_chars = reinterpret_cast<uint8_t*>(rec + 88);
+  {
+    int ch = 0;
 #pragma unroll
-    for (int i = 0; i < kMaxS - 1; ++i) {
-      if (i < NB && old_row[i] == r && old_col[i] == c)   // later boxes paint over earlier
-        code = old_x[i] ? 'X' : p.sprite_char[i];
+    for (int i = 0; i < kMaxS; ++i) if (i == lane) ch = p.sprite_char[i];
+    if (lane < kMaxS) s_chars[lane] = (uint8_t)ch;
+    __syncwarp();
+  }
+  const int P_CHAR = s_chars[NB];
+  const bool is_box = lane < NB;
+  const int32_t* mine = rec + (is_box ? lane : 0) * PCL_SPRITE_WORDS;
+  int b_row = mine[PCL_S_ROW], b_col = mine[PCL_S_COL];
+  const int b_x_old = mine[PCL_S_AUX0];
+
+  // Character of the stale board (= previous final render) at (r, c): P on top,
+  // then a box (drawn 'X' when the judge marked it), else the backdrop.
+  // Box positions are still the old ones in `rec` while this is used.
+  auto stale_cell = [&](int r, int c) -> int {
+    if (pl_vis && r == pl_row && c == pl_col) return P_CHAR;
+    int code = s_bd[r * pitch + c];
+    for (int i = 0; i < NB; ++i) {
+      const int32_t* b = rec + i * PCL_SPRITE_WORDS;
+      if (b[PCL_S_ROW] == r && b[PCL_S_COL] == c) code = b[PCL_S_AUX0] ? 'X' : s_chars[i];
     }
     return code;
   };
 
   // ---- group 0: boxes (BoxSprite.update, warehouse_manager.py:208-226)
   if (action >= 0 && action <= 3) {
-    // layers['P'][rows+-1, cols+-1] with NumPy index rules.
+    // layers['P'][rows +- 1, cols +- 1] with NumPy index rules: -1 wraps, >= size raises.
     const int dr = action == 0 ? 1 : action == 1 ? -1 : 0;
     const int dc = action == 2 ? 1 : action == 3 ? -1 : 0;
-    const int motion = action == 0 ? PCL_M_N : action == 1 ? PCL_M_S
-                     : action == 2 ? PCL_M_W : PCL_M_E;
+    int rr = b_row + dr, cc = b_col + dc;
+    if (rr < 0) rr += H;
+    if (cc < 0) cc += W;
+    const bool oob = is_box && (rr >= H || cc >= W);
+    const bool pushed = is_box && !oob && pl_vis && rr == pl_row && cc == pl_col;
+    if (__any_sync(PCL_FULL, oob)) plot.error |= PCL_ENV_ERR_INDEX;
+    const unsigned who = __ballot_sync(PCL_FULL, pushed);
+    if (who) {                               // at most one box can be next to P
+      const int j = __ffs(who) - 1;
+      const int32_t* r = rec + j * PCL_SPRITE_WORDS;
+      Sprite box;
+      box.row = r[PCL_S_ROW]; box.col = r[PCL_S_COL];
+      box.vrow = r[PCL_S_VROW]; box.vcol = r[PCL_S_VCOL];
+      box.flags = r[PCL_S_FLAGS]; box.aux0 = r[PCL_S_AUX0]; box.aux1 = box.aux2 = 0;
+      uint32_t imp[4];
 #pragma unroll
-    for (int i = 0; i < kMaxS - 1; ++i) {
-      if (i < NB) {
-        int rr = sp[i].row + dr, cc = sp[i].col + dc;
-        if (rr < 0) rr += H;
-        if (cc < 0) cc += W;
-        bool pushed = false;
-        if (rr >= H || cc >= W) plot.error |= PCL_ENV_ERR_INDEX;
-        else pushed = pl_vis && rr == pl_row && cc == pl_col;
-        if (pushed) {
-          const uint32_t (&imp)[4] = p.impassable[i];
-          walker_move(sp[i], i, motion, plot, H, W, false, false, lane,
-                      [&](int r, int c) { return in_set(imp, stale_cell(r, c)); });
+      for (int w = 0; w < 4; ++w) imp[w] = p.impassable[0][w];
+#pragma unroll
+      for (int i = 1; i < kMaxS - 1; ++i)
+        if (i == j) {
+#pragma unroll
+          for (int w = 0; w < 4; ++w) imp[w] = p.impassable[i][w];
         }
+      walker_move(box, j, motion_of_action(action), plot, H, W, false, false, lane,
+                  [&](int r2, int c2) { return in_set(imp, stale_cell(r2, c2)); });
+      __syncwarp();
+      if (lane == 0) {
+        int32_t* w = rec + j * PCL_SPRITE_WORDS;
+        w[PCL_S_ROW] = box.row; w[PCL_S_COL] = box.col;
+        w[PCL_S_VROW] = box.vrow; w[PCL_S_VCOL] = box.vcol; w[PCL_S_FLAGS] = box.flags;
       }
+      __syncwarp();
+      if (lane == j) { b_row = box.row; b_col = box.col; }
     }
   }
 
-  // ---- group 1: JudgeDrape.update (:245-266)
-  int num_boxes = 0, on_goals = 0;
-#pragma unroll
-  for (int i = 0; i < kMaxS - 1; ++i) {
-    if (i < NB) {
-      bool first = true;
-#pragma unroll
-      for (int j = 0; j < kMaxS - 1; ++j)
-        if (j < i && sp[j].row == sp[i].row && sp[j].col == sp[i].col) first = false;
-      const bool goal = backdrop[(int64_t)sp[i].row * p.pitch + sp[i].col] == '_';
-      sp[i].aux0 = goal ? 1 : 0;
-      num_boxes += first ? 1 : 0;
-      on_goals += (first && goal) ? 1 : 0;
+  // ---- group 1: JudgeDrape.update (:245-266), one lane per box
+  bool first = is_box, goal = false;
+  if (is_box) {
+    for (int i = 0; i < lane; ++i) {
+      const int32_t* b = rec + i * PCL_SPRITE_WORDS;
+      if (b[PCL_S_ROW] == b_row && b[PCL_S_COL] == b_col) first = false;
     }
+    goal = s_bd[b_row * pitch + b_col] == '_';
   }
-  add_reward(dir, on_goals - judge.aux0);
-  judge.aux0 = on_goals;
+  const int num_boxes = __popc(__ballot_sync(PCL_FULL, first));
+  const int on_goals = __popc(__ballot_sync(PCL_FULL, first && goal));
+  if (is_box) rec[lane * PCL_SPRITE_WORDS + PCL_S_AUX0] = goal ? 1 : 0;
+  add_reward(dir, on_goals - r_judge[PCL_D_AUX0]);
   if (action == 5 || on_goals == num_boxes) terminate(dir);
+  __syncwarp();
 
-  // ---- group 2: PlayerSprite.update (:284-295), board = boxes moved + X redrawn
+  // ---- group 2: PlayerSprite.update (:284-295); board = boxes moved, X redrawn
   if (action >= 0 && action <= 3) {
-    const int motion = action == 0 ? PCL_M_N : action == 1 ? PCL_M_S
-                     : action == 2 ? PCL_M_W : PCL_M_E;
-    const uint32_t (&imp)[4] = p.impassable[NB];
-    auto now_cell = [&](int r, int c) -> int {
-      if (pl_vis && r == pl_row && c == pl_col) return p.sprite_char[NB];
-      int code = backdrop[(int64_t)r * p.pitch + c];
+    uint32_t imp[4];
 #pragma unroll
-      for (int i = 0; i < kMaxS - 1; ++i)
-        if (i < NB && visible(sp[i]) && sp[i].row == r && sp[i].col == c)
-          code = sp[i].aux0 ? 'X' : p.sprite_char[i];
-      return code;
-    };
-    walker_move(player, NB, motion, plot, H, W, false, false, lane,
-                [&](int r, int c) { return in_set(imp, now_cell(r, c)); });
+    for (int w = 0; w < 4; ++w) imp[w] = p.impassable[kMaxS - 1][w];
+#pragma unroll
+    for (int i = 1; i < kMaxS - 1; ++i)
+      if (i == NB) {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) imp[w] = p.impassable[i][w];
+      }
+    walker_move(player, NB, motion_of_action(action), plot, H, W, false, false, lane,
+                [&](int r2, int c2) { return in_set(imp, stale_cell(r2, c2)); });
   }
 
-  plot.game_over = dir.game_over;
+  // ---- _apply_and_clear_plot + records back
+  __syncwarp();
   if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < kMaxS - 1; ++i)
-      if (i < NB) store_record(g_sprites + i * PCL_SPRITE_WORDS, sp[i]);
-    store_record(g_sprites + NB * PCL_SPRITE_WORDS, player);
-    store_record(g_drapes, judge);
-    store_record(g_plot, plot);
+    int32_t* w = rec + NB * PCL_SPRITE_WORDS;
+    w[PCL_S_ROW] = player.row; w[PCL_S_COL] = player.col;
+    w[PCL_S_VROW] = player.vrow; w[PCL_S_VCOL] = player.vcol; w[PCL_S_FLAGS] = player.flags;
+    r_judge[PCL_D_AUX0] = on_goals;
+    r_plot[PCL_P_FRAME] = plot.frame; r_plot[PCL_P_GAME_OVER] = dir.game_over;
+    r_plot[PCL_P_ERROR] = plot.error;
     p.out.d_reward[env] = dir.reward;
     p.out.d_has_reward[env] = (uint8_t)dir.has_reward;
     p.out.d_discount[env] = dir.discount;
     p.out.d_done[env] = (uint8_t)dir.game_over;
   }
+  __syncwarp();
+  for (int i = lane; i < S * PCL_SPRITE_WORDS; i += 32) g_sprites[i] = rec[i];
+  if (lane < PCL_DRAPE_WORDS) g_drapes[lane] = r_judge[lane];
+  if (lane >= 16) g_plot[lane - 16] = r_plot[lane - 16];
 
-  // ---- final render: backdrop, boxes (as 'X' on goals), player.
-  uint8_t* board = p.out.d_board + (int64_t)env * H * p.pitch;
-  const int segs_per_row = p.pitch >> 4;
-  const int total = H * segs_per_row;
-  for (int seg = lane; seg < total; seg += 32) {
-    const int r = seg / segs_per_row;
-    const int c0 = (seg - r * segs_per_row) << 4;
-    uint4 px = __ldg(reinterpret_cast<const uint4*>(backdrop + (int64_t)r * p.pitch + c0));
-#pragma unroll
-    for (int i = 0; i < kMaxS - 1; ++i)
-      if (i < NB)
-        paint_bits(px, sprite_bit(sp[i], r, c0), sp[i].aux0 ? 'X' : p.sprite_char[i]);
-    paint_bits(px, sprite_bit(player, r, c0), p.sprite_char[NB]);
-    *reinterpret_cast<uint4*>(board + (int64_t)r * p.pitch + c0) = px;
-  }
+  // ---- final render: patch the sprite cells into the staged tile, stream it out.
+  // Boxes never share a cell with each other or with P (each is impassable to
+  // the others), so the patches are independent; P goes last to keep z-order.
+  if (is_box && (mine[PCL_S_FLAGS] & 1))
+    s_bd[b_row * pitch + b_col] = goal ? 'X' : s_chars[lane];
+  __syncwarp();
+  if (lane == 0 && visible(player)) s_bd[player.row * pitch + player.col] = (uint8_t)P_CHAR;
+  __syncwarp();
+  uint8_t* board = p.out.d_board + (int64_t)env * tile;
+  const int n16 = (int)(tile >> 4);
+  for (int i = lane; i < n16; i += 32)
+    reinterpret_cast<uint4*>(board)[i] = reinterpret_cast<const uint4*>(s_bd)[i];
 }
 
 }  // namespace
 
 cudaError_t launch_warehouse(const StepParams& p, cudaStream_t s) {
   const int blocks = (p.B + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  warehouse_step<<<blocks, kWarpsPerBlock * 32, 0, s>>>(p);
+  const size_t smem = (kRecWords * 4 + (size_t)p.H * p.pitch) * kWarpsPerBlock;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(warehouse_step,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  warehouse_step<<<blocks, kWarpsPerBlock * 32, smem, s>>>(p);
   return cudaGetLastError();
 }
 
