@@ -66,7 +66,7 @@ __device__ __forceinline__ bool same_cell(const Sprite& a, const Sprite& b) {
   return a.row == b.row && a.col == b.col;
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 7)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
 marauders_step(const StepParams p) {
   const int lane = threadIdx.x & 31;
   const int env = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);

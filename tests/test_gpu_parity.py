@@ -393,3 +393,102 @@ def test_large_batch_invariants():
   assert bool((total_reward % 100 == 0).all())
   assert int(eng.error_codes().abs().max()) == 0
   assert first.shape == (B, 64, 64)
+
+
+# --------------------------------------------------- engine-level behaviours
+
+def test_partial_reset_touches_only_masked_envs():
+  from pycolab_b200 import batched, levels
+  from pycolab_b200.games import scrolly_maze
+  torch = _torch()
+  art = levels.scrolly_maze_level(4, world_shape=(65, 65), board_shape=(32, 32))
+  eng = batched.BatchedEngine([scrolly_maze.make_game(*art)], batch=6, auto_reset=False)
+  first = eng.its_showtime().board.clone()
+  rs = np.random.RandomState(0)
+  for _ in range(25):
+    eng.play(torch.from_numpy(rs.randint(0, 4, size=6).astype(np.int32)).cuda())
+  before = eng.board.clone()
+  frames = eng.frames().clone()
+  mask = torch.tensor([1, 0, 0, 1, 0, 0], dtype=torch.uint8, device='cuda')
+  eng.reset(mask)
+  torch.cuda.synchronize()
+  assert bool((eng.board[[0, 3]] == first[[0, 3]]).all())
+  assert bool((eng.board[[1, 2, 4, 5]] == before[[1, 2, 4, 5]]).all())
+  assert eng.frames().tolist() == [0, int(frames[1]), int(frames[2]), 0, int(frames[4]),
+                                   int(frames[5])]
+
+
+def test_finished_env_freezes_without_auto_reset():
+  """Upstream raises on play() after the episode ended (engine.py:622-624); the
+  batched engine leaves such an env untouched instead."""
+  from pycolab_b200 import batched, levels
+  from pycolab_b200.games import scrolly_maze
+  torch = _torch()
+  art = levels.scrolly_maze_level(4, world_shape=(65, 65), board_shape=(32, 32))
+  eng = batched.BatchedEngine([scrolly_maze.make_game(*art)], batch=2, auto_reset=False)
+  eng.its_showtime()
+  res = eng.play(torch.tensor([5, 4], dtype=torch.int32, device='cuda'))   # env 0 quits
+  assert res.done.tolist() == [1, 0] and res.discount.tolist() == [0.0, 1.0]
+  frozen = res.board[0].clone()
+  for _ in range(5):
+    res = eng.play(torch.tensor([0, 0], dtype=torch.int32, device='cuda'))
+  assert res.done.tolist() == [1, 0]
+  assert bool((res.board[0] == frozen).all())
+  assert eng.frames().tolist() == [1, 6]
+
+
+def test_facade_raises_like_the_reference():
+  from pycolab_b200 import levels
+  from pycolab_b200.games import fixtures, scrolly_maze
+  art = levels.scrolly_maze_level(4, world_shape=(65, 65), board_shape=(32, 32))
+  game = scrolly_maze.make_game(*art)
+  with pytest.raises(RuntimeError):
+    game.play(0)                               # before its_showtime
+  game.its_showtime()
+  with pytest.raises(RuntimeError):
+    game.its_showtime()                        # twice
+  with pytest.raises(RuntimeError):
+    game.add_sprite('q', (0, 0), scrolly_maze.PlayerSprite, (0, 0))
+  _, reward, discount = game.play(5)           # quit
+  assert reward is None and discount == 0.0 and game.game_over
+  with pytest.raises(RuntimeError):
+    game.play(0)                               # after the episode ended
+  # A margin-less Scrolly that clips a diagonal order to (0, 0) makes the
+  # egocentric walker raise upstream (sprites.py:449-454): same here.
+  pattern = np.zeros((6, 6), dtype=bool)
+  fx = fixtures.make_game(['    ', ' P  ', '    ', '    '], ' ',
+                          {'P': dict(impassable='#', egocentric=True)},
+                          {'#': dict(pattern=pattern, corner=(0, 0), margins=None)},
+                          update_schedule=[['#'], ['P']], z_order='#P')
+  fx.its_showtime()
+  fx.play('se')                                # permits for the next frame
+  with pytest.raises(RuntimeError):
+    for _ in range(6):
+      fx.play('nw')                            # corner (0,0): clipped to (0,0)
+
+
+def test_facade_things_and_layers_follow_the_device():
+  from pycolab_b200 import levels
+  from pycolab_b200.games import scrolly_maze
+  art = levels.scrolly_maze_level(9, world_shape=(65, 65), board_shape=(32, 32))
+  game = scrolly_maze.make_game(*art)
+  world = ogames.make_scrolly_maze(art[0], art[1], '+', art[2])
+  obs, _, _ = game.its_showtime()
+  out = world.its_showtime()
+  rs = np.random.RandomState(1)
+  for _ in range(40):
+    a = int(rs.randint(0, 5))
+    obs, _, _ = game.play(a)
+    out = world.play(a)
+    if game.game_over:
+      break
+  np.testing.assert_array_equal(obs.board, out[0])
+  for ch in 'Pabc':
+    assert tuple(game.things[ch].position) == world.things[ch].position
+    assert tuple(game.things[ch].virtual_position) == world.things[ch].virtual_position
+  for ch in '#@':
+    np.testing.assert_array_equal(game.things[ch].curtain, world.things[ch].curtain)
+  assert set(obs.layers) == set(world.chars)
+  for ch in obs.layers:
+    np.testing.assert_array_equal(obs.layers[ch], out[0] == ord(ch))
+  assert game.the_plot.frame == world.plot.frame
