@@ -65,7 +65,8 @@ typedef enum pcl_program {
   PCL_PROG_SCROLLY_MAZE = 1, /* examples/scrolly_maze.py:212-364               */
   PCL_PROG_WAREHOUSE = 2,    /* examples/warehouse_manager.py:139-295          */
   PCL_PROG_MARAUDERS = 3,    /* examples/extraterrestrial_marauders.py:91-256  */
-  PCL_PROG_FIXTURE = 4       /* tests/test_things.py TestMazeWalker/TestScrolly */
+  PCL_PROG_FIXTURE = 4,      /* tests/test_things.py TestMazeWalker/TestScrolly */
+  PCL_PROG_BETTER_SCROLLY = 5 /* examples/better_scrolly_maze.py:209-324        */
 } pcl_program;
 
 /* Motion codes (prefab_parts/sprites.py:140-150). */
@@ -204,8 +205,14 @@ int pcl_render(pcl_handle* h, const uint8_t* d_backdrop, int64_t backdrop_bstrid
 int pcl_export_curtain(pcl_handle* h, int drape_index, uint8_t* d_out, void* stream);
 
 /* ScrollingCropper.crop (cropping.py:393-426): track sprite `sprite_index`,
- * update the per-env window corner (kept in the plot record) and copy the
- * crop_rows x crop_cols window of d_board into d_crop u8 [B, crop_rows, crop_cols]. */
+ * update the per-env window corner and copy the crop_rows x crop_cols window of
+ * d_board into d_crop u8 [B, crop_rows, crop_cols].  The corner lives in
+ * d_crop_state, i32 [B, 4] = (row, col, initialised, episode) owned by the
+ * caller, one array per cropper object (zero-filled at creation); a window
+ * re-initialises itself when the env's episode counter moves on, as
+ * ScrollingCropper.set_engine does for a new Engine (cropping.py:375-391).
+ * d_crop_state == NULL selects a single built-in cropper slot in the plot record.
+ * sprite_index < 0 is a FixedCropper at (offset_rows, offset_cols). */
 typedef struct pcl_crop_spec {
   int32_t rows, cols;          /* window shape */
   int32_t sprite_index;        /* entity to track (a sprite) */
@@ -215,7 +222,7 @@ typedef struct pcl_crop_spec {
   int32_t saccade;
 } pcl_crop_spec;
 int pcl_crop(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d_board,
-             uint8_t* d_crop, void* stream);
+             uint8_t* d_crop, int32_t* d_crop_state, void* stream);
 
 /* Copy the per-env latched error words (PCL_ENV_ERR_*) to d_out i32 [B]. */
 int pcl_error_codes(pcl_handle* h, int32_t* d_out, void* stream);

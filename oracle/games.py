@@ -298,6 +298,60 @@ def marauders_program(world, ch, actions):
 
 
 # ==========================================================================
+# better_scrolly_maze
+# ==========================================================================
+
+def make_better_scrolly(maze_art):
+  """examples/better_scrolly_maze.py:209-221."""
+  order = ['a', 'b', 'c', 'P', '@']
+  backdrop, masks = split_art(maze_art, order, ' ')
+  shape = backdrop.shape
+  things = {}
+  for ch in 'abc':                               # PatrollerSprite :282-286
+    w = em.Walker(ch, shape, mask_position(masks[ch]), impassable='#')
+    w.aux['moving_east'] = bool(ord(ch) % 2)
+    things[ch] = w
+  things['P'] = em.Walker('P', shape, mask_position(masks['P']), impassable='#')
+  things['@'] = em.PlainDrape('@', masks['@'])
+  return em.World(shape[0], shape[1], backdrop, things, z_order='abc@P',
+                  groups=[order], program=better_scrolly_program)
+
+
+def better_scrolly_program(world, ch, actions):
+  plot = world.plot
+  ent = world.things[ch]
+  board = world.board
+  if ch == 'P':                                   # PlayerSprite.update :263-276
+    motion = {0: em.M_N, 1: em.M_S, 2: em.M_W, 3: em.M_E, 4: em.M_STAY}.get(actions) \
+        if actions is not None else None
+    if motion is not None:
+      em.walker_move(ent, board, plot, motion)
+    if actions == 5:
+      plot.terminate_episode()
+  elif ch in 'abc':                               # PatrollerSprite.update :288-305
+    if plot.frame % 2:
+      em.walker_move(ent, board, plot, em.M_STAY)
+      return
+    row, col = ent.position
+    if board[row, col - 1] == ord('#'):           # layers['#'][row, col-1]
+      ent.aux['moving_east'] = True
+    if board[row, col + 1] == ord('#'):
+      ent.aux['moving_east'] = False
+    em.walker_move(ent, board, plot, em.M_E if ent.aux['moving_east'] else em.M_W)
+    if ent.position == world.things['P'].position:
+      plot.terminate_episode()
+  elif ch == '@':                                 # CashDrape.update :314-324
+    where = world.things['P'].position
+    if ent.curtain[where]:
+      plot.add_reward(100)
+      ent.curtain[where] = False
+      if not ent.curtain.any():
+        plot.terminate_episode()
+  else:
+    raise KeyError(ch)
+
+
+# ==========================================================================
 # Test-fixture world: generic MazeWalkers / Scrollys / static drapes driven by
 # per-entity motion codes (tests/test_things.py:203-295).
 # ==========================================================================

@@ -29,6 +29,7 @@ ENV_ERR_INDEX = 0x8
 ENV_ERR_BAD_Z = 0x10
 
 PROG_NONE, PROG_SCROLLY_MAZE, PROG_WAREHOUSE, PROG_MARAUDERS, PROG_FIXTURE = 0, 1, 2, 3, 4
+PROG_BETTER_SCROLLY = 5
 
 # Record word indices (pcl.h enums).
 S_ROW, S_COL, S_VROW, S_VCOL, S_FLAGS, S_AUX0, S_AUX1, S_AUX2 = range(8)
@@ -123,7 +124,7 @@ SYMBOLS = {
                              C.c_void_p, C.c_void_p, C.c_void_p]),
     'pcl_export_curtain': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     'pcl_crop': (C.c_int, [C.c_void_p, C.POINTER(CropSpec), C.c_void_p, C.c_void_p,
-                           C.c_void_p]),
+                           C.c_void_p, C.c_void_p]),
     'pcl_error_codes': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     'pcl_launch_count': (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
 }

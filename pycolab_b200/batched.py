@@ -288,15 +288,26 @@ class BatchedEngine(object):
     _lib.check(self._lib.pcl_launch_count(self._h, C.byref(n)), 'pcl_launch_count')
     return n.value
 
-  def crop(self, crop_spec):
-    """ScrollingCropper.crop over the last boards: u8 [B, rows, cols]."""
+  def new_crop_state(self):
+    """Corner state of one cropper object: i32 [B, 4] (row, col, initialised,
+    episode), zero = not yet initialised.  One per ScrollingCropper."""
+    return _torch().zeros((self.batch, 4), dtype=_torch().int32, device=self.device)
+
+  def crop(self, crop_spec, state=None, out=None):
+    """ScrollingCropper / FixedCropper .crop over the last boards: u8 [B, rows,
+    cols].  `state` (from new_crop_state) keeps this cropper's window corners;
+    None uses the single built-in slot in the plot record."""
     torch = _torch()
     shape = (self.batch, crop_spec.rows, crop_spec.cols)
-    if self._crop_out is None or tuple(self._crop_out.shape) != shape:
-      self._crop_out = torch.empty(shape, dtype=torch.uint8, device=self.device)
+    if out is None:
+      if self._crop_out is None or tuple(self._crop_out.shape) != shape:
+        self._crop_out = torch.empty(shape, dtype=torch.uint8, device=self.device)
+      out = self._crop_out
     _lib.check(self._lib.pcl_crop(self._h, C.byref(crop_spec), self._board.data_ptr(),
-                                  self._crop_out.data_ptr(), self._stream()), 'pcl_crop')
-    return self._crop_out
+                                  out.data_ptr(),
+                                  None if state is None else state.data_ptr(),
+                                  self._stream()), 'pcl_crop')
+    return out
 
   def sprite_state(self):
     """i32 [B, S, 8] device tensor of sprite records (PCL_S_* words)."""

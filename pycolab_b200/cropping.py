@@ -21,6 +21,8 @@ class ObservationCropper(object):
     self._pad_char = None
 
   def set_engine(self, engine):
+    if engine is not self._engine:
+      self._state = None          # a new Engine forgets the window (cropping.py:375-391)
     self._engine = engine
 
   def crop(self, observation):
@@ -47,7 +49,9 @@ class ObservationCropper(object):
     b = self._engine.batched
     if b is None:
       raise RuntimeError('crop() called before the Engine entered play mode')
-    board = b.crop(spec)[0].cpu().numpy().copy()
+    if getattr(self, '_state', None) is None:
+      self._state = b.new_crop_state()
+    board = b.crop(spec, state=self._state)[0].cpu().numpy().copy()
     chars = set(self._engine.things) | set(self._engine.backdrop.palette)
     return rendering.Observation(board=board, layers=rendering.LazyLayers(board, chars))
 

@@ -117,6 +117,17 @@ int validate(const pcl_spec& s) {
       }
       return PCL_OK;
     }
+    case PCL_PROG_BETTER_SCROLLY: {
+      if (!chars_are(s.sprite_char, s.n_sprites, "Pabc")) return PCL_ERR_UNSUPPORTED;
+      if (!chars_are(s.drape_char, s.n_drapes, "@")) return PCL_ERR_UNSUPPORTED;
+      if (!chars_are(s.z_order, 5, "abc@P")) return PCL_ERR_UNSUPPORTED;
+      const int lens[1] = {5};
+      if (!groups_are(s, "abcP@", lens, 1)) return PCL_ERR_UNSUPPORTED;
+      for (int i = 0; i < 4; ++i)
+        if (s.sprite_confined[i] || s.sprite_egocentric[i]) return PCL_ERR_UNSUPPORTED;
+      if (s.bits_words < (s.cols + 31) / 32 + 1) return PCL_ERR_INVALID;
+      return PCL_OK;
+    }
     case PCL_PROG_FIXTURE: {
       // Any MazeWalker / Scrolly / plain-drape mix; entities and z-order must
       // be consistent permutations of each other.
@@ -178,6 +189,7 @@ int launch(pcl_handle* h, const StepParams& p, cudaStream_t stream) {
     case PCL_PROG_WAREHOUSE: e = pcl::launch_warehouse(p, stream); break;
     case PCL_PROG_MARAUDERS: e = pcl::launch_marauders(p, stream); break;
     case PCL_PROG_FIXTURE: e = pcl::launch_fixture(p, stream); break;
+    case PCL_PROG_BETTER_SCROLLY: e = pcl::launch_better_scrolly(p, stream); break;
     default: return PCL_ERR_UNSUPPORTED;
   }
   h->launches += 1;
@@ -250,6 +262,9 @@ int pcl_bind_state(pcl_handle* h, const pcl_state* st) {
     for (int d = 0; d < 2; ++d)
       if (!st->d_bits[d] || !st->d_bits_init[d] || st->bits_bstride[d] == 0) return PCL_ERR_INVALID;
     if (!st->d_rng) return PCL_ERR_INVALID;
+  }
+  if (h->spec.program == PCL_PROG_BETTER_SCROLLY) {
+    if (!st->d_bits[0] || !st->d_bits_init[0] || st->bits_bstride[0] == 0) return PCL_ERR_INVALID;
   }
   if (h->spec.program == PCL_PROG_FIXTURE) {
     if (!st->d_z_order || !st->d_z_order_init) return PCL_ERR_INVALID;
@@ -359,6 +374,7 @@ int pcl_export_curtain(pcl_handle* h, int drape_index, uint8_t* d_out, void* str
     p.bits_bstride = h->st.pattern_bstride[drape_index];
     if (drape_index == 1) p.stale_slot = 0;
   } else if (h->spec.program == PCL_PROG_MARAUDERS ||
+             h->spec.program == PCL_PROG_BETTER_SCROLLY ||
              (h->spec.program == PCL_PROG_FIXTURE && !h->spec.drape_kind[drape_index])) {
     p.scrolly = 0;
     p.bits = h->st.d_bits[drape_index];
@@ -375,7 +391,7 @@ int pcl_export_curtain(pcl_handle* h, int drape_index, uint8_t* d_out, void* str
 }
 
 int pcl_crop(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d_board, uint8_t* d_crop,
-             void* stream) {
+             int32_t* d_crop_state, void* stream) {
   if (!h || !crop || !d_board || !d_crop) return PCL_ERR_INVALID;
   if (!h->bound) return PCL_ERR_UNBOUND;
   if (crop->rows <= 0 || crop->cols <= 0 || crop->sprite_index >= h->spec.n_sprites)
@@ -390,6 +406,7 @@ int pcl_crop(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d_board, u
   p.B = h->batch; p.H = h->spec.rows; p.W = h->spec.cols; p.pitch = h->spec.pitch;
   p.S = h->spec.n_sprites; p.crop = *crop;
   p.sprites = h->st.d_sprites; p.plot = h->st.d_plot; p.board = d_board; p.out = d_crop;
+  p.state = d_crop_state;
   h->launches += 1;
   return pcl::launch_crop(p, (cudaStream_t)stream) == cudaSuccess ? PCL_OK : PCL_ERR_CUDA;
 }

@@ -313,12 +313,10 @@ cudaError_t launch_fixture(const StepParams& p, cudaStream_t s) {
   const int blocks = (p.B + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const size_t board_bytes = ((size_t)p.H * p.pitch + 15) & ~(size_t)15;
   const size_t smem = (sizeof(WarpState) + board_bytes) * kWarpsPerBlock;
-  static size_t configured = 0;
-  if (smem > configured) {
+  if (smem > 48 * 1024) {   // opt in per launch: the attribute is per device, handles are not
     cudaError_t e = cudaFuncSetAttribute(fixture_step,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   fixture_step<<<blocks, kWarpsPerBlock * 32, smem, s>>>(p);
   return cudaGetLastError();

@@ -37,6 +37,7 @@ cudaError_t launch_scrolly_maze(const StepParams& p, cudaStream_t s);
 cudaError_t launch_warehouse(const StepParams& p, cudaStream_t s);
 cudaError_t launch_marauders(const StepParams& p, cudaStream_t s);
 cudaError_t launch_fixture(const StepParams& p, cudaStream_t s);
+cudaError_t launch_better_scrolly(const StepParams& p, cudaStream_t s);
 
 struct RenderParams {
   int B, H, W, pitch, S, D;
@@ -64,6 +65,7 @@ struct CropParams {
   pcl_crop_spec crop;
   const int32_t* sprites;
   int32_t* plot;
+  int32_t* state;                // i32 [B, 4] per-cropper corner state, or NULL
   const uint8_t* board;
   uint8_t* out;
 };

@@ -152,9 +152,13 @@ __global__ void __launch_bounds__(128) crop_kernel(const CropParams p) {
   const int32_t* rec = p.sprites + ((int64_t)env * p.S + (fixed ? 0 : c.sprite_index)) * PCL_SPRITE_WORDS;
   const bool have = !fixed && (rec[PCL_S_FLAGS] & 1);     // _centroid :544-598
   const int crow = fixed ? 0 : rec[PCL_S_ROW], ccol = fixed ? 0 : rec[PCL_S_COL];
-  int wr = fixed ? c.offset_rows : plot[PCL_P_CROP_R];
-  int wc = fixed ? c.offset_cols : plot[PCL_P_CROP_C];
-  const int init = fixed ? 1 : plot[PCL_P_CROP_INIT];
+  // Corner state: the caller's per-cropper array, or the plot record's one slot.
+  int32_t* state = p.state ? p.state + (int64_t)env * 4 : plot + PCL_P_CROP_R;
+  const int episode = plot[PCL_P_EPISODES];
+  int wr = fixed ? c.offset_rows : state[0];
+  int wc = fixed ? c.offset_cols : state[1];
+  // A new episode is a new Engine upstream: set_engine() forgets the corner.
+  const int init = fixed ? 1 : (p.state ? (state[2] && state[3] == episode) : state[2]);
   const bool pad = c.pad_char >= 0;
   auto rectify = [&]() {                                  // :533-542
     wr = max(0, wr) - max(0, wr + c.rows - p.H);
@@ -192,7 +196,10 @@ __global__ void __launch_bounds__(128) crop_kernel(const CropParams p) {
     }
   }
   __syncwarp();
-  if (lane == 0 && !fixed) { plot[PCL_P_CROP_R] = wr; plot[PCL_P_CROP_C] = wc; plot[PCL_P_CROP_INIT] = 1; }
+  if (lane == 0 && !fixed) {
+    state[0] = wr; state[1] = wc; state[2] = 1;
+    if (p.state) state[3] = episode;
+  }
   // _do_crop :118-227: pad fill + window copy.
   const uint8_t* board = p.board + (int64_t)env * p.H * p.pitch;
   uint8_t* out = p.out + (int64_t)env * c.rows * c.cols;

@@ -405,12 +405,10 @@ cudaError_t launch_scrolly_maze(const StepParams& p, cudaStream_t s) {
   const size_t per_warp = kRecWords * 4 + (size_t)p.H * p.pitch +
                           2 * (((size_t)p.H * 12 + 15) & ~(size_t)15);
   const size_t smem = per_warp * kWarpsPerBlock;
-  static size_t configured = 0;
-  if (smem > configured) {
+  if (smem > 48 * 1024) {   // opt in per launch: the attribute is per device, handles are not
     cudaError_t e = cudaFuncSetAttribute(scrolly_maze_step,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   scrolly_maze_step<<<blocks, kWarpsPerBlock * 32, smem, s>>>(p);
   return cudaGetLastError();

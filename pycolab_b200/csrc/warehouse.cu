@@ -252,12 +252,10 @@ warehouse_step(const StepParams p) {
 cudaError_t launch_warehouse(const StepParams& p, cudaStream_t s) {
   const int blocks = (p.B + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const size_t smem = (kRecWords * 4 + (size_t)p.H * p.pitch) * kWarpsPerBlock;
-  static size_t configured = 0;
-  if (smem > configured) {
+  if (smem > 48 * 1024) {   // opt in per launch: the attribute is per device, handles are not
     cudaError_t e = cudaFuncSetAttribute(warehouse_step,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   warehouse_step<<<blocks, kWarpsPerBlock * 32, smem, s>>>(p);
   return cudaGetLastError();

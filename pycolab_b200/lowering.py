@@ -41,6 +41,9 @@ LOWERED_CLASSES = {
     ('extraterrestrial_marauders', 'MarauderDrape'): 'marauders.marauder',
     ('extraterrestrial_marauders', 'UpwardLaserBoltSprite'): 'marauders.up_bolt',
     ('extraterrestrial_marauders', 'DownwardLaserBoltSprite'): 'marauders.down_bolt',
+    ('better_scrolly_maze', 'PlayerSprite'): 'better.player',
+    ('better_scrolly_maze', 'PatrollerSprite'): 'better.patroller',
+    ('better_scrolly_maze', 'CashDrape'): 'better.cash',
     # General entities: the reference's test fixtures and this package's twins.
     ('test_things', 'TestMazeWalker'): 'fixture.walker',
     ('test_things', 'TestScrolly'): 'fixture.scrolly',
@@ -328,6 +331,29 @@ def _lower_marauders(engine, roles):
   return game
 
 
+def _lower_better_scrolly(engine, roles):
+  th = engine.things
+  want = {'P': 'better.player', 'a': 'better.patroller', 'b': 'better.patroller',
+          'c': 'better.patroller', '@': 'better.cash'}
+  if roles != want:
+    raise NotLoweredError('better_scrolly_maze program needs exactly {} (got {})'.format(
+        want, roles))
+  game = LoweredGame()
+  _common(engine, game, _lib.PROG_BETTER_SCROLLY)
+  sprites = [th[c] for c in 'Pabc']
+  records = [_sprite_record(th['P'])]
+  records += [_sprite_record(th[c], aux0=int(bool(th[c]._moving_east))) for c in 'abc']
+  _set_sprites(game, sprites, records)
+  game.drape_chars = '@'
+  game.margins = [(-1, -1)]
+  game.bits = {0: pack_rows(th['@'].curtain, game.bits_words)}
+  rec = [0] * _lib.DRAPE_WORDS
+  rec[_lib.D_LAST_FRAME] = _lib.NEVER
+  game.drapes = np.array([rec], dtype=np.int32)
+  game.plot = np.array(_plot_record(aux0=int(th['@'].curtain.sum())), dtype=np.int32)
+  return game
+
+
 def _lower_fixture(engine, roles):
   th = engine.things
   game = LoweredGame()
@@ -389,4 +415,6 @@ def lower(engine):
     return _lower_marauders(engine, roles)
   if family == 'fixture':
     return _lower_fixture(engine, roles)
+  if family == 'better':
+    return _lower_better_scrolly(engine, roles)
   raise NotLoweredError(family)

@@ -173,6 +173,39 @@ def fixture_scrolly(name, seed, margins, second_ego, T=400):
        curtains=np.stack(curtains).astype(np.uint8))
 
 
+def better_scrolly(name, level, T=400):
+  """better_scrolly_maze stock level + its three croppers (player view with an
+  initial offset and no padding, patroller view padded with (None, 3) margins,
+  fixed teaser window)."""
+  art, offset, teaser = refdriver.ref_better_scrolly_stock(level)
+  rs = np.random.RandomState(700 + level)
+  actions = rs.randint(0, 5, size=T).tolist()
+  sprites, views = [], [[], [], []]
+  state = {}
+
+  def make():
+    eng = refdriver.ref_better_scrolly(level=level)
+    if 'croppers' not in state:
+      state['croppers'] = refdriver.ref_better_scrolly_croppers(level)
+    for c in state['croppers']:
+      c.set_engine(eng)
+    return eng
+
+  rec = sprite_recorder('Pabc', sprites)
+
+  def on_frame(env, out):
+    rec(env, out)
+    for v, c in zip(views, state['croppers']):
+      v.append(c.crop(out[0]).board.copy())
+
+  traj = tj.run_trajectory(make, actions, on_frame=on_frame)
+  save(name, art=tj.art_to_u8(art), starter_offset=np.array(offset, dtype=np.int32),
+       teaser_corner=np.array(teaser, dtype=np.int32),
+       actions=np.array(actions, dtype=np.int32), sprites=np.array(sprites, dtype=np.int32),
+       view_player=np.stack(views[0]), view_patroller=np.stack(views[1]),
+       view_teaser=np.stack(views[2]), **traj)
+
+
 def fixture_directives(name, seed, T=250):
   """Walkers + a static drape with Plot directives injected through
   test_things.post_update: rewards, z-order changes, a final termination."""
@@ -308,6 +341,8 @@ def main():
 
   for seed in range(3):
     fixture_directives('fixture_directives_%d' % seed, seed)
+  for level in (0, 1, 2):
+    better_scrolly('better_stock_L%d' % level, level)
 
   cropper('crop_ego_pad', ' ', (None, None), None, True)
   cropper('crop_margins_nopad', None, (2, 3), None, True)

@@ -53,6 +53,33 @@ def ref_stock_scrolly_art(level):
           m.MAZES_WHAT_LIES_BENEATH[level])
 
 
+def ref_better_scrolly(art=None, level=None):
+  sys.path.insert(0, REFERENCE_ROOT) if REFERENCE_ROOT not in sys.path else None
+  _import()
+  from pycolab.examples import better_scrolly_maze as m
+  if level is not None:
+    return m.make_game(level)
+  saved = m.MAZES_ART
+  try:
+    m.MAZES_ART = [art]
+    return m.make_game(0)
+  finally:
+    m.MAZES_ART = saved
+
+
+def ref_better_scrolly_stock(level):
+  """(art, STARTER_OFFSET, TEASER_CORNER) of a stock better_scrolly_maze level."""
+  _import()
+  from pycolab.examples import better_scrolly_maze as m
+  return list(m.MAZES_ART[level]), tuple(m.STARTER_OFFSET[level]), tuple(m.TEASER_CORNER[level])
+
+
+def ref_better_scrolly_croppers(level):
+  _import()
+  from pycolab.examples import better_scrolly_maze as m
+  return m.make_croppers(level)
+
+
 def ref_warehouse(art, beneath=' ', level=None):
   m = _import()['warehouse_manager']
   if level is not None:

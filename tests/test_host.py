@@ -320,9 +320,24 @@ def test_reference_marauders_example_loads_and_lowers(compat_examples):
 
 @needs_ref
 def test_reference_example_outside_the_lowered_set_is_refused(compat_examples):
-  mod = compat_examples('better_scrolly_maze')
+  mod = compat_examples('hello_world')
   with pytest.raises(NotLoweredError):
-    lowering.lower(mod.make_game(0))
+    lowering.lower(mod.make_game())
+
+
+@needs_ref
+def test_reference_better_scrolly_example_loads_and_lowers(compat_examples):
+  from pycolab_b200.games import better_scrolly_maze as g_better
+  mod = compat_examples('better_scrolly_maze')
+  for level in (0, 1, 2):
+    theirs = lowering.lower(mod.make_game(level))
+    ours = lowering.lower(g_better.make_game(mod.MAZES_ART[level]))
+    assert theirs.program == _lib.PROG_BETTER_SCROLLY
+    _same_lowering(theirs, ours)
+  # the example's own croppers are this package's classes
+  views = mod.make_croppers(0)
+  assert [type(v).__name__ for v in views] == ['ScrollingCropper', 'ScrollingCropper',
+                                               'FixedCropper']
 
 
 @needs_ref

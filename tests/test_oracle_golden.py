@@ -89,6 +89,46 @@ def test_fixture_scrolly(name):
       out = world.play(int(g['actions'][t]))
 
 
+def better_croppers(g, world_or_engine, make_scrolling, make_fixed):
+  """The three better_scrolly_maze views (better_scrolly_maze.py:224-251)."""
+  views = [
+      make_scrolling(10, 30, ['P'], initial_offset=tuple(int(x) for x in g['starter_offset'])),
+      make_scrolling(7, 10, ['c'], pad_char=' ', scroll_margins=(None, 3)),
+      make_fixed(tuple(int(x) for x in g['teaser_corner']), 12, 20, ' '),
+  ]
+  return views
+
+
+@pytest.mark.parametrize('name', gc.names('better_'))
+def test_better_scrolly(name):
+  g = gc.load(name)
+  art = tj.u8_to_art(g['art'])
+  sprites, views = [], [[], [], []]
+  crops = better_croppers(
+      g, None,
+      lambda r, c, t, **kw: em.ScrollingCrop(r, c, t, **kw),
+      lambda corner, r, c, pad: ('fixed', corner, r, c, pad))
+
+  def make():
+    w = games.make_better_scrolly(art)
+    for c in crops[:2]:
+      c.set_engine(w)
+    return w
+
+  def on_frame(env, out):
+    sprites.append(gc.oracle_sprite_rows(env, 'Pabc'))
+    views[0].append(crops[0].crop(out[0]))
+    views[1].append(crops[1].crop(out[0]))
+    _, corner, r, c, pad = crops[2]
+    views[2].append(em.crop_window(out[0], corner, r, c, pad))
+
+  got = tj.run_trajectory(make, g['actions'].tolist(), on_frame=on_frame)
+  tj.assert_same_trajectory(g, got, name)
+  np.testing.assert_array_equal(g['sprites'], np.array(sprites))
+  for key, v in zip(('view_player', 'view_patroller', 'view_teaser'), views):
+    np.testing.assert_array_equal(g[key], np.stack(v), err_msg=key)
+
+
 def directive_actions(row, order):
   """Device action row -> the oracle fixture program's action dict."""
   n = len(order)
