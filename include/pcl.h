@@ -224,6 +224,24 @@ typedef struct pcl_crop_spec {
 int pcl_crop(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d_board,
              uint8_t* d_crop, int32_t* d_crop_state, void* stream);
 
+/* Observation post-processors as one table look-up per cell
+ * (rendering.py:304-661): out[b, d, r, c] = table[board[b, r, c]][d].
+ *   ObservationCharacterRepainter: depth 1, u8 table = the character mapping;
+ *   ObservationToArray:            the value mapping (scalars or depth-vectors);
+ *   ObservationToFeatureArray:     f32 one-hot, table[ch][d] = (ch == layers[d]).
+ * d_table is [128, depth] of `dtype`; d_valid u8 [128] marks characters the
+ * mapping knows (NULL = all); a board holding an unknown character sets
+ * *d_unknown (i32, may be NULL) to 1 (upstream RuntimeError, rendering.py:520-526).
+ * Output strides are in ELEMENTS, so any `permute` is just a stride choice. */
+typedef struct pcl_observe_spec {
+  int32_t depth;
+  int32_t dtype;              /* 0 uint8, 1 int32, 2 float32, 3 int64, 4 float64 */
+  int64_t stride_b, stride_d, stride_r, stride_c;
+} pcl_observe_spec;
+int pcl_observe(pcl_handle* h, const pcl_observe_spec* spec, const void* d_table,
+                const uint8_t* d_valid, const uint8_t* d_board, void* d_out,
+                int32_t* d_unknown, void* stream);
+
 /* Copy the per-env latched error words (PCL_ENV_ERR_*) to d_out i32 [B]. */
 int pcl_error_codes(pcl_handle* h, int32_t* d_out, void* stream);
 

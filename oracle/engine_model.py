@@ -545,6 +545,41 @@ class ScrollingCrop(object):
     return crop_window(board, self.corner, self.rows, self.cols, self.pad)
 
 
+# --------------------------------------------------------------------------
+# Observation post-processors (rendering.py:304-661), board-only restatements.
+# --------------------------------------------------------------------------
+
+def observation_to_array(board, value_mapping, dtype=None, permute=None):
+  """rendering.py:409-542."""
+  first = next(iter(value_mapping.values()))
+  dtype = dtype if dtype is not None else np.array(first).dtype
+  try:
+    depth, is_3d = len(first), True
+  except TypeError:
+    depth, is_3d = 1, False
+  out = np.zeros((depth,) + board.shape, dtype=dtype)
+  for code in np.unique(board):
+    if chr(code) not in value_mapping:
+      raise RuntimeError('character %r outside the value mapping' % chr(code))
+    out[:, board == code] = np.reshape(value_mapping[chr(code)], (depth, 1))
+  result = out if is_3d else out[0]
+  return result if permute is None else np.transpose(result, permute)
+
+
+def observation_repaint(board, character_mapping):
+  """rendering.py:304-406 (board part)."""
+  lut = np.arange(256, dtype=np.uint8)
+  for src, dst in character_mapping.items():
+    lut[ord(src)] = ord(dst)
+  return lut[board]
+
+
+def observation_to_feature_array(board, layers, permute=None):
+  """rendering.py:545-661 with occluded layers (board == ord(c))."""
+  out = np.stack([(board == ord(c)).astype(np.float32) for c in layers])
+  return out if permute is None else np.transpose(out, permute)
+
+
 def crop_window(board, corner, rows, cols, pad_char):
   """cropping.py:118-227 `_do_crop`, board part."""
   top, left = corner

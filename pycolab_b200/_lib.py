@@ -107,6 +107,11 @@ class CropSpec(C.Structure):
               ('offset_cols', C.c_int32), ('saccade', C.c_int32)]
 
 
+class ObserveSpec(C.Structure):
+  _fields_ = [('depth', C.c_int32), ('dtype', C.c_int32), ('stride_b', C.c_int64),
+              ('stride_d', C.c_int64), ('stride_r', C.c_int64), ('stride_c', C.c_int64)]
+
+
 # name -> (restype, argtypes); every symbol include/pcl.h declares.
 SYMBOLS = {
     'pcl_abi_version': (C.c_int, []),
@@ -125,6 +130,8 @@ SYMBOLS = {
     'pcl_export_curtain': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     'pcl_crop': (C.c_int, [C.c_void_p, C.POINTER(CropSpec), C.c_void_p, C.c_void_p,
                            C.c_void_p, C.c_void_p]),
+    'pcl_observe': (C.c_int, [C.c_void_p, C.POINTER(ObserveSpec), C.c_void_p, C.c_void_p,
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'pcl_error_codes': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     'pcl_launch_count': (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
 }

@@ -309,6 +309,40 @@ class BatchedEngine(object):
                                   self._stream()), 'pcl_crop')
     return out
 
+  # --- observation post-processors (rendering.py:304-661) over the whole batch
+  def to_feature_array(self, layers, permute=None):
+    """ObservationToFeatureArray: float32 one-hot planes, [B, C, rows, cols] (or
+    the last three axes permuted)."""
+    from pycolab_b200 import observers
+    permute = observers.check_permute(permute, True, 'ObservationToFeatureArray')
+    return observers.observe(self._lib, self._h, self._board, self.rows, self.cols,
+                             observers.feature_table(layers), None, True, permute,
+                             self._stream())
+
+  def to_array(self, value_mapping, dtype=None, permute=None):
+    """ObservationToArray: map characters to scalars ([B, rows, cols]) or vectors
+    ([B, D, rows, cols]); raises RuntimeError on a character outside the mapping."""
+    from pycolab_b200 import observers
+    torch = _torch()
+    table, valid, is_3d = observers.value_table(value_mapping, dtype)
+    permute = observers.check_permute(permute, is_3d, 'ObservationToArray')
+    unknown = torch.zeros((1,), dtype=torch.int32, device=self.device)
+    out = observers.observe(self._lib, self._h, self._board, self.rows, self.cols, table,
+                            valid, is_3d, permute, self._stream(), unknown)
+    if int(unknown[0]):
+      raise RuntimeError(
+          'This ObservationToArray only knows array values for the characters {}, but it '
+          'received an observation with a character not in that set'.format(
+              ''.join(value_mapping.keys())))
+    return out
+
+  def repaint(self, character_mapping):
+    """ObservationCharacterRepainter over every board: u8 [B, rows, cols]."""
+    from pycolab_b200 import observers
+    return observers.observe(self._lib, self._h, self._board, self.rows, self.cols,
+                             observers.repaint_table(character_mapping), None, False, None,
+                             self._stream())
+
   def sprite_state(self):
     """i32 [B, S, 8] device tensor of sprite records (PCL_S_* words)."""
     return self.sprites

@@ -411,6 +411,25 @@ int pcl_crop(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d_board, u
   return pcl::launch_crop(p, (cudaStream_t)stream) == cudaSuccess ? PCL_OK : PCL_ERR_CUDA;
 }
 
+int pcl_observe(pcl_handle* h, const pcl_observe_spec* spec, const void* d_table,
+                const uint8_t* d_valid, const uint8_t* d_board, void* d_out,
+                int32_t* d_unknown, void* stream) {
+  if (!h || !spec || !d_table || !d_board || !d_out) return PCL_ERR_INVALID;
+  if (spec->depth < 1 || spec->depth > 32 || spec->dtype < 0 || spec->dtype > 4)
+    return PCL_ERR_INVALID;
+  pcl::ObserveParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = h->batch; p.H = h->spec.rows; p.W = h->spec.cols; p.pitch = h->spec.pitch;
+  p.depth = spec->depth; p.dtype = spec->dtype;
+  p.words = spec->dtype >= 3 ? 2 : 1;
+  p.stride_b = spec->stride_b * p.words; p.stride_d = spec->stride_d * p.words;
+  p.stride_r = spec->stride_r * p.words; p.stride_c = spec->stride_c * p.words;
+  p.table = d_table; p.valid = d_valid; p.board = d_board; p.out = d_out;
+  p.unknown = d_unknown;
+  h->launches += 1;
+  return pcl::launch_observe(p, (cudaStream_t)stream) == cudaSuccess ? PCL_OK : PCL_ERR_CUDA;
+}
+
 int pcl_error_codes(pcl_handle* h, int32_t* d_out, void* stream) {
   if (!h || !d_out) return PCL_ERR_INVALID;
   if (!h->bound) return PCL_ERR_UNBOUND;

@@ -60,6 +60,18 @@ struct ExportParams {
 };
 cudaError_t launch_export_curtain(const ExportParams& p, cudaStream_t s);
 
+struct ObserveParams {
+  int B, H, W, pitch, depth, dtype;
+  int words;                     // 32-bit words per element (2 for int64 / float64)
+  int64_t stride_b, stride_d, stride_r, stride_c;   // in 32-bit words (bytes for uint8)
+  const void* table;             // [128, depth]
+  const uint8_t* valid;          // u8 [128] or NULL
+  const uint8_t* board;          // u8 [B, H, pitch]
+  void* out;
+  int32_t* unknown;              // i32 [1] or NULL
+};
+cudaError_t launch_observe(const ObserveParams& p, cudaStream_t s);
+
 struct CropParams {
   int B, H, W, pitch, S;
   pcl_crop_spec crop;

@@ -89,6 +89,105 @@ class BaseObservationRenderer(object):
     return (self._rows, self._cols)
 
 
+class _BoardOnDevice(object):
+  """A batch-1 handle (no step program) to run pcl_observe over one board."""
+
+  def __init__(self):
+    self._handles = {}
+
+  def __call__(self, board, table, valid, is_3d, permute, want_unknown=False):
+    import torch
+    from pycolab_b200 import _lib
+    from pycolab_b200 import observers
+    lib = _lib.load()
+    rows, cols = board.shape
+    pitch = (cols + 15) // 16 * 16
+    key = (rows, cols)
+    if key not in self._handles:
+      spec = _lib.Spec()
+      spec.abi_version, spec.program = _lib.ABI_VERSION, _lib.PROG_NONE
+      spec.rows, spec.cols, spec.pitch = rows, cols, pitch
+      handle = C.c_void_p()
+      _lib.check(lib.pcl_create(C.byref(spec), 1, 0, C.byref(handle)), 'pcl_create')
+      self._handles[key] = handle
+    dev = torch.device('cuda', 0)
+    padded = np.zeros((1, rows, pitch), dtype=np.uint8)
+    padded[0, :, :cols] = board
+    t_board = torch.from_numpy(padded).to(dev)
+    unknown = torch.zeros((1,), dtype=torch.int32, device=dev) if want_unknown else None
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    out = observers.observe(lib, self._handles[key], t_board, rows, cols, table, valid,
+                            is_3d, permute, stream, unknown)
+    torch.cuda.synchronize(dev)
+    return out[0].cpu().numpy(), (bool(int(unknown[0])) if want_unknown else False)
+
+
+_on_device = _BoardOnDevice()
+
+
+class ObservationToArray(object):
+  """Characters -> scalars or vectors (rendering.py:409-542); device look-up."""
+
+  def __init__(self, value_mapping, dtype=None, permute=None):
+    from pycolab_b200 import observers
+    self._value_mapping = value_mapping
+    self._table, self._valid, self._is_3d = observers.value_table(value_mapping, dtype)
+    try:
+      self._permute = observers.check_permute(permute, self._is_3d, 'ObservationToArray')
+    except ValueError:
+      kind = ('1-D vectors' if self._is_3d else 'scalars')
+      nums = ('0, 1, and 2' if self._is_3d else '0 and 1')
+      raise ValueError(
+          'When the value mapping contains {}, the permute argument to the '
+          'ObservationToArray constructor must be a list or tuple containing some '
+          'permutation of the integers {}.'.format(kind, nums))
+
+  def __call__(self, observation):
+    out, unknown = _on_device(observation.board, self._table, self._valid, self._is_3d,
+                              self._permute, want_unknown=True)
+    if unknown:
+      raise RuntimeError(
+          'This ObservationToArray only knows array values for the characters {}, but it '
+          'received an observation with a character not in that set'.format(
+              str(''.join(self._value_mapping.keys()))))
+    return out
+
+
+class ObservationCharacterRepainter(object):
+  """Repaint characters through a mapping (rendering.py:304-406): returns an
+  `Observation` whose layers follow the repainted board."""
+
+  def __init__(self, character_mapping):
+    from pycolab_b200 import observers
+    self._character_mapping = character_mapping
+    self._table = observers.repaint_table(character_mapping)
+
+  def __call__(self, original_observation):
+    board, _ = _on_device(original_observation.board, self._table, None, False, None)
+    chars = (set(original_observation.layers) - set(self._character_mapping)).union(
+        self._character_mapping.values())
+    return Observation(board=board, layers=LazyLayers(board, chars))
+
+
+class ObservationToFeatureArray(object):
+  """One-hot float32 feature planes for the chosen layers (rendering.py:545-661)."""
+
+  def __init__(self, layers, permute=None):
+    from pycolab_b200 import observers
+    self._layers = layers
+    self._table = observers.feature_table(layers)
+    self._permute = observers.check_permute(permute, True, 'ObservationToFeatureArray')
+
+  def __call__(self, observation):
+    if not any(l in observation.layers for l in self._layers):
+      raise RuntimeError(
+          'The layers argument to this ObservationToFeatureArray, {!r}, has no entry that '
+          'refers to an actual feature in the input observation. Actual features in the '
+          'observation are {!r}.'.format(self._layers, ''.join(sorted(observation.layers))))
+    out, _ = _on_device(observation.board, self._table, None, True, self._permute)
+    return out
+
+
 def render_on_device(backdrop, painted, device=0):
   """One `pcl_render` launch for a single canvas; returns uint8 [rows, cols].
 
