@@ -186,8 +186,12 @@ class Engine(object):
                          'not exist')
     if errors & _lib.ENV_ERR_INDEX:
       raise IndexError('a board look-up fell off the array')
-    self._board = rendering.Observation(
-        board=board, layers=rendering.LazyLayers(board, self._chars))
+    if self._occlusion_in_layers:
+      layers = rendering.LazyLayers(board, self._chars)
+    else:
+      layers = rendering.UnoccludedLayers(self._backdrop.curtain,
+                                          dict(self._sprites_and_drapes), self._chars)
+    self._board = rendering.Observation(board=board, layers=layers)
     return self._board, reward, discount
 
   def _sync_things(self):

@@ -38,7 +38,7 @@ class FixtureDrape(plab_things.Drape):
 
 
 def make_game(art, what_lies_beneath, walkers, scrollys=None, drapes='',
-              update_schedule=None, z_order=None):
+              update_schedule=None, z_order=None, occlusion_in_layers=True):
   """walkers: {char: dict(impassable, confined, egocentric)}; scrollys:
   {char: dict(pattern, corner, margins)}; drapes: chars of static drapes."""
   scrollys = scrollys or {}
@@ -60,7 +60,8 @@ def make_game(art, what_lies_beneath, walkers, scrollys=None, drapes='',
   if update_schedule is None:
     update_schedule = [chars]
   return ascii_art.ascii_art_to_game(art, what_lies_beneath, sprites, dr,
-                                     update_schedule=update_schedule, z_order=z_order)
+                                     update_schedule=update_schedule, z_order=z_order,
+                                     occlusion_in_layers=occlusion_in_layers)
 
 
 def action_rows(game_or_lowered, motions, reward=None, terminate=False, z=None):

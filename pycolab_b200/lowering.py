@@ -221,8 +221,13 @@ def _common(engine, game, program):
   game.backdrop = np.zeros((engine.rows, game.pitch), dtype=np.uint8)
   game.backdrop[:, :engine.cols] = backdrop.curtain
   game.backdrop_chars = ''.join(sorted(backdrop.palette))
-  if not engine._occlusion_in_layers:
-    raise NotLoweredError('occlusion_in_layers=False is not lowered yet')
+  # Unoccluded layers (rendering.py:187-301) change what `layers[...]` look-ups
+  # inside update() see; only programs whose logic never reads layers keep
+  # their semantics, so only those accept occlusion_in_layers=False.
+  if not engine._occlusion_in_layers and program not in (_lib.PROG_SCROLLY_MAZE,
+                                                         _lib.PROG_FIXTURE):
+    raise NotLoweredError('occlusion_in_layers=False is lowered only for games whose '
+                          'entities never consult `layers`')
 
 
 def _set_sprites(game, sprites, records):

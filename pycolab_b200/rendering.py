@@ -46,6 +46,40 @@ class LazyLayers(collections.abc.Mapping):
     return len(self._chars)
 
 
+class UnoccludedLayers(collections.abc.Mapping):
+  """Layers of `BaseUnoccludedObservationRenderer` (rendering.py:187-301): every
+  character's mask shows where its owner PLACES it, hidden or not — backdrop
+  characters where the backdrop holds them, a drape's whole curtain, a visible
+  sprite's cell.  Built on demand from the entity state mirrored off the device."""
+
+  def __init__(self, backdrop, things, chars):
+    self._backdrop = backdrop
+    self._things = things
+    self._chars = frozenset(chars)
+    self._cache = {}
+
+  def __getitem__(self, char):
+    if char not in self._chars:
+      raise KeyError(char)
+    if char not in self._cache:
+      mask = self._backdrop == ord(char)
+      ent = self._things.get(char)
+      if ent is not None:
+        if hasattr(ent, 'curtain'):
+          mask = mask | np.asarray(ent.curtain, dtype=bool)
+        elif ent.visible:
+          mask = mask.copy()
+          mask[tuple(ent.position)] = True
+      self._cache[char] = mask
+    return self._cache[char]
+
+  def __iter__(self):
+    return iter(self._chars)
+
+  def __len__(self):
+    return len(self._chars)
+
+
 class BaseObservationRenderer(object):
   """GPU-backed canvas with the reference's painter API (rendering.py:69-184)."""
 
@@ -186,6 +220,27 @@ class ObservationToFeatureArray(object):
           'observation are {!r}.'.format(self._layers, ''.join(sorted(observation.layers))))
     out, _ = _on_device(observation.board, self._table, None, True, self._permute)
     return out
+
+
+class BaseUnoccludedObservationRenderer(BaseObservationRenderer):
+  """Same canvas protocol; layers ignore occlusion (rendering.py:187-301).  The
+  board is still flattened on the GPU; the layers are the painted masks."""
+
+  def render(self):
+    board = render_on_device(self._backdrop, self._painted)
+    layers = {}
+    for ch in self._chars:
+      mask = self._backdrop == ord(ch)
+      for kind, painted_ch, data in self._painted:
+        if painted_ch != ch:
+          continue
+        if kind == 'drape':
+          mask = mask | data
+        else:
+          mask = mask.copy()
+          mask[data] = True
+      layers[ch] = mask
+    return Observation(board=board, layers=layers)
 
 
 def render_on_device(backdrop, painted, device=0):

@@ -206,6 +206,47 @@ def better_scrolly(name, level, T=400):
        view_teaser=np.stack(views[2]), **traj)
 
 
+def fixture_unoccluded(name, seed, T=120):
+  """occlusion_in_layers=False (BaseUnoccludedObservationRenderer,
+  rendering.py:187-301): per-frame layers of every character."""
+  rs = np.random.RandomState(6000 + seed)
+  PH, PW, H, W = 13, 17, 7, 10
+  pattern = rs.random_sample((PH, PW)) < 0.25
+  corner = (int(rs.randint(0, PH - H + 1)), int(rs.randint(0, PW - W + 1)))
+  art = np.full((H, W), ord(' '), dtype=np.uint8)
+  art[rs.random_sample((H, W)) < 0.15] = ord('.')
+  art[1:4, 2:7] = ord('%')
+  art[3, 4] = ord('P')
+  art[5, 7] = ord('q')
+  art_l = tj.u8_to_art(art)
+  walkers = {'P': dict(impassable='#', egocentric=True),
+             'q': dict(impassable='', confined=True)}
+  scrollys = {'#': dict(pattern=pattern, corner=corner, margins=(2, 3))}
+  schedule = [['#'], ['P', 'q', '%']]
+  z_order = 'q%#P'
+  env = refdriver.ref_fixture(art_l, ' ', walkers, scrollys, drapes='%',
+                              update_schedule=schedule, z_order=z_order,
+                              occlusion_in_layers=False)
+  out = env.its_showtime()
+  chars = ''.join(sorted(out[0].layers))
+  boards, layers = [], []
+
+  def record(out):
+    boards.append(tj.board_of(out[0]).copy())
+    layers.append(np.stack([np.array(out[0].layers[c], dtype=bool) for c in chars]))
+  record(out)
+  motions = rs.randint(0, 9, size=T)
+  for m in motions:
+    record(env.play(refdriver.fixture_actions_to_ref(int(m))))
+  cfg = dict(walkers=walkers,
+             scrollys={'#': dict(corner=list(corner), margins=[2, 3])},
+             drapes='%', schedule=schedule, z_order=z_order, what_lies_beneath=' ',
+             action_chars='', layer_chars=chars)
+  save(name, art=art, config=np.frombuffer(json.dumps(cfg).encode(), np.uint8),
+       pattern_hash=pattern.astype(np.uint8), actions=motions.astype(np.int32),
+       boards=np.stack(boards), layers=np.stack(layers).astype(np.uint8))
+
+
 def fixture_directives(name, seed, T=250):
   """Walkers + a static drape with Plot directives injected through
   test_things.post_update: rewards, z-order changes, a final termination."""
@@ -343,6 +384,8 @@ def main():
     fixture_directives('fixture_directives_%d' % seed, seed)
   for level in (0, 1, 2):
     better_scrolly('better_stock_L%d' % level, level)
+  for seed in range(2):
+    fixture_unoccluded('fixture_unoccluded_%d' % seed, seed)
 
   cropper('crop_ego_pad', ' ', (None, None), None, True)
   cropper('crop_margins_nopad', None, (2, 3), None, True)

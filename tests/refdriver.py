@@ -119,7 +119,7 @@ _NAMES = ('n', 'ne', 'e', 'se', 's', 'sw', 'w', 'nw', 'stay')
 
 
 def ref_fixture(art, what_lies_beneath, walkers, scrollys=None, drapes='',
-                update_schedule=None, z_order=None):
+                update_schedule=None, z_order=None, occlusion_in_layers=True):
   """Same signature as oracle.games.make_fixture_world, built from the
   reference's own test fixtures (tests/test_things.py)."""
   mods = _import()
@@ -147,7 +147,8 @@ def ref_fixture(art, what_lies_beneath, walkers, scrollys=None, drapes='',
   if update_schedule is None:
     update_schedule = [chars]
   return aa.ascii_art_to_game(art, what_lies_beneath, sprites, dr,
-                              update_schedule=update_schedule, z_order=z_order)
+                              update_schedule=update_schedule, z_order=z_order,
+                              occlusion_in_layers=occlusion_in_layers)
 
 
 def fixture_actions_to_ref(actions):

@@ -120,6 +120,49 @@ def test_fixture_directives_golden(name):
   assert int(eng.error_codes().abs().max()) == 0
 
 
+@pytest.mark.parametrize('name', gc.names('fixture_unoccluded_'))
+def test_unoccluded_layers_golden(name):
+  """occlusion_in_layers=False through the facade (rendering.py:187-301)."""
+  from pycolab_b200.games import fixtures
+  g = gc.load(name)
+  kw, cfg = gc.fixture_kwargs(g)
+  game = fixtures.make_game(kw['art'], kw['what_lies_beneath'], kw['walkers'],
+                            kw['scrollys'], kw['drapes'], kw['update_schedule'],
+                            kw['z_order'], occlusion_in_layers=False)
+  names = ('n', 'ne', 'e', 'se', 's', 'sw', 'w', 'nw', 'stay')
+  obs, _, _ = game.its_showtime()
+  chars = cfg['layer_chars']
+  for t in range(len(g['actions']) + 1):
+    np.testing.assert_array_equal(obs.board, g['boards'][t], err_msg='t=%d' % t)
+    assert ''.join(sorted(obs.layers)) == chars
+    for i, ch in enumerate(chars):
+      np.testing.assert_array_equal(obs.layers[ch], g['layers'][t][i].astype(bool),
+                                    err_msg='layer %r t=%d' % (ch, t))
+    if t < len(g['actions']):
+      obs, _, _ = game.play(names[int(g['actions'][t])])
+
+
+def test_unoccluded_renderer_class():
+  from pycolab_b200 import rendering
+  r = rendering.BaseUnoccludedObservationRenderer(3, 4, 'ab. ')
+  r.clear()
+  bd = np.full((3, 4), ord('.'), np.uint8)
+  bd[0, 0] = ord(' ')
+  r.paint_all_of(bd)
+  mask = np.zeros((3, 4), bool)
+  mask[1, :] = True
+  r.paint_drape('a', mask)
+  r.paint_sprite('b', (1, 2))
+  obs = r.render()
+  want = bd.copy()
+  want[1, :] = ord('a')
+  want[1, 2] = ord('b')
+  np.testing.assert_array_equal(obs.board, want)
+  np.testing.assert_array_equal(obs.layers['a'], mask)          # not occluded by b
+  np.testing.assert_array_equal(obs.layers['.'], bd == ord('.'))  # nor the backdrop by a
+  assert obs.layers['b'].sum() == 1 and obs.layers['b'][1, 2]
+
+
 def test_fixture_per_env_actions_vs_oracle():
   """Every env gets its own random motions; auto-reset off; vs the oracle."""
   from pycolab_b200 import batched
