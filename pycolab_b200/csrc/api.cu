@@ -73,7 +73,8 @@ int validate(const pcl_spec& s) {
         if (s.sprite_egocentric[i] != (i == 0)) return PCL_ERR_UNSUPPORTED;
       }
       if (s.pattern_rows < s.rows || s.pattern_cols < s.cols) return PCL_ERR_INVALID;
-      if (s.pattern_words < (s.pattern_cols + 31) / 32 + 2) return PCL_ERR_INVALID;
+      if ((s.pattern_words & 1) || s.pattern_words < (((s.pattern_cols - s.cols) >> 5) & ~1) + 4 ||
+          s.pattern_words < (s.pattern_cols + 31) / 32 + 1) return PCL_ERR_INVALID;
       if (s.cols > 64) return PCL_ERR_UNSUPPORTED;   // window rows are staged as 3 words
       for (int d = 0; d < 2; ++d) {
         const int mr = s.margins[d][0], mc = s.margins[d][1];

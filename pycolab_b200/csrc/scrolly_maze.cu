@@ -62,16 +62,35 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
-// 16 window bits starting at bit `off` (< 80) of a 3-word staged row.
-__device__ __forceinline__ unsigned window16(const uint32_t* row3, int off) {
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::
+               "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+
+// A 64-cell window row starts at bit corner_c of its pattern row; the four words
+// from the even word at or below corner_c >> 5 always cover it (<= 31 + 32 + 64
+// bits), and pattern rows are 8-byte aligned (pattern_words is even), so a row is
+// staged with two 8-byte cp.async into a 16-byte smem slot.
+// 16 window bits starting at bit `off` (< 112) of such a 4-word staged row.
+__device__ __forceinline__ unsigned window16(const uint32_t* row4, int off) {
   const int w = off >> 5, sh = off & 31;
-  const uint32_t lo = row3[w];
-  const uint32_t hi = row3[w < 2 ? w + 1 : 2];
+  const uint32_t lo = row4[w];
+  const uint32_t hi = row4[w < 3 ? w + 1 : 3];
   return __funnelshift_r(lo, hi, sh) & 0xffffu;
 }
 
 __device__ __forceinline__ size_t warp_smem_bytes(int H, int pitch) {
-  return kRecWords * 4 + (size_t)H * pitch + 2 * (((size_t)H * 12 + 15) & ~(size_t)15);
+  return kRecWords * 4 + (size_t)H * pitch + 2 * ((size_t)H * 16);
+}
+
+// Programmatic dependent launch: let the next kernel of the stream begin its
+// launch/prologue while this one runs, and wait for everything earlier in the
+// stream before touching global memory.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait_prior_grids() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7)
@@ -90,6 +109,7 @@ scrolly_maze_step(const StepParams p) {
     }
     s_sel[idx] = (uint16_t)sel;
   }
+  pdl_launch_dependents();
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -101,7 +121,10 @@ scrolly_maze_step(const StepParams p) {
   int32_t* rec = reinterpret_cast<int32_t*>(my);
   uint8_t* s_bd = my + kRecWords * 4;
   uint32_t* s_wall = reinterpret_cast<uint32_t*>(s_bd + (size_t)H * p.pitch);
-  uint32_t* s_coin = s_wall + ((H * 3 + 3) & ~3);
+  uint32_t* s_coin = s_wall + H * 4;
+  // Everything above ran without touching global memory; from here on the
+  // kernel reads state earlier work in the stream may have produced.
+  pdl_wait_prior_grids();
 
   int32_t* g_sprites = p.st.d_sprites + (int64_t)env * kS * PCL_SPRITE_WORDS;
   int32_t* g_drapes = p.st.d_drapes + (int64_t)env * 2 * PCL_DRAPE_WORDS;
@@ -110,6 +133,11 @@ scrolly_maze_step(const StepParams p) {
   uint32_t* coin_pat = p.st.d_pattern[1] + (int64_t)env * p.st.pattern_bstride[1];
   const uint8_t* backdrop = p.st.d_backdrop + (int64_t)env * p.st.backdrop_bstride;
 
+  // ---- 0. the backdrop tile depends on nothing: get it moving first --------
+  {
+    const int n16 = (H * p.pitch) >> 4;
+    for (int i = lane; i < n16; i += 32) cp_async16(s_bd + i * 16, backdrop + i * 16);
+  }
   // ---- 1. records -> smem (coalesced) ------------------------------------
   rec[lane] = g_sprites[lane];
   rec[32 + lane] = lane < 16 ? g_drapes[lane] : g_plot[lane - 16];
@@ -118,10 +146,13 @@ scrolly_maze_step(const StepParams p) {
   bool restart;                              // engine.py:520-581, 619-624
   if (p.mode == MODE_RESET) {
     restart = (p.env_mask == nullptr) || (p.env_mask[env] != 0);
-    if (!restart) return;
+    if (!restart) { cp_async_wait_all(); return; }
   } else {
     restart = was_over && p.auto_reset;
-    if (was_over && !p.auto_reset) return;   // reference raises; env stays frozen
+    if (was_over && !p.auto_reset) {         // reference raises; env stays frozen
+      cp_async_wait_all();
+      return;
+    }
   }
   int action;
   if (restart) {
@@ -191,15 +222,13 @@ scrolly_maze_step(const StepParams p) {
   const int cc_pred = coins.corner_c + (ordered && motion != PCL_M_NONE ? plot.order_c : 0);
 
   // ---- 3. one batch of loads ---------------------------------------------
+  const int we = (wc >> 5) & ~1, ce = (cc_pred >> 5) & ~1;   // first staged word (even)
   {
-    const int n16 = (H * p.pitch) >> 4;
-    for (int i = lane; i < n16; i += 32) cp_async16(s_bd + i * 16, backdrop + i * 16);
-    const int nrow = H * 3;
-    const int ww0 = wc >> 5, cw0 = cc_pred >> 5;
-    for (int i = lane; i < nrow; i += 32) {
-      const int r = i / 3, k = i - r * 3;
-      cp_async4(s_wall + i, wall_pat + (int64_t)(wr + r) * PWW + ww0 + k);
-      cp_async4(s_coin + i, coin_pat + (int64_t)(cr_pred + r) * PWW + cw0 + k);
+    const int nhalf = H * 2;                 // two 8-byte halves per window row
+    for (int i = lane; i < nhalf; i += 32) {
+      const int r = i >> 1, k = (i & 1) * 2;
+      cp_async8(s_wall + i * 2, wall_pat + (int64_t)(wr + r) * PWW + we + k);
+      cp_async8(s_coin + i * 2, coin_pat + (int64_t)(cr_pred + r) * PWW + ce + k);
     }
   }
   // Walker start positions: every look-up below is relative to these.
@@ -345,19 +374,18 @@ scrolly_maze_step(const StepParams p) {
     p.out.d_done[env] = (uint8_t)dir.game_over;
     // The coin window was staged before the pick-up: clear the bit there too.
     if (picked_r >= 0) {
-      const int r2 = picked_r - cr_pred, b = picked_c - ((cc_pred >> 5) << 5);
-      if ((unsigned)r2 < (unsigned)H && (unsigned)b < 96u)
-        s_coin[r2 * 3 + (b >> 5)] &= ~(1u << (b & 31));
+      const int r2 = picked_r - cr_pred, b = picked_c - (ce << 5);
+      if ((unsigned)r2 < (unsigned)H && (unsigned)b < 128u)
+        s_coin[r2 * 4 + (b >> 5)] &= ~(1u << (b & 31));
     }
   }
   const int cr = coins.corner_r, cc = coins.corner_c;
+  int ce_final = ce;
   if (cr != cr_pred || cc != cc_pred) {      // '@' issued its own order: restage
     __syncwarp();
-    const int nrow = H * 3, cw0 = cc >> 5;
-    for (int i = lane; i < nrow; i += 32) {
-      const int r = i / 3, k = i - r * 3;
-      s_coin[i] = coin_pat[(int64_t)(cr + r) * PWW + cw0 + k];
-    }
+    ce_final = (cc >> 5) & ~1;
+    for (int i = lane; i < H * 4; i += 32)
+      s_coin[i] = coin_pat[(int64_t)(cr + (i >> 2)) * PWW + ce_final + (i & 3)];
   }
   __syncwarp();
   g_sprites[lane] = rec[lane];
@@ -365,53 +393,86 @@ scrolly_maze_step(const StepParams p) {
   else g_plot[lane - 16] = rec[32 + lane];
 
   // ---- 5. final render, z-order a b c @ # P (engine.py:737-759) ----------
+  // The loop body is the bandwidth-critical code: no divisions, no 64-bit
+  // address math, no per-sprite tests.  a, b, c lie under both drapes, so they
+  // are patched into the staged backdrop up front (in z-order, by one lane); the
+  // player is the top layer and is patched into the one segment that holds it.
   uint8_t* board = p.out.d_board + (int64_t)env * H * p.pitch;
-  const int segs_per_row = p.pitch >> 4;
-  const int total = H * segs_per_row;
-  const int wsh = wc & 31, csh = cc & 31;
-  const int stale_r = coins.aux0, stale_c = coins.aux1;
-  for (int seg = lane; seg < total; seg += 32) {
-    const int r = seg / segs_per_row;
-    const int c0 = (seg - r * segs_per_row) << 4;
-    const int ncols = min(16, W - c0);
-    const unsigned valid = (1u << ncols) - 1u;
-    uint4 px = *reinterpret_cast<const uint4*>(s_bd + (size_t)r * p.pitch + c0);
-    unsigned coin_bits = window16(s_coin + r * 3, csh + c0) & valid;
-    const unsigned wall_bits = window16(s_wall + r * 3, wsh + c0) & valid;
-    if (r == stale_r && (unsigned)(stale_c - c0) < 16u) coin_bits |= 1u << (stale_c - c0);
+  const int pitch = p.pitch;
+  const int spr = pitch >> 4;                // 16-byte segments per row
+  const int total = H * spr;
+  const int wsh = wc - (we << 5), csh = cc - (ce_final << 5);   // bit offsets in staged rows
+  const int stale_seg = coins.aux0 >= 0 ? coins.aux0 * spr + (coins.aux1 >> 4) : -1;
+  const unsigned stale_bit = 1u << (coins.aux1 & 15);
+  const int p_seg = visible(sp[0]) ? sp[0].row * spr + (sp[0].col >> 4) : -1;
+  const int p_word = (sp[0].col & 15) >> 2;
+  const uint32_t p_keep = ~(0xffu << ((sp[0].col & 3) * 8));
+  const uint32_t p_char = (uint32_t)p.sprite_char[0] << ((sp[0].col & 3) * 8);
+  if (lane == 0) {
 #pragma unroll
-    for (int i = 1; i < kS; ++i) {           // a, b, c lie under both drapes
-      const unsigned m = sprite_bit(sp[i], r, c0);
-      if (m) paint_bits(px, m, p.sprite_char[i]);
+    for (int i = 1; i < kS; ++i)
+      if (visible(sp[i])) s_bd[sp[i].row * pitch + sp[i].col] = p.sprite_char[i];
+  }
+  __syncwarp();
+  const unsigned drape_chars = ('#' << 8) | '@';           // bytes 4 and 5 of the permute
+  const bool ragged = (W & 15) != 0;         // last segment of a row is partly padding
+  int r = lane / spr, sg = lane - r * spr;   // this lane's (row, segment) and its stride
+  const int dr = 32 / spr, dsg = 32 - dr * spr;
+  for (int seg = lane; seg < total; seg += 32) {
+    const int c0 = sg << 4;
+    const int off = r * pitch + c0;
+    uint4 px = *reinterpret_cast<const uint4*>(s_bd + off);
+    unsigned coin_bits = window16(s_coin + r * 4, csh + c0);
+    unsigned wall_bits = window16(s_wall + r * 4, wsh + c0);
+    if (ragged && sg == spr - 1) {
+      const unsigned valid = (1u << (W - c0)) - 1u;
+      coin_bits &= valid; wall_bits &= valid;
     }
-    const unsigned drape_chars = ('#' << 8) | '@';         // bytes 4 and 5 of the permute
+    if (seg == stale_seg) coin_bits |= stale_bit;
     px.x = __byte_perm(px.x, drape_chars, s_sel[((wall_bits & 0xfu) << 4) | (coin_bits & 0xfu)]);
     px.y = __byte_perm(px.y, drape_chars, s_sel[(wall_bits & 0xf0u) | ((coin_bits >> 4) & 0xfu)]);
     px.z = __byte_perm(px.z, drape_chars,
                        s_sel[((wall_bits >> 4) & 0xf0u) | ((coin_bits >> 8) & 0xfu)]);
     px.w = __byte_perm(px.w, drape_chars,
                        s_sel[((wall_bits >> 8) & 0xf0u) | ((coin_bits >> 12) & 0xfu)]);
-    const unsigned m = sprite_bit(sp[0], r, c0);
-    if (m) paint_bits(px, m, p.sprite_char[0]);
-    *reinterpret_cast<uint4*>(board + (int64_t)r * p.pitch + c0) = px;
+    if (seg == p_seg) {
+      if (p_word == 0) px.x = (px.x & p_keep) | p_char;
+      else if (p_word == 1) px.y = (px.y & p_keep) | p_char;
+      else if (p_word == 2) px.z = (px.z & p_keep) | p_char;
+      else px.w = (px.w & p_keep) | p_char;
+    }
+    *reinterpret_cast<uint4*>(board + off) = px;
+    r += dr; sg += dsg;
+    if (sg >= spr) { sg -= spr; ++r; }
   }
 }
 
 }  // namespace
 
 cudaError_t launch_scrolly_maze(const StepParams& p, cudaStream_t s) {
-  if (p.W > 64) return cudaErrorInvalidValue;       // 3-word window rows
+  if (p.W > 64 || (p.PWW & 1)) return cudaErrorInvalidValue;   // 4-word staged window rows
   const int blocks = (p.B + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  const size_t per_warp = kRecWords * 4 + (size_t)p.H * p.pitch +
-                          2 * (((size_t)p.H * 12 + 15) & ~(size_t)15);
+  const size_t per_warp = kRecWords * 4 + (size_t)p.H * p.pitch + 2 * ((size_t)p.H * 16);
   const size_t smem = per_warp * kWarpsPerBlock;
   if (smem > 48 * 1024) {   // opt in per launch: the attribute is per device, handles are not
     cudaError_t e = cudaFuncSetAttribute(scrolly_maze_step,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  scrolly_maze_step<<<blocks, kWarpsPerBlock * 32, smem, s>>>(p);
-  return cudaGetLastError();
+  // Programmatic dependent launch: this kernel may start (prologue only) before
+  // the previous kernel of the stream has drained; it calls griddepcontrol.wait
+  // before its first global access.
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(kWarpsPerBlock * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, scrolly_maze_step, p);
 }
 
 }  // namespace pcl

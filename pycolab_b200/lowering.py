@@ -268,7 +268,7 @@ def _lower_scrolly_maze(engine, roles):
   game.margins = [(-1, -1) if d._scroll_margins is None else tuple(d._scroll_margins)
                   for d in (walls, coins)]
   game.pattern_rows, game.pattern_cols = walls.whole_pattern.shape
-  game.pattern_words = (game.pattern_cols + 31) // 32 + 2
+  game.pattern_words = round_up((game.pattern_cols + 31) // 32 + 3, 2)
   game.patterns = {0: pack_rows(walls.whole_pattern, game.pattern_words),
                    1: pack_rows(coins.whole_pattern, game.pattern_words)}
   game.pattern_mutable = {0: False, 1: True}
@@ -394,7 +394,7 @@ def _lower_fixture(engine, roles):
       game.bits[d] = pack_rows(ent.curtain, game.bits_words)
   if shape is not None:
     game.pattern_rows, game.pattern_cols = shape
-    game.pattern_words = (shape[1] + 31) // 32 + 2
+    game.pattern_words = round_up((shape[1] + 31) // 32 + 3, 2)
     for d, ch in enumerate(drape_chars):
       if game.drape_kind[d]:
         game.patterns[d] = pack_rows(th[ch].whole_pattern, game.pattern_words)
