@@ -66,12 +66,20 @@ __device__ __forceinline__ bool same_cell(const Sprite& a, const Sprite& b) {
   return a.row == b.row && a.col == b.col;
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+constexpr int kRecWords = 96;        // 7 sprites * 8 = 56, 2 drapes * 8 = 16, plot 16, pad
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 7)
 marauders_step(const StepParams p) {
+  // Records are staged in shared memory with coalesced loads; only the fields
+  // this game uses are pulled into registers (keeps the kernel at one wave).
+  __shared__ int32_t s_rec[kWarpsPerBlock][kRecWords];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int lane = threadIdx.x & 31;
   const int env = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (env >= p.B) return;
   const int H = p.H, W = p.W;
+  int32_t* rec = s_rec[threadIdx.x >> 5];
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   int32_t* g_sprites = p.st.d_sprites + (int64_t)env * kS * PCL_SPRITE_WORDS;
   int32_t* g_drapes = p.st.d_drapes + (int64_t)env * 2 * PCL_DRAPE_WORDS;
@@ -80,49 +88,57 @@ marauders_step(const StepParams p) {
   uint32_t* g_mara = p.st.d_bits[1] + (int64_t)env * p.st.bits_bstride[1];
   uint32_t* mt = p.st.d_rng + (int64_t)env * PCL_MT_WORDS;
 
-  Plot plot = load_record_rw<Plot>(g_plot);
+  const int was_over = g_plot[PCL_P_GAME_OVER];
   bool restart;
   if (p.mode == MODE_RESET) {
     restart = (p.env_mask == nullptr) || (p.env_mask[env] != 0);
     if (!restart) return;
   } else {
-    restart = plot.game_over && p.auto_reset;
-    if (plot.game_over && !p.auto_reset) return;
+    restart = was_over && p.auto_reset;
+    if (was_over && !p.auto_reset) return;
   }
-
-  Sprite sp[kS];
-  Drape bunkers, marauders;
-  u64 brow = 0, xrow = 0;          // lane r holds row r of the B / X curtain
-  int action;
   const int BW = p.BW;
   auto load_row = [&](const uint32_t* base) -> u64 {
     if (lane >= H) return 0;
     const uint32_t* row = base + lane * BW;
     return (u64)row[0] | ((u64)row[1] << 32);
   };
-  if (restart) {
-    const int episodes = plot.episodes, error = plot.error;
-    plot = load_record<Plot>(p.st.d_plot_init + (int64_t)env * p.st.plot_init_bstride);
-    plot.episodes = episodes + 1;
-    plot.error = error;
-    const int32_t* si = p.st.d_sprites_init + (int64_t)env * p.st.sprites_init_bstride;
-#pragma unroll
-    for (int i = 0; i < kS; ++i) sp[i] = load_record<Sprite>(si + i * PCL_SPRITE_WORDS);
-    const int32_t* di = p.st.d_drapes_init + (int64_t)env * p.st.drapes_init_bstride;
-    bunkers = load_record<Drape>(di);
-    marauders = load_record<Drape>(di + PCL_DRAPE_WORDS);
-    brow = load_row(p.st.d_bits_init[0] + (int64_t)env * p.st.bits_init_bstride[0]);
-    xrow = load_row(p.st.d_bits_init[1] + (int64_t)env * p.st.bits_init_bstride[1]);
-    action = PCL_ACTION_NONE;
-  } else {
-#pragma unroll
-    for (int i = 0; i < kS; ++i) sp[i] = load_record_rw<Sprite>(g_sprites + i * PCL_SPRITE_WORDS);
-    bunkers = load_record_rw<Drape>(g_drapes);
-    marauders = load_record_rw<Drape>(g_drapes + PCL_DRAPE_WORDS);
-    brow = load_row(g_bunk);
-    xrow = load_row(g_mara);
-    action = p.actions[(int64_t)env * p.actions_per_env];
+  u64 brow, xrow;                  // lane r holds row r of the B / X curtain
+  int action;
+  {
+    const int32_t* ss = restart ? p.st.d_sprites_init + (int64_t)env * p.st.sprites_init_bstride
+                                : g_sprites;
+    const int32_t* sd = restart ? p.st.d_drapes_init + (int64_t)env * p.st.drapes_init_bstride
+                                : g_drapes;
+    const int32_t* sq = restart ? p.st.d_plot_init + (int64_t)env * p.st.plot_init_bstride
+                                : g_plot;
+    const int episodes = g_plot[PCL_P_EPISODES], error = g_plot[PCL_P_ERROR];
+    rec[lane] = ss[lane];
+    if (lane < 24) rec[32 + lane] = ss[32 + lane];
+    if (lane < 16) rec[56 + lane] = sd[lane]; else rec[56 + lane] = sq[lane - 16];
+    brow = load_row(restart ? p.st.d_bits_init[0] + (int64_t)env * p.st.bits_init_bstride[0]
+                            : g_bunk);
+    xrow = load_row(restart ? p.st.d_bits_init[1] + (int64_t)env * p.st.bits_init_bstride[1]
+                            : g_mara);
+    action = restart ? PCL_ACTION_NONE : p.actions[(int64_t)env * p.actions_per_env];
+    __syncwarp();
+    if (restart && lane == 0) { rec[72 + PCL_P_EPISODES] = episodes + 1; rec[72 + PCL_P_ERROR] = error; }
+    __syncwarp();
   }
+  Sprite sp[kS];
+#pragma unroll
+  for (int i = 0; i < kS; ++i) {
+    const int32_t* r = rec + i * PCL_SPRITE_WORDS;
+    sp[i].row = r[PCL_S_ROW]; sp[i].col = r[PCL_S_COL];
+    sp[i].vrow = r[PCL_S_VROW]; sp[i].vcol = r[PCL_S_VCOL];
+    sp[i].flags = r[PCL_S_FLAGS]; sp[i].aux0 = sp[i].aux1 = sp[i].aux2 = 0;
+  }
+  Drape marauders;
+  marauders.aux0 = rec[56 + PCL_DRAPE_WORDS + PCL_D_AUX0];
+  Plot plot;
+  plot.frame = rec[72 + PCL_P_FRAME]; plot.error = rec[72 + PCL_P_ERROR];
+  plot.aux0 = rec[72 + PCL_P_AUX0]; plot.aux1 = rec[72 + PCL_P_AUX1];
+  plot.order_frame = PCL_NEVER; plot.order_r = plot.order_c = 0; plot.ego_mask = 0;
   Directives dir = fresh_directives();
   plot.frame += 1;
 
@@ -242,24 +258,33 @@ marauders_step(const StepParams p) {
   }
 
   // ---- _apply_and_clear_plot + state write-back
-  plot.game_over = dir.game_over;
   if (lane < H) {
     uint32_t* rb = g_bunk + lane * BW;
     uint32_t* rx = g_mara + lane * BW;
     rb[0] = (uint32_t)brow; rb[1] = (uint32_t)(brow >> 32);
     rx[0] = (uint32_t)xrow; rx[1] = (uint32_t)(xrow >> 32);
   }
+  __syncwarp();
   if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < kS; ++i) store_record(g_sprites + i * PCL_SPRITE_WORDS, sp[i]);
-    store_record(g_drapes, bunkers);
-    store_record(g_drapes + PCL_DRAPE_WORDS, marauders);
-    store_record(g_plot, plot);
+    for (int i = 0; i < kS; ++i) {
+      int32_t* r = rec + i * PCL_SPRITE_WORDS;
+      r[PCL_S_ROW] = sp[i].row; r[PCL_S_COL] = sp[i].col;
+      r[PCL_S_VROW] = sp[i].vrow; r[PCL_S_VCOL] = sp[i].vcol; r[PCL_S_FLAGS] = sp[i].flags;
+    }
+    rec[56 + PCL_DRAPE_WORDS + PCL_D_AUX0] = marauders.aux0;
+    rec[72 + PCL_P_FRAME] = plot.frame; rec[72 + PCL_P_GAME_OVER] = dir.game_over;
+    rec[72 + PCL_P_ERROR] = plot.error;
+    rec[72 + PCL_P_AUX0] = plot.aux0; rec[72 + PCL_P_AUX1] = plot.aux1;
     p.out.d_reward[env] = dir.reward;
     p.out.d_has_reward[env] = (uint8_t)dir.has_reward;
     p.out.d_discount[env] = dir.discount;
     p.out.d_done[env] = (uint8_t)dir.game_over;
   }
+  __syncwarp();
+  g_sprites[lane] = rec[lane];
+  if (lane < 24) g_sprites[32 + lane] = rec[32 + lane];
+  if (lane < 16) g_drapes[lane] = rec[56 + lane]; else g_plot[lane - 16] = rec[56 + lane];
 
   // ---- final render, z-order P B X a b c d y z
   const uint8_t* backdrop = p.st.d_backdrop + (int64_t)env * p.st.backdrop_bstride;
@@ -289,8 +314,16 @@ marauders_step(const StepParams p) {
 
 cudaError_t launch_marauders(const StepParams& p, cudaStream_t s) {
   const int blocks = (p.B + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  marauders_step<<<blocks, kWarpsPerBlock * 32, 0, s>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(kWarpsPerBlock * 32);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, marauders_step, p);
 }
 
 }  // namespace pcl
