@@ -142,6 +142,12 @@ typedef struct pcl_state {
   /* per-env z-order (chars, back to front) for programs whose entities issue
    * Plot.change_z_order (engine.py:796-835): u8 [B, n_sprites + n_drapes]; NULL = spec z_order */
   uint8_t* d_z_order;  const uint8_t* d_z_order_init; int64_t z_order_init_bstride;
+  /* Level sharing: envs that play the same level need only one copy of its
+   * static data.  When d_level (i32 [B]) is non-NULL, every array the step never
+   * writes — d_backdrop, read-only patterns, every *_init template — is indexed
+   * by d_level[env] instead of env (the *_bstride is then the per-LEVEL stride);
+   * mutable arrays stay env-indexed.  NULL = env-indexed (or bstride 0). */
+  const int32_t* d_level;
 } pcl_state;
 
 /* Per-step outputs = the (observation, reward, discount) triple of

@@ -91,6 +91,7 @@ class State(C.Structure):
       ('d_rng', C.c_void_p),
       ('d_z_order', C.c_void_p), ('d_z_order_init', C.c_void_p),
       ('z_order_init_bstride', C.c_int64),
+      ('d_level', C.c_void_p),
   ]
 
 

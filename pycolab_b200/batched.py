@@ -71,13 +71,10 @@ class BatchedEngine(object):
     dev = self.device
 
     def tiled(arrays, dtype):
-      """Stack per-game numpy arrays into a device tensor over envs (or one)."""
-      if shared:
-        return torch.from_numpy(np.ascontiguousarray(arrays[0]).astype(dtype))[None].to(dev)
+      """Static data: ONE copy per level ([n_levels, ...]); envs find theirs
+      through the level index (pcl_state.d_level), or share the single copy."""
       stacked = np.stack([np.ascontiguousarray(a).astype(dtype) for a in arrays])
-      t = torch.from_numpy(stacked).to(dev)
-      reps = (B + n - 1) // n
-      return t.repeat((reps,) + (1,) * (t.dim() - 1))[:B].contiguous()
+      return torch.from_numpy(stacked).to(dev)
 
     def per_env(arrays, dtype):
       stacked = np.stack([np.ascontiguousarray(a).astype(dtype) for a in arrays])
@@ -90,6 +87,10 @@ class BatchedEngine(object):
 
     self._keep = []             # every tensor the handle points at
     st = _lib.State()
+    self.level = None           # i32 [B]: which level each env plays
+    if not shared:
+      self.level = (torch.arange(B, dtype=torch.int32, device=dev) % n).contiguous()
+      st.d_level = self.level.data_ptr()
     self.backdrop = tiled([g.backdrop for g in games], np.uint8)
     st.d_backdrop, st.backdrop_bstride = self.backdrop.data_ptr(), bstride(self.backdrop)
     self.patterns, self.bits = {}, {}

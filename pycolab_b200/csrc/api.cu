@@ -374,6 +374,7 @@ int pcl_export_curtain(pcl_handle* h, int drape_index, uint8_t* d_out, void* str
     p.bits = h->st.d_pattern[drape_index];
     p.bits_bstride = h->st.pattern_bstride[drape_index];
     if (drape_index == 1) p.stale_slot = 0;
+    else p.level = h->st.d_level;            // the wall pattern is read-only: per level
   } else if (h->spec.program == PCL_PROG_MARAUDERS ||
              h->spec.program == PCL_PROG_BETTER_SCROLLY ||
              (h->spec.program == PCL_PROG_FIXTURE && !h->spec.drape_kind[drape_index])) {
@@ -384,6 +385,7 @@ int pcl_export_curtain(pcl_handle* h, int drape_index, uint8_t* d_out, void* str
     p.scrolly = 1;
     p.bits = h->st.d_pattern[drape_index];
     p.bits_bstride = h->st.pattern_bstride[drape_index];
+    p.level = h->st.d_level;                 // fixture patterns are read-only: per level
   } else {
     return PCL_ERR_UNSUPPORTED;
   }

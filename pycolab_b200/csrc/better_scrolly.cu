@@ -49,6 +49,7 @@ better_scrolly_step(const StepParams p) {
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * kWarpsPerBlock + warp;
   if (env >= p.B) return;
+  const int64_t lvl = p.st.d_level ? p.st.d_level[env] : env;   // index of static level data
   const int H = p.H, W = p.W, pitch = p.pitch, BW = p.BW;
   const size_t tile = (size_t)H * pitch;
   const size_t bits_bytes = (((size_t)H * BW * 4) + 15) & ~(size_t)15;
@@ -61,7 +62,7 @@ better_scrolly_step(const StepParams p) {
   int32_t* g_drapes = p.st.d_drapes + (int64_t)env * PCL_DRAPE_WORDS;
   int32_t* g_plot = p.st.d_plot + (int64_t)env * PCL_PLOT_WORDS;
   uint32_t* g_coin = p.st.d_bits[0] + (int64_t)env * p.st.bits_bstride[0];
-  const uint8_t* backdrop = p.st.d_backdrop + (int64_t)env * p.st.backdrop_bstride;
+  const uint8_t* backdrop = p.st.d_backdrop + lvl * p.st.backdrop_bstride;
 
   {
     const int n16 = (int)(tile >> 4);
@@ -79,13 +80,13 @@ better_scrolly_step(const StepParams p) {
   const int nbits = H * BW;
   if (restart) {
     const int episodes = g_plot[PCL_P_EPISODES], error = g_plot[PCL_P_ERROR];
-    rec[lane] = __ldg(p.st.d_sprites_init + (int64_t)env * p.st.sprites_init_bstride + lane);
+    rec[lane] = __ldg(p.st.d_sprites_init + lvl * p.st.sprites_init_bstride + lane);
     if (lane < 8) rec[32 + lane] = __ldg(p.st.d_drapes_init +
-                                         (int64_t)env * p.st.drapes_init_bstride + lane);
+                                         lvl * p.st.drapes_init_bstride + lane);
     if (lane >= 16) rec[32 + lane] = __ldg(p.st.d_plot_init +
-                                           (int64_t)env * p.st.plot_init_bstride + lane - 16);
+                                           lvl * p.st.plot_init_bstride + lane - 16);
     // Fresh coins (one Engine per episode): template -> live curtain and smem.
-    const uint32_t* src = p.st.d_bits_init[0] + (int64_t)env * p.st.bits_init_bstride[0];
+    const uint32_t* src = p.st.d_bits_init[0] + lvl * p.st.bits_init_bstride[0];
     for (int i = lane; i < nbits; i += 32) { const uint32_t w = __ldg(src + i); g_coin[i] = w; s_coin[i] = w; }
     __syncwarp();
     if (lane == 0) { rec[48 + PCL_P_EPISODES] = episodes + 1; rec[48 + PCL_P_ERROR] = error; }

@@ -48,12 +48,13 @@ struct Ctx {
   uint8_t* board;                    // smem, H * pitch
   const uint8_t* backdrop;
   int env, lane;
+  int64_t lvl;                       // index of static level data
 };
 
 __device__ __forceinline__ bool drape_bit(const Ctx& c, int d, int r, int col) {
   const StepParams& p = *c.p;
   if (p.drape_kind[d]) {             // Scrolly: window of the pattern (drapes.py:689-695)
-    const uint32_t* pat = p.st.d_pattern[d] + (int64_t)c.env * p.st.pattern_bstride[d];
+    const uint32_t* pat = p.st.d_pattern[d] + c.lvl * p.st.pattern_bstride[d];
     const int pr = c.st->drapes[d][PCL_D_CORNER_R] + r, pc = c.st->drapes[d][PCL_D_CORNER_C] + col;
     return bit_at(pat + (int64_t)pr * p.PWW, pc);
   }
@@ -170,14 +171,15 @@ fixture_step(const StepParams p) {
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * kWarpsPerBlock + warp;
   if (env >= p.B) return;
+  const int64_t lvl = p.st.d_level ? p.st.d_level[env] : env;   // index of static level data
   const int H = p.H, W = p.W, S = p.S, D = p.D, n = S + D;
   const size_t board_bytes = ((size_t)H * p.pitch + 15) & ~(size_t)15;
   uint8_t* my = smem_raw + warp * (sizeof(WarpState) + board_bytes);
   WarpState* st = reinterpret_cast<WarpState*>(my);
   Ctx c;
   c.p = &p; c.st = st; c.board = my + sizeof(WarpState);
-  c.backdrop = p.st.d_backdrop + (int64_t)env * p.st.backdrop_bstride;
-  c.env = env; c.lane = lane;
+  c.backdrop = p.st.d_backdrop + lvl * p.st.backdrop_bstride;
+  c.env = env; c.lane = lane; c.lvl = lvl;
 
   int32_t* g_sprites = p.st.d_sprites + (int64_t)env * S * PCL_SPRITE_WORDS;
   int32_t* g_drapes = p.st.d_drapes + (int64_t)env * D * PCL_DRAPE_WORDS;
@@ -194,13 +196,13 @@ fixture_step(const StepParams p) {
     restart = was_over && p.auto_reset;
     if (was_over && !p.auto_reset) return;
   }
-  const int32_t* src_s = restart ? p.st.d_sprites_init + (int64_t)env * p.st.sprites_init_bstride
+  const int32_t* src_s = restart ? p.st.d_sprites_init + lvl * p.st.sprites_init_bstride
                                  : g_sprites;
-  const int32_t* src_d = restart ? p.st.d_drapes_init + (int64_t)env * p.st.drapes_init_bstride
+  const int32_t* src_d = restart ? p.st.d_drapes_init + lvl * p.st.drapes_init_bstride
                                  : g_drapes;
-  const int32_t* src_p = restart ? p.st.d_plot_init + (int64_t)env * p.st.plot_init_bstride
+  const int32_t* src_p = restart ? p.st.d_plot_init + lvl * p.st.plot_init_bstride
                                  : g_plot;
-  const uint8_t* src_z = restart ? p.st.d_z_order_init + (int64_t)env * p.st.z_order_init_bstride
+  const uint8_t* src_z = restart ? p.st.d_z_order_init + lvl * p.st.z_order_init_bstride
                                  : g_z;
   const int episodes = g_plot[PCL_P_EPISODES], old_error = g_plot[PCL_P_ERROR];
   for (int i = lane; i < S * PCL_SPRITE_WORDS; i += 32) (&st->sprites[0][0])[i] = src_s[i];

@@ -80,6 +80,7 @@ marauders_step(const StepParams p) {
   const int H = p.H, W = p.W;
   int32_t* rec = s_rec[threadIdx.x >> 5];
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int64_t lvl = p.st.d_level ? p.st.d_level[env] : env;   // index of static level data
 
   int32_t* g_sprites = p.st.d_sprites + (int64_t)env * kS * PCL_SPRITE_WORDS;
   int32_t* g_drapes = p.st.d_drapes + (int64_t)env * 2 * PCL_DRAPE_WORDS;
@@ -106,19 +107,19 @@ marauders_step(const StepParams p) {
   u64 brow, xrow;                  // lane r holds row r of the B / X curtain
   int action;
   {
-    const int32_t* ss = restart ? p.st.d_sprites_init + (int64_t)env * p.st.sprites_init_bstride
+    const int32_t* ss = restart ? p.st.d_sprites_init + lvl * p.st.sprites_init_bstride
                                 : g_sprites;
-    const int32_t* sd = restart ? p.st.d_drapes_init + (int64_t)env * p.st.drapes_init_bstride
+    const int32_t* sd = restart ? p.st.d_drapes_init + lvl * p.st.drapes_init_bstride
                                 : g_drapes;
-    const int32_t* sq = restart ? p.st.d_plot_init + (int64_t)env * p.st.plot_init_bstride
+    const int32_t* sq = restart ? p.st.d_plot_init + lvl * p.st.plot_init_bstride
                                 : g_plot;
     const int episodes = g_plot[PCL_P_EPISODES], error = g_plot[PCL_P_ERROR];
     rec[lane] = ss[lane];
     if (lane < 24) rec[32 + lane] = ss[32 + lane];
     if (lane < 16) rec[56 + lane] = sd[lane]; else rec[56 + lane] = sq[lane - 16];
-    brow = load_row(restart ? p.st.d_bits_init[0] + (int64_t)env * p.st.bits_init_bstride[0]
+    brow = load_row(restart ? p.st.d_bits_init[0] + lvl * p.st.bits_init_bstride[0]
                             : g_bunk);
-    xrow = load_row(restart ? p.st.d_bits_init[1] + (int64_t)env * p.st.bits_init_bstride[1]
+    xrow = load_row(restart ? p.st.d_bits_init[1] + lvl * p.st.bits_init_bstride[1]
                             : g_mara);
     action = restart ? PCL_ACTION_NONE : p.actions[(int64_t)env * p.actions_per_env];
     __syncwarp();
@@ -287,7 +288,7 @@ marauders_step(const StepParams p) {
   if (lane < 16) g_drapes[lane] = rec[56 + lane]; else g_plot[lane - 16] = rec[56 + lane];
 
   // ---- final render, z-order P B X a b c d y z
-  const uint8_t* backdrop = p.st.d_backdrop + (int64_t)env * p.st.backdrop_bstride;
+  const uint8_t* backdrop = p.st.d_backdrop + lvl * p.st.backdrop_bstride;
   uint8_t* board = p.out.d_board + (int64_t)env * H * p.pitch;
   const int segs_per_row = p.pitch >> 4;
   const int total = H * segs_per_row;

@@ -54,6 +54,7 @@ cudaError_t launch_render(const RenderParams& p, cudaStream_t s);
 struct ExportParams {
   int B, H, W, pitch, PWW, BW, drape, scrolly;
   const uint32_t* bits; int64_t bits_bstride;   // pattern (scrolly) or board bits
+  const int32_t* level;          // level index when `bits` is per-level static data, else NULL
   const int32_t* drapes; int D;
   int stale_slot;                // drape aux pair holding a stale cell, or -1
   uint8_t* out;

@@ -127,7 +127,9 @@ __global__ void export_curtain_kernel(const ExportParams p) {
   const int stale_r = p.stale_slot >= 0 ? drec[PCL_D_AUX0] : -1;
   const int stale_c = p.stale_slot >= 0 ? drec[PCL_D_AUX1] : -1;
   const int rw = p.scrolly ? p.PWW : p.BW;
-  const uint32_t* bits = p.bits + (int64_t)env * p.bits_bstride;
+  // Read-only patterns are stored once per level (pcl_state.d_level).
+  const int64_t src_index = p.level ? p.level[env] : env;
+  const uint32_t* bits = p.bits + src_index * p.bits_bstride;
   uint8_t* out = p.out + (int64_t)env * p.H * p.pitch;
   for (int seg = threadIdx.x; seg < total; seg += blockDim.x) {
     const int r = seg / segs_per_row;

@@ -125,13 +125,14 @@ scrolly_maze_step(const StepParams p) {
   // Everything above ran without touching global memory; from here on the
   // kernel reads state earlier work in the stream may have produced.
   pdl_wait_prior_grids();
+  const int64_t lvl = p.st.d_level ? p.st.d_level[env] : env;   // index of static level data
 
   int32_t* g_sprites = p.st.d_sprites + (int64_t)env * kS * PCL_SPRITE_WORDS;
   int32_t* g_drapes = p.st.d_drapes + (int64_t)env * 2 * PCL_DRAPE_WORDS;
   int32_t* g_plot = p.st.d_plot + (int64_t)env * PCL_PLOT_WORDS;
-  const uint32_t* wall_pat = p.st.d_pattern[0] + (int64_t)env * p.st.pattern_bstride[0];
+  const uint32_t* wall_pat = p.st.d_pattern[0] + lvl * p.st.pattern_bstride[0];
   uint32_t* coin_pat = p.st.d_pattern[1] + (int64_t)env * p.st.pattern_bstride[1];
-  const uint8_t* backdrop = p.st.d_backdrop + (int64_t)env * p.st.backdrop_bstride;
+  const uint8_t* backdrop = p.st.d_backdrop + lvl * p.st.backdrop_bstride;
 
   // ---- 0. the backdrop tile depends on nothing: get it moving first --------
   {
@@ -158,13 +159,13 @@ scrolly_maze_step(const StepParams p) {
   if (restart) {
     const int episodes = rec[48 + PCL_P_EPISODES], error = rec[48 + PCL_P_ERROR];
     __syncwarp();
-    const int32_t* si = p.st.d_sprites_init + (int64_t)env * p.st.sprites_init_bstride;
-    const int32_t* di = p.st.d_drapes_init + (int64_t)env * p.st.drapes_init_bstride;
-    const int32_t* pi = p.st.d_plot_init + (int64_t)env * p.st.plot_init_bstride;
+    const int32_t* si = p.st.d_sprites_init + lvl * p.st.sprites_init_bstride;
+    const int32_t* di = p.st.d_drapes_init + lvl * p.st.drapes_init_bstride;
+    const int32_t* pi = p.st.d_plot_init + lvl * p.st.plot_init_bstride;
     rec[lane] = __ldg(si + lane);
     rec[32 + lane] = lane < 16 ? __ldg(di + lane) : __ldg(pi + lane - 16);
     // Fresh coins: restore the mutable pattern (one Engine per episode).
-    const uint32_t* src = p.st.d_pattern_init[1] + (int64_t)env * p.st.pattern_init_bstride[1];
+    const uint32_t* src = p.st.d_pattern_init[1] + lvl * p.st.pattern_init_bstride[1];
     const int n = p.PH * PWW;
     for (int i = lane; i < n; i += 32) coin_pat[i] = __ldg(src + i);
     __syncwarp();

@@ -51,6 +51,7 @@ warehouse_step(const StepParams p) {
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * kWarpsPerBlock + warp;
   if (env >= p.B) return;
+  const int64_t lvl = p.st.d_level ? p.st.d_level[env] : env;   // index of static level data
   const int H = p.H, W = p.W, S = p.S, NB = p.S - 1, pitch = p.pitch;
   const size_t tile = (size_t)H * pitch;
   uint8_t* my = smem_raw + warp * (kRecWords * 4 + tile);
@@ -62,7 +63,7 @@ warehouse_step(const StepParams p) {
   int32_t* g_sprites = p.st.d_sprites + (int64_t)env * S * PCL_SPRITE_WORDS;
   int32_t* g_drapes = p.st.d_drapes + (int64_t)env * PCL_DRAPE_WORDS;
   int32_t* g_plot = p.st.d_plot + (int64_t)env * PCL_PLOT_WORDS;
-  const uint8_t* backdrop = p.st.d_backdrop + (int64_t)env * p.st.backdrop_bstride;
+  const uint8_t* backdrop = p.st.d_backdrop + lvl * p.st.backdrop_bstride;
 
   // ---- the backdrop tile does not depend on anything: start it first
   {
@@ -80,11 +81,11 @@ warehouse_step(const StepParams p) {
     if (was_over && !p.auto_reset) { cp_async_wait_all(); return; }
   }
   {
-    const int32_t* ss = restart ? p.st.d_sprites_init + (int64_t)env * p.st.sprites_init_bstride
+    const int32_t* ss = restart ? p.st.d_sprites_init + lvl * p.st.sprites_init_bstride
                                 : g_sprites;
-    const int32_t* sd = restart ? p.st.d_drapes_init + (int64_t)env * p.st.drapes_init_bstride
+    const int32_t* sd = restart ? p.st.d_drapes_init + lvl * p.st.drapes_init_bstride
                                 : g_drapes;
-    const int32_t* sp = restart ? p.st.d_plot_init + (int64_t)env * p.st.plot_init_bstride
+    const int32_t* sp = restart ? p.st.d_plot_init + lvl * p.st.plot_init_bstride
                                 : g_plot;
     const int episodes = g_plot[PCL_P_EPISODES], error = g_plot[PCL_P_ERROR];
     for (int i = lane; i < S * PCL_SPRITE_WORDS; i += 32) rec[i] = ss[i];
