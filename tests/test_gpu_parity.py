@@ -492,3 +492,31 @@ def test_facade_things_and_layers_follow_the_device():
   for ch in obs.layers:
     np.testing.assert_array_equal(obs.layers[ch], out[0] == ord(ch))
   assert game.the_plot.frame == world.plot.frame
+
+
+def test_run_equals_repeated_play_and_host_without_board():
+  """pcl_run (T steps, one C call) == T x pcl_step; play_host(want_board=False)."""
+  from pycolab_b200 import batched, levels
+  from pycolab_b200.games import warehouse_manager
+  torch = _torch()
+  art = levels.warehouse_level(9, shape=(20, 26), num_boxes=5, num_goals=6)
+  a = batched.BatchedEngine([warehouse_manager.make_game(art)], batch=48)
+  b = batched.BatchedEngine([warehouse_manager.make_game(art)], batch=48)
+  c = batched.BatchedEngine([warehouse_manager.make_game(art)], batch=48)
+  for e in (a, b, c):
+    e.its_showtime()
+  rs = np.random.RandomState(4)
+  acts = rs.randint(0, 5, size=(25, 48)).astype(np.int32)
+  t_acts = torch.from_numpy(acts).cuda()
+  n0 = b.launch_count()
+  rb = b.run(t_acts)
+  assert b.launch_count() - n0 == 25
+  for t in range(25):
+    ra = a.play(t_acts[t])
+    _, reward, has, disc, done = c.play_host(acts[t], want_board=False)
+  torch.cuda.synchronize()
+  assert bool((ra.board == rb.board).all()) and bool((ra.reward == rb.reward).all())
+  assert bool((a.sprites == b.sprites).all()) and bool((a.plot == b.plot).all())
+  np.testing.assert_array_equal(ra.reward.cpu().numpy(), reward)
+  np.testing.assert_array_equal(ra.done.cpu().numpy(), done)
+  assert bool((c.board == a.board).all())
