@@ -301,6 +301,59 @@ __device__ __forceinline__ unsigned sprite_bit(const Sprite& s, int r, int c0) {
   return (visible(s) && s.row == r && (unsigned)dc < 16u) ? (1u << dc) : 0u;
 }
 
+// ------------------------------------------------- TMA (1-D bulk) tile moves --
+// A board tile is a contiguous, 16-byte aligned run of H * pitch bytes, so it
+// moves between HBM and shared memory as ONE bulk-copy instruction issued by
+// one lane (SASS UBLKCP), completion tracked by an mbarrier (loads) or a bulk
+// group (stores), instead of H * pitch / 512 vector load/store rounds per warp.
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(arrivals));
+  // Make the initialised barrier visible to the async proxy (the bulk copy
+  // engine).  A CTA-scope proxy fence is enough for a barrier only this CTA
+  // uses; the cluster-scope mbarrier_init fence would also flush L1 (CCTL.IVALL).
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// Global -> shared; `bytes` a multiple of 16.  Call from ONE thread.
+__device__ __forceinline__ void tile_load_bulk(void* smem_dst, const void* gmem_src,
+                                               uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+               :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+               "[%0], [%1], %2, [%3];"
+               :: "r"(smem_addr(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" :: "r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// Shared -> global; make the generic-proxy writes to the tile visible to the
+// async proxy first.  Call tile_store_bulk from ONE thread after a warp/block
+// barrier; that thread must tile_store_wait() before the CTA can retire.
+__device__ __forceinline__ void tile_store_fence() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tile_store_bulk(void* gmem_dst, const void* smem_src,
+                                                uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               :: "l"(gmem_dst), "r"(smem_addr(smem_src)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tile_store_wait() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // ------------------------------------------------------------- env scoping --
 
 enum { MODE_STEP = 0, MODE_RESET = 1 };

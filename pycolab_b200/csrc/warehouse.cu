@@ -65,20 +65,21 @@ warehouse_step(const StepParams p) {
   int32_t* g_plot = p.st.d_plot + (int64_t)env * PCL_PLOT_WORDS;
   const uint8_t* backdrop = p.st.d_backdrop + lvl * p.st.backdrop_bstride;
 
-  // ---- the backdrop tile does not depend on anything: start it first
-  {
-    const int n16 = (int)(tile >> 4);
-    for (int i = lane; i < n16; i += 32) cp_async16(s_bd + i * 16, backdrop + i * 16);
-  }
+  // ---- the backdrop tile does not depend on anything: start it first, as one
+  // TMA bulk copy tracked by this warp's mbarrier (rec words 104..105 are padding).
+  uint64_t* bar = reinterpret_cast<uint64_t*>(rec + 104);
+  if (lane == 0) mbar_init(bar, 1);
+  __syncwarp();
+  if (lane == 0) tile_load_bulk(s_bd, backdrop, (uint32_t)tile, bar);
   // ---- records -> smem
   const int was_over = g_plot[PCL_P_GAME_OVER];
   bool restart;
   if (p.mode == MODE_RESET) {
     restart = (p.env_mask == nullptr) || (p.env_mask[env] != 0);
-    if (!restart) { cp_async_wait_all(); return; }
+    if (!restart) { mbar_wait(bar, 0); return; }
   } else {
     restart = was_over && p.auto_reset;
-    if (was_over && !p.auto_reset) { cp_async_wait_all(); return; }
+    if (was_over && !p.auto_reset) { mbar_wait(bar, 0); return; }
   }
   {
     const int32_t* ss = restart ? p.st.d_sprites_init + lvl * p.st.sprites_init_bstride
@@ -95,7 +96,7 @@ warehouse_step(const StepParams p) {
     if (restart && lane == 0) { r_plot[PCL_P_EPISODES] = episodes + 1; r_plot[PCL_P_ERROR] = error; }
   }
   const int action = restart ? PCL_ACTION_NONE : p.actions[(int64_t)env * p.actions_per_env];
-  cp_async_wait_all();
+  mbar_wait(bar, 0);
   __syncwarp();
 
   Plot plot;
@@ -243,9 +244,12 @@ warehouse_step(const StepParams p) {
   if (lane == 0 && visible(player)) s_bd[player.row * pitch + player.col] = (uint8_t)P_CHAR;
   __syncwarp();
   uint8_t* board = p.out.d_board + (int64_t)env * tile;
-  const int n16 = (int)(tile >> 4);
-  for (int i = lane; i < n16; i += 32)
-    reinterpret_cast<uint4*>(board)[i] = reinterpret_cast<const uint4*>(s_bd)[i];
+  tile_store_fence();
+  __syncwarp();
+  if (lane == 0) {
+    tile_store_bulk(board, s_bd, (uint32_t)tile);
+    tile_store_wait();                       // the tile must outlive the copy's reads
+  }
 }
 
 }  // namespace
