@@ -66,8 +66,16 @@ typedef enum pcl_program {
   PCL_PROG_WAREHOUSE = 2,    /* examples/warehouse_manager.py:139-295          */
   PCL_PROG_MARAUDERS = 3,    /* examples/extraterrestrial_marauders.py:91-256  */
   PCL_PROG_FIXTURE = 4,      /* tests/test_things.py TestMazeWalker/TestScrolly */
-  PCL_PROG_BETTER_SCROLLY = 5 /* examples/better_scrolly_maze.py:209-324        */
+  PCL_PROG_BETTER_SCROLLY = 5, /* examples/better_scrolly_maze.py:209-324       */
+  PCL_PROG_CLASSICS = 6      /* examples/classics/{four_rooms,cliff_walk,chain_walk}.py */
 } pcl_program;
+
+/* PCL_PROG_CLASSICS: pcl_spec.program_arg[0] selects the rule set; the games
+ * pay float rewards (1.0, -1.0, -100.0, 100.0) which d_reward carries as the
+ * equal int32 value. */
+enum { PCL_CLASSIC_FOUR_ROOMS = 0, /* four_rooms.py:52-80; program_arg[1..2] = goal cell (4, 3) */
+       PCL_CLASSIC_CLIFF_WALK = 1, /* cliff_walk.py:46-86 */
+       PCL_CLASSIC_CHAIN_WALK = 2  /* chain_walk.py:44-73 */ };
 
 /* Motion codes (prefab_parts/sprites.py:140-150). */
 enum { PCL_M_N = 0, PCL_M_NE, PCL_M_E, PCL_M_SE, PCL_M_S, PCL_M_SW, PCL_M_W,
@@ -118,7 +126,7 @@ typedef struct pcl_spec {
   int32_t group_len[PCL_MAX_SPRITES + PCL_MAX_DRAPES];
   uint8_t group_chars[PCL_MAX_SPRITES + PCL_MAX_DRAPES]; /* update order, concatenated */
   int32_t drape_kind[PCL_MAX_DRAPES];      /* 0 = plain bool curtain (d_bits), 1 = Scrolly (d_pattern) */
-  int32_t reserved[8];
+  int32_t program_arg[8];                  /* per-program constants (see pcl_program); else 0 */
 } pcl_spec;
 
 /* Device buffers of one handle (all caller-owned).  A "*_bstride" is the

@@ -9,6 +9,9 @@ paints `char`.  Reference (under /root/reference/pycolab/):
   examples/warehouse_manager.py:139-295       -> make_warehouse / warehouse_program
   examples/extraterrestrial_marauders.py:91-256 -> make_marauders / marauders_program
   tests/test_things.py:153-295 (fixtures)     -> make_fixture_world / fixture_program
+  examples/better_scrolly_maze.py:209-324     -> make_better_scrolly / better_scrolly_program
+  examples/classics/four_rooms.py:45-85, cliff_walk.py:39-86,
+  chain_walk.py:37-73                         -> make_classic / classics_program
   ascii_art.py:31-292                         -> split_art
 """
 
@@ -349,6 +352,62 @@ def better_scrolly_program(world, ch, actions):
         plot.terminate_episode()
   else:
     raise KeyError(ch)
+
+
+# ==========================================================================
+# classics: four_rooms, cliff_walk, chain_walk.  One
+# MazeWalker 'P', no drapes, one update group; rewards are Python floats.
+# ==========================================================================
+
+CLASSIC_KINDS = ('four_rooms', 'cliff_walk', 'chain_walk')
+
+
+def make_classic(kind, art):
+  """four_rooms.py:45-49, cliff_walk.py:39-43, chain_walk.py:37-41."""
+  assert kind in CLASSIC_KINDS
+  beneath = ' ' if kind == 'four_rooms' else '.'
+  backdrop, masks = split_art(art, ['P'], beneath)
+  shape = backdrop.shape
+  walker = em.Walker('P', shape, mask_position(masks['P']),
+                     impassable='#' if kind == 'four_rooms' else '',      # four_rooms.py:60-63
+                     confined=(kind == 'cliff_walk'))                     # cliff_walk.py:54-57
+  world = em.World(shape[0], shape[1], backdrop, {'P': walker}, z_order='P',
+                   groups=[['P']], program=classics_program)
+  world.classic_kind = kind
+  return world
+
+
+def classics_program(world, ch, actions):
+  plot, ent, board = world.plot, world.things[ch], world.board
+  kind = world.classic_kind
+  if kind == 'chain_walk':                        # chain_walk.py:60-73
+    motion = {0: em.M_W, 1: em.M_E}.get(actions) if actions is not None else None
+  else:                                           # four_rooms.py:68-76, cliff_walk.py:62-71
+    motion = {0: em.M_N, 1: em.M_S, 2: em.M_W, 3: em.M_E}.get(actions) \
+        if actions is not None else None
+  if motion is not None:
+    em.walker_move(ent, board, plot, motion)
+  if kind == 'four_rooms':                        # :78-80
+    if ent.position == (4, 3):
+      plot.add_reward(1.0)
+      plot.terminate_episode()
+  elif kind == 'cliff_walk':                      # :72-86
+    if motion is None:
+      return
+    row, col = ent.position
+    if row == ent.rows - 1 and 0 < col < ent.cols - 2:
+      plot.add_reward(-100.0)
+    else:
+      plot.add_reward(-1.0)
+    if row == ent.rows - 1 and 0 < col:
+      plot.terminate_episode()
+  else:                                           # chain_walk.py:66-73
+    if ent.col == 0:
+      plot.add_reward(1.0)
+      plot.terminate_episode()
+    elif ent.col == ent.cols - 1:
+      plot.add_reward(100.0)
+      plot.terminate_episode()
 
 
 # ==========================================================================

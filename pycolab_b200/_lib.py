@@ -29,7 +29,8 @@ ENV_ERR_INDEX = 0x8
 ENV_ERR_BAD_Z = 0x10
 
 PROG_NONE, PROG_SCROLLY_MAZE, PROG_WAREHOUSE, PROG_MARAUDERS, PROG_FIXTURE = 0, 1, 2, 3, 4
-PROG_BETTER_SCROLLY = 5
+PROG_BETTER_SCROLLY, PROG_CLASSICS = 5, 6
+CLASSIC_FOUR_ROOMS, CLASSIC_CLIFF_WALK, CLASSIC_CHAIN_WALK = 0, 1, 2
 
 # Record word indices (pcl.h enums).
 S_ROW, S_COL, S_VROW, S_VCOL, S_FLAGS, S_AUX0, S_AUX1, S_AUX2 = range(8)
@@ -71,7 +72,7 @@ class Spec(C.Structure):
       ('group_len', C.c_int32 * _N),
       ('group_chars', C.c_uint8 * _N),
       ('drape_kind', C.c_int32 * MAX_DRAPES),
-      ('reserved', C.c_int32 * 8),
+      ('program_arg', C.c_int32 * 8),
   ]
 
 

@@ -129,6 +129,18 @@ int validate(const pcl_spec& s) {
       if (s.bits_words < (s.cols + 31) / 32 + 1) return PCL_ERR_INVALID;
       return PCL_OK;
     }
+    case PCL_PROG_CLASSICS: {
+      if (!chars_are(s.sprite_char, s.n_sprites, "P") || s.n_drapes != 0) return PCL_ERR_UNSUPPORTED;
+      if (!chars_are(s.z_order, 1, "P")) return PCL_ERR_UNSUPPORTED;
+      const int lens[1] = {1};
+      if (!groups_are(s, "P", lens, 1)) return PCL_ERR_UNSUPPORTED;
+      if (s.sprite_egocentric[0]) return PCL_ERR_UNSUPPORTED;
+      const int rule = s.program_arg[0];
+      if (rule != PCL_CLASSIC_FOUR_ROOMS && rule != PCL_CLASSIC_CLIFF_WALK &&
+          rule != PCL_CLASSIC_CHAIN_WALK) return PCL_ERR_INVALID;
+      if (s.rows * s.pitch > 8192) return PCL_ERR_UNSUPPORTED;   // the tile is staged per env in smem
+      return PCL_OK;
+    }
     case PCL_PROG_FIXTURE: {
       // Any MazeWalker / Scrolly / plain-drape mix; entities and z-order must
       // be consistent permutations of each other.
@@ -177,6 +189,7 @@ void fill_params(const pcl_handle* h, StepParams* p) {
   memcpy(p->confined, s.sprite_confined, sizeof(p->confined));
   memcpy(p->egocentric, s.sprite_egocentric, sizeof(p->egocentric));
   memcpy(p->drape_kind, s.drape_kind, sizeof(p->drape_kind));
+  memcpy(p->program_arg, s.program_arg, sizeof(p->program_arg));
   p->n_groups = s.n_groups;
   memcpy(p->group_len, s.group_len, sizeof(p->group_len));
   memcpy(p->group_chars, s.group_chars, sizeof(p->group_chars));
@@ -191,6 +204,7 @@ int launch(pcl_handle* h, const StepParams& p, cudaStream_t stream) {
     case PCL_PROG_MARAUDERS: e = pcl::launch_marauders(p, stream); break;
     case PCL_PROG_FIXTURE: e = pcl::launch_fixture(p, stream); break;
     case PCL_PROG_BETTER_SCROLLY: e = pcl::launch_better_scrolly(p, stream); break;
+    case PCL_PROG_CLASSICS: e = pcl::launch_classics(p, stream); break;
     default: return PCL_ERR_UNSUPPORTED;
   }
   h->launches += 1;

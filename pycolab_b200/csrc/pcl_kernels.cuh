@@ -24,6 +24,7 @@ struct StepParams {
   int confined[PCL_MAX_SPRITES];
   int egocentric[PCL_MAX_SPRITES];
   int drape_kind[PCL_MAX_DRAPES];
+  int program_arg[8];
   int n_groups;
   int group_len[PCL_MAX_SPRITES + PCL_MAX_DRAPES];
   uint8_t group_chars[PCL_MAX_SPRITES + PCL_MAX_DRAPES];
@@ -38,6 +39,7 @@ cudaError_t launch_warehouse(const StepParams& p, cudaStream_t s);
 cudaError_t launch_marauders(const StepParams& p, cudaStream_t s);
 cudaError_t launch_fixture(const StepParams& p, cudaStream_t s);
 cudaError_t launch_better_scrolly(const StepParams& p, cudaStream_t s);
+cudaError_t launch_classics(const StepParams& p, cudaStream_t s);
 
 struct RenderParams {
   int B, H, W, pitch, S, D;

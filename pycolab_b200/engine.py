@@ -167,7 +167,10 @@ class Engine(object):
     import torch
     torch.cuda.synchronize(self._batched.device)
     board = result.board[0].cpu().numpy().copy()
-    reward = int(result.reward[0]) if int(result.has_reward[0]) else None
+    # d_reward is int32; games whose reference rewards are Python floats
+    # (examples/classics) get the equal float back.
+    reward = (self._batched.game.reward_type(int(result.reward[0]))
+              if int(result.has_reward[0]) else None)
     discount = float(result.discount[0])
     self._game_over = bool(int(result.done[0]))
     self._sync_things()

@@ -142,3 +142,28 @@ def marauders_level(rows=16, cols=39):
     art[11:14, 4 + 9 * b: 8 + 9 * b] = ord('B')
   art[rows - 1, 2] = ord('P')
   return _to_art(art)
+
+
+def classic_level(kind):
+  """A second, larger level for each `examples/classics` game (the stock art is
+  the only one the reference ships; the rules read only the board shape and,
+  for four_rooms, the fixed goal cell (4, 3) — four_rooms.py:78)."""
+  if kind == 'four_rooms':
+    rows, cols = 15, 21
+    a = np.full((rows, cols), ord(' '), dtype=np.uint8)
+    a[0, :] = a[-1, :] = a[:, 0] = a[:, -1] = ord('#')
+    a[:, 10] = ord('#')
+    a[7, :] = ord('#')
+    for r, c in ((3, 10), (11, 10), (7, 4), (7, 15)):   # doors
+      a[r, c] = ord(' ')
+    a[2, 7] = ord('P')
+    return _to_art(a)
+  if kind == 'cliff_walk':
+    a = np.full((6, 20), ord('.'), dtype=np.uint8)
+    a[5, 0] = ord('P')
+    return _to_art(a)
+  if kind == 'chain_walk':
+    a = np.full((1, 40), ord('.'), dtype=np.uint8)
+    a[0, 17] = ord('P')
+    return _to_art(a)
+  raise ValueError(kind)

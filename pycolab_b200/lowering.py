@@ -44,6 +44,9 @@ LOWERED_CLASSES = {
     ('better_scrolly_maze', 'PlayerSprite'): 'better.player',
     ('better_scrolly_maze', 'PatrollerSprite'): 'better.patroller',
     ('better_scrolly_maze', 'CashDrape'): 'better.cash',
+    ('four_rooms', 'PlayerSprite'): 'classics.four_rooms',
+    ('cliff_walk', 'PlayerSprite'): 'classics.cliff_walk',
+    ('chain_walk', 'PlayerSprite'): 'classics.chain_walk',
     # General entities: the reference's test fixtures and this package's twins.
     ('test_things', 'TestMazeWalker'): 'fixture.walker',
     ('test_things', 'TestScrolly'): 'fixture.scrolly',
@@ -134,13 +137,16 @@ class LoweredGame(object):
     self.backdrop_chars = ''
     self.drape_kind = None      # per drape: 1 = Scrolly (fixture program only)
     self.dynamic_z = False      # per-env z-order array (Plot.change_z_order)
+    self.program_arg = [0] * 8  # pcl_spec.program_arg
+    self.reward_type = int      # the reference's reward type (classics pay floats)
 
   def signature(self):
     """Everything that must agree between envs sharing one handle."""
     return (self.program, self.rows, self.cols, self.sprite_chars, self.drape_chars,
             tuple(map(tuple, self.impassable)), tuple(self.confined),
             tuple(self.egocentric), tuple(map(tuple, self.margins)), self.z_order,
-            tuple(self.groups), self.pattern_rows, self.pattern_cols)
+            tuple(self.groups), self.pattern_rows, self.pattern_cols,
+            tuple(self.program_arg))
 
   def make_spec(self, auto_reset):
     s = _lib.Spec()
@@ -164,6 +170,8 @@ class LoweredGame(object):
         s.drape_kind[i] = self.drape_kind[i]
     for i, ch in enumerate(self.z_order):
       s.z_order[i] = ord(ch)
+    for i, v in enumerate(self.program_arg):
+      s.program_arg[i] = int(v)
     s.n_groups = len(self.groups)
     k = 0
     for g, group in enumerate(self.groups):
@@ -359,6 +367,29 @@ def _lower_better_scrolly(engine, roles):
   return game
 
 
+def _lower_classics(engine, roles):
+  """examples/classics: one MazeWalker 'P', no drapes; the rule set rides in
+  pcl_spec.program_arg (four_rooms.py:78 fixes the goal cell at (4, 3))."""
+  if list(roles) != ['P']:
+    raise NotLoweredError('classics programs have exactly one entity, P (got {})'.format(roles))
+  game = LoweredGame()
+  _common(engine, game, _lib.PROG_CLASSICS)
+  rule = roles['P'].split('.')[1]
+  game.program_arg[0] = {'four_rooms': _lib.CLASSIC_FOUR_ROOMS,
+                         'cliff_walk': _lib.CLASSIC_CLIFF_WALK,
+                         'chain_walk': _lib.CLASSIC_CHAIN_WALK}[rule]
+  if rule == 'four_rooms':
+    game.program_arg[1], game.program_arg[2] = 4, 3
+  if game.rows * game.pitch > 8192:
+    raise NotLoweredError('classics boards are staged whole in shared memory (<= 8 KiB)')
+  player = engine.things['P']
+  _set_sprites(game, [player], [_sprite_record(player)])
+  game.drapes = np.zeros((0, _lib.DRAPE_WORDS), dtype=np.int32)
+  game.plot = np.array(_plot_record(), dtype=np.int32)
+  game.reward_type = float
+  return game
+
+
 def _lower_fixture(engine, roles):
   th = engine.things
   game = LoweredGame()
@@ -420,6 +451,8 @@ def lower(engine):
     return _lower_marauders(engine, roles)
   if family == 'fixture':
     return _lower_fixture(engine, roles)
+  if family == 'classics':
+    return _lower_classics(engine, roles)
   if family == 'better':
     return _lower_better_scrolly(engine, roles)
   raise NotLoweredError(family)

@@ -344,8 +344,27 @@ def cropper(name, pad, margins, offset, saccade, T=300):
        corners=np.array(corners, dtype=np.int32), **traj)
 
 
+def classic(name, kind, art, actions):
+  """examples/classics game; rewards are Python floats there, so the fixture
+  also records the reward's type."""
+  sprites, kinds = [], []
+
+  def on_frame(env, out):
+    sprite_recorder('P', sprites)(env, out)
+    kinds.append(0 if out[1] is None else (2 if isinstance(out[1], float) else 1))
+  stock = refdriver.ref_classic_art(kind)
+  traj = tj.run_trajectory(lambda: refdriver.ref_classic(kind, art), actions, on_frame=on_frame)
+  save(name, art=tj.art_to_u8(art or stock),
+       kind=np.frombuffer(kind.encode(), dtype=np.uint8),
+       actions=np.array(actions, dtype=np.int32),
+       sprites=np.array(sprites, dtype=np.int32),
+       reward_type=np.array(kinds, dtype=np.uint8), **traj)
+
+
 def main():
   assert refdriver.available(), '/root/reference is required'
+  if sys.argv[1:] == ['classics']:      # add these without rewriting the older files
+    return classics()
   # BASELINE.json configs[0]: stock scrolly_maze, 1000 random-action steps.
   for level, T in ((0, 1000), (1, 400), (2, 400)):
     maze, board, beneath = refdriver.ref_stock_scrolly_art(level)
@@ -390,6 +409,15 @@ def main():
   cropper('crop_ego_pad', ' ', (None, None), None, True)
   cropper('crop_margins_nopad', None, (2, 3), None, True)
   cropper('crop_margins_pad_offset', ' ', (2, 3), (1, -2), False)
+  classics()
+
+
+def classics():
+  for kind in ('four_rooms', 'cliff_walk', 'chain_walk'):
+    n_actions = 3 if kind == 'chain_walk' else 6
+    for which, art in (('stock', None), ('other', levels.classic_level(kind))):
+      actions = np.random.RandomState(len(kind) + len(which)).randint(0, n_actions, size=1200)
+      classic('classic_%s_%s' % (kind, which), kind, art, actions.tolist())
 
 
 if __name__ == '__main__':

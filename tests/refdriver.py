@@ -80,6 +80,28 @@ def ref_better_scrolly_croppers(level):
   return m.make_croppers(level)
 
 
+def ref_classic(kind, art=None):
+  """examples/classics/{four_rooms,cliff_walk,chain_walk}.make_game, optionally
+  on other art."""
+  _import()
+  import importlib
+  m = importlib.import_module('pycolab.examples.classics.' + kind)
+  if art is None:
+    return m.make_game()
+  saved = m.GAME_ART
+  try:
+    m.GAME_ART = art
+    return m.make_game()
+  finally:
+    m.GAME_ART = saved
+
+
+def ref_classic_art(kind):
+  _import()
+  import importlib
+  return list(importlib.import_module('pycolab.examples.classics.' + kind).GAME_ART)
+
+
 def ref_warehouse(art, beneath=' ', level=None):
   m = _import()['warehouse_manager']
   if level is not None:

@@ -341,6 +341,25 @@ def test_reference_better_scrolly_example_loads_and_lowers(compat_examples):
 
 
 @needs_ref
+@pytest.mark.parametrize('kind', ['four_rooms', 'cliff_walk', 'chain_walk'])
+def test_reference_classics_examples_load_and_lower(compat_examples, kind):
+  import importlib
+  from oracle import games as ogames
+  mod = compat_examples(os.path.join('classics', kind))
+  ours_mod = importlib.import_module('pycolab_b200.games.classics.' + kind)
+  assert list(mod.GAME_ART) == list(ours_mod.GAME_ART)
+  theirs, ours = lowering.lower(mod.make_game()), lowering.lower(ours_mod.make_game())
+  assert theirs.program == _lib.PROG_CLASSICS and theirs.reward_type is float
+  _same_lowering(theirs, ours)
+  # ... and the lowered initial state is the oracle's
+  world = ogames.make_classic(kind, list(mod.GAME_ART))
+  w = world.things['P']
+  assert tuple(theirs.sprites[0, :5]) == (w.row, w.col, w.vrow, w.vcol, 1)
+  np.testing.assert_array_equal(theirs.backdrop[:, :theirs.cols], world.backdrop)
+  assert bool(theirs.confined[0]) == w.confined
+
+
+@needs_ref
 def test_reference_test_fixtures_load_and_lower(compat_examples):
   """The reference's own tests/test_things.py fixtures lower to the general
   device program, identically to this package's games/fixtures.py."""

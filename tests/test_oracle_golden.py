@@ -183,3 +183,25 @@ def test_cropper(name):
   tj.assert_same_trajectory(g, got, name)
   np.testing.assert_array_equal(g['crops'], np.stack(crops))
   np.testing.assert_array_equal(g['corners'], np.array(corners))
+
+
+def reward_types(sink):
+  def on_frame(env, out):
+    sink.append(0 if out[1] is None else (2 if isinstance(out[1], float) else 1))
+  return on_frame
+
+
+@pytest.mark.parametrize('name', gc.names('classic_'))
+def test_classics(name):
+  g = gc.load(name)
+  kind, art = bytes(g['kind']).decode(), tj.u8_to_art(g['art'])
+  sprites, types = [], []
+
+  def on_frame(env, out):
+    _sprite_sink('P', sprites)(env, out)
+    reward_types(types)(env, out)
+  got = tj.run_trajectory(lambda: games.make_classic(kind, art), g['actions'].tolist(),
+                          on_frame=on_frame)
+  tj.assert_same_trajectory(g, got, name)
+  np.testing.assert_array_equal(g['sprites'], np.array(sprites))
+  np.testing.assert_array_equal(g['reward_type'], np.array(types, dtype=np.uint8))

@@ -207,6 +207,34 @@ def test_fixture_scrolly_random(seed, margins):
                                   ora.things['#'].curtain)
 
 
+@pytest.mark.parametrize('kind', games.CLASSIC_KINDS)
+@pytest.mark.parametrize('art', ['stock', 'other'])
+def test_classics(kind, art):
+  from pycolab_b200 import levels
+  art = None if art == 'stock' else levels.classic_level(kind)
+  stock = refdriver.ref_classic_art(kind)
+  n_actions = 3 if kind == 'chain_walk' else 6     # includes no-op / unmapped actions
+  actions = np.random.RandomState(len(kind)).randint(0, n_actions, size=2500).tolist()
+  rewards = []
+
+  def make_ref():
+    return refdriver.ref_classic(kind, art)
+  ref, ora = make_ref(), games.make_classic(kind, art or stock)
+  r_out, o_out = ref.its_showtime(), ora.its_showtime()
+  episodes = 0
+  for t, a in enumerate(actions):
+    _compare(ref, ora, r_out, o_out, t, True)
+    assert type(r_out[1]) is type(o_out[1]), (t, r_out[1], o_out[1])   # float rewards
+    rewards.append(r_out[1])
+    if ref.game_over:
+      episodes += 1
+      ref, ora = make_ref(), games.make_classic(kind, art or stock)
+      r_out, o_out = ref.its_showtime(), ora.its_showtime()
+      continue
+    r_out, o_out = ref.play(a), ora.play(a)
+  assert episodes >= 1 and any(r is not None for r in rewards)
+
+
 @pytest.mark.parametrize('pad,margins', [(' ', (None, None)), (None, (2, 3)),
                                          (' ', (2, 3))])
 def test_scrolling_cropper(pad, margins):
