@@ -50,10 +50,6 @@ __device__ __forceinline__ int action_to_motion(int a) {   // scrolly_maze.py:26
        : a == 3 ? PCL_M_E : a == 4 ? PCL_M_STAY : PCL_M_NONE;
 }
 
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::
-               "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
-}
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::
                "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
@@ -71,16 +67,17 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
 // from the even word at or below corner_c >> 5 always cover it (<= 31 + 32 + 64
 // bits), and pattern rows are 8-byte aligned (pattern_words is even), so a row is
 // staged with two 8-byte cp.async into a 16-byte smem slot.
-// 16 window bits starting at bit `off` (< 112) of such a 4-word staged row.
-__device__ __forceinline__ unsigned window16(const uint32_t* row4, int off) {
-  const int w = off >> 5, sh = off & 31;
-  const uint32_t lo = row4[w];
-  const uint32_t hi = row4[w < 3 ? w + 1 : 3];
-  return __funnelshift_r(lo, hi, sh) & 0xffffu;
+
+// prmt.b32 without __byte_perm's selector masking (the table holds nibbles 0..5).
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
 }
 
-__device__ __forceinline__ size_t warp_smem_bytes(int H, int pitch) {
-  return kRecWords * 4 + (size_t)H * pitch + 2 * ((size_t)H * 16);
+__host__ __device__ __forceinline__ size_t warp_smem_bytes(int H, int pitch) {
+  // records, backdrop tile, two 4-word window rows per board row, one word per segment
+  return kRecWords * 4 + (size_t)H * pitch + 2 * ((size_t)H * 16) + (size_t)H * (pitch >> 2);
 }
 
 // Programmatic dependent launch: let the next kernel of the stream begin its
@@ -394,57 +391,70 @@ scrolly_maze_step(const StepParams p) {
   else g_plot[lane - 16] = rec[32 + lane];
 
   // ---- 5. final render, z-order a b c @ # P (engine.py:737-759) ----------
-  // The loop body is the bandwidth-critical code: no divisions, no 64-bit
-  // address math, no per-sprite tests.  a, b, c lie under both drapes, so they
-  // are patched into the staged backdrop up front (in z-order, by one lane); the
-  // player is the top layer and is patched into the one segment that holds it.
-  uint8_t* board = p.out.d_board + (int64_t)env * H * p.pitch;
+  // 5a. Window rows -> ONE word per 16-cell board segment (wall16 << 16 | coin16),
+  // aligned to the board: each lane shifts whole rows once, so the streaming loop
+  // below does no bit addressing at all.  Cells past W and the stale coin
+  // (drapes.py:689 has not refreshed the curtain yet) are folded in here.
   const int pitch = p.pitch;
   const int spr = pitch >> 4;                // 16-byte segments per row
-  const int total = H * spr;
-  const int wsh = wc - (we << 5), csh = cc - (ce_final << 5);   // bit offsets in staged rows
-  const int stale_seg = coins.aux0 >= 0 ? coins.aux0 * spr + (coins.aux1 >> 4) : -1;
-  const unsigned stale_bit = 1u << (coins.aux1 & 15);
-  const int p_seg = visible(sp[0]) ? sp[0].row * spr + (sp[0].col >> 4) : -1;
-  const int p_word = (sp[0].col & 15) >> 2;
-  const uint32_t p_keep = ~(0xffu << ((sp[0].col & 3) * 8));
-  const uint32_t p_char = (uint32_t)p.sprite_char[0] << ((sp[0].col & 3) * 8);
+  uint32_t* s_seg = s_coin + H * 4;
+  {
+    const int wsh = wc - (we << 5), csh = cc - (ce_final << 5);   // 0..63 into the staged row
+    const uint32_t m_lo = W >= 32 ? 0xffffffffu : (1u << W) - 1u;
+    const uint32_t m_hi = W >= 64 ? 0xffffffffu : W > 32 ? (1u << (W - 32)) - 1u : 0u;
+    for (int r = lane; r < H; r += 32) {
+      const uint4 wv = *reinterpret_cast<const uint4*>(s_wall + r * 4);
+      const uint4 cv = *reinterpret_cast<const uint4*>(s_coin + r * 4);
+      const uint32_t wa = (wsh & 32) ? wv.y : wv.x, wb = (wsh & 32) ? wv.z : wv.y,
+                     wd = (wsh & 32) ? wv.w : wv.z;
+      const uint32_t ca = (csh & 32) ? cv.y : cv.x, cb = (csh & 32) ? cv.z : cv.y,
+                     cd = (csh & 32) ? cv.w : cv.z;
+      const uint32_t w_lo = __funnelshift_r(wa, wb, wsh & 31) & m_lo;
+      const uint32_t w_hi = __funnelshift_r(wb, wd, wsh & 31) & m_hi;
+      const uint32_t c_lo = __funnelshift_r(ca, cb, csh & 31) & m_lo;
+      const uint32_t c_hi = __funnelshift_r(cb, cd, csh & 31) & m_hi;
+      uint32_t* out = s_seg + r * spr;
+      out[0] = __byte_perm(c_lo, w_lo, 0x5410);
+      if (spr > 1) out[1] = __byte_perm(c_lo, w_lo, 0x7632);
+      if (spr > 2) out[2] = __byte_perm(c_hi, w_hi, 0x5410);
+      if (spr > 3) out[3] = __byte_perm(c_hi, w_hi, 0x7632);
+    }
+  }
+  // a, b, c lie under both drapes, so they are patched into the staged backdrop
+  // up front (in z-order, by one lane); the player is the top layer and is
+  // patched into the one segment that holds it.
+  __syncwarp();
   if (lane == 0) {
+    if (coins.aux0 >= 0) s_seg[coins.aux0 * spr + (coins.aux1 >> 4)] |= 1u << (coins.aux1 & 15);
 #pragma unroll
     for (int i = 1; i < kS; ++i)
       if (visible(sp[i])) s_bd[sp[i].row * pitch + sp[i].col] = p.sprite_char[i];
   }
   __syncwarp();
+  // 5b. The streaming loop: 16 cells per lane per iteration, segment index ==
+  // 16-byte index into both the staged tile and the board (pitch = 16 * spr).
+  const int total = H * spr;
+  const int p_seg = visible(sp[0]) ? sp[0].row * spr + (sp[0].col >> 4) : -1;
+  const int p_word = (sp[0].col & 15) >> 2;
+  const uint32_t p_keep = ~(0xffu << ((sp[0].col & 3) * 8));
+  const uint32_t p_char = (uint32_t)p.sprite_char[0] << ((sp[0].col & 3) * 8);
   const unsigned drape_chars = ('#' << 8) | '@';           // bytes 4 and 5 of the permute
-  const bool ragged = (W & 15) != 0;         // last segment of a row is partly padding
-  int r = lane / spr, sg = lane - r * spr;   // this lane's (row, segment) and its stride
-  const int dr = 32 / spr, dsg = 32 - dr * spr;
+  const uint4* src = reinterpret_cast<const uint4*>(s_bd);
+  uint4* dst = reinterpret_cast<uint4*>(p.out.d_board + (int64_t)env * H * pitch);
   for (int seg = lane; seg < total; seg += 32) {
-    const int c0 = sg << 4;
-    const int off = r * pitch + c0;
-    uint4 px = *reinterpret_cast<const uint4*>(s_bd + off);
-    unsigned coin_bits = window16(s_coin + r * 4, csh + c0);
-    unsigned wall_bits = window16(s_wall + r * 4, wsh + c0);
-    if (ragged && sg == spr - 1) {
-      const unsigned valid = (1u << (W - c0)) - 1u;
-      coin_bits &= valid; wall_bits &= valid;
-    }
-    if (seg == stale_seg) coin_bits |= stale_bit;
-    px.x = __byte_perm(px.x, drape_chars, s_sel[((wall_bits & 0xfu) << 4) | (coin_bits & 0xfu)]);
-    px.y = __byte_perm(px.y, drape_chars, s_sel[(wall_bits & 0xf0u) | ((coin_bits >> 4) & 0xfu)]);
-    px.z = __byte_perm(px.z, drape_chars,
-                       s_sel[((wall_bits >> 4) & 0xf0u) | ((coin_bits >> 8) & 0xfu)]);
-    px.w = __byte_perm(px.w, drape_chars,
-                       s_sel[((wall_bits >> 8) & 0xf0u) | ((coin_bits >> 12) & 0xfu)]);
+    uint4 px = src[seg];
+    const uint32_t bits = s_seg[seg];
+    px.x = prmt(px.x, drape_chars, s_sel[((bits >> 12) & 0xf0u) | (bits & 0xfu)]);
+    px.y = prmt(px.y, drape_chars, s_sel[((bits >> 16) & 0xf0u) | ((bits >> 4) & 0xfu)]);
+    px.z = prmt(px.z, drape_chars, s_sel[((bits >> 20) & 0xf0u) | ((bits >> 8) & 0xfu)]);
+    px.w = prmt(px.w, drape_chars, s_sel[((bits >> 24) & 0xf0u) | ((bits >> 12) & 0xfu)]);
     if (seg == p_seg) {
       if (p_word == 0) px.x = (px.x & p_keep) | p_char;
       else if (p_word == 1) px.y = (px.y & p_keep) | p_char;
       else if (p_word == 2) px.z = (px.z & p_keep) | p_char;
       else px.w = (px.w & p_keep) | p_char;
     }
-    *reinterpret_cast<uint4*>(board + off) = px;
-    r += dr; sg += dsg;
-    if (sg >= spr) { sg -= spr; ++r; }
+    dst[seg] = px;
   }
 }
 
@@ -453,8 +463,7 @@ scrolly_maze_step(const StepParams p) {
 cudaError_t launch_scrolly_maze(const StepParams& p, cudaStream_t s) {
   if (p.W > 64 || (p.PWW & 1)) return cudaErrorInvalidValue;   // 4-word staged window rows
   const int blocks = (p.B + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  const size_t per_warp = kRecWords * 4 + (size_t)p.H * p.pitch + 2 * ((size_t)p.H * 16);
-  const size_t smem = per_warp * kWarpsPerBlock;
+  const size_t smem = warp_smem_bytes(p.H, p.pitch) * kWarpsPerBlock;
   if (smem > 48 * 1024) {   // opt in per launch: the attribute is per device, handles are not
     cudaError_t e = cudaFuncSetAttribute(scrolly_maze_step,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
