@@ -82,9 +82,17 @@ class Plot(dict):
   def prior_chapter(self):
     return self._prior_chapter
 
+  @prior_chapter.setter
+  def prior_chapter(self, val):
+    self._prior_chapter = val
+
   @property
   def this_chapter(self):
     return self._this_chapter
+
+  @this_chapter.setter
+  def this_chapter(self, val):
+    self._this_chapter = val
 
   @property
   def next_chapter(self):

@@ -365,6 +365,8 @@ def main():
   assert refdriver.available(), '/root/reference is required'
   if sys.argv[1:] == ['classics']:      # add these without rewriting the older files
     return classics()
+  if sys.argv[1:] == ['stories']:
+    return stories()
   # BASELINE.json configs[0]: stock scrolly_maze, 1000 random-action steps.
   for level, T in ((0, 1000), (1, 400), (2, 400)):
     maze, board, beneath = refdriver.ref_stock_scrolly_art(level)
@@ -410,6 +412,66 @@ def main():
   cropper('crop_margins_nopad', None, (2, 3), None, True)
   cropper('crop_margins_pad_offset', ' ', (2, 3), (1, -2), False)
   classics()
+  stories()
+
+
+# Same-shape (4x12) chapters for a list-style story without croppers.
+STORY_LIST_CHAPTERS = (
+    ('cliff_walk', None),
+    ('chain_walk', ['............', '.....P......', '............', '............']),
+    ('cliff_walk', ['............', '............', '........P...', '............']),
+)
+
+
+def story_cases():
+  """name -> (reference Story builder, actions): see `story()`."""
+  st = refdriver.ref_storytelling()
+  ref_cropping = refdriver._import()['cropping']
+
+  def classics_list():
+    # (A list-story of scrolly_maze levels is not a usable case: the reference
+    # copies the old Plot's scrolling-protocol entries into the next game, whose
+    # Scrollys then reject the stale order with scrolling.Error.)
+    return st.Story([lambda k=k, a=a: refdriver.ref_classic(k, a) for k, a in STORY_LIST_CHAPTERS])
+
+  def classics_cropped():
+    def cliff():
+      game = refdriver.ref_classic('cliff_walk')
+      game.the_plot.next_chapter = 'chain'
+      return game
+
+    def rooms():
+      game = refdriver.ref_classic('four_rooms')
+      game.the_plot.next_chapter = 'cliff'
+      return game
+    return st.Story(
+        {'rooms': rooms, 'cliff': cliff, 'chain': lambda: refdriver.ref_classic('chain_walk')},
+        first_chapter='rooms',
+        croppers={'rooms': ref_cropping.FixedCropper((1, 0), 4, 12), 'cliff': None,
+                  'chain': ref_cropping.FixedCropper((0, 0), 4, 12, pad_char='.')})
+
+  rs = np.random.RandomState(77)
+  a1 = rs.randint(0, 5, size=700)
+  a1[rs.random_sample(700) < 0.01] = 5              # quit now and then: next chapter
+  a2 = rs.randint(0, 4, size=900)
+  return {'story_classics_list': (classics_list, (a1 % 4).tolist()),
+          'story_classics_cropped': (classics_cropped, a2.tolist())}
+
+
+def story(name, make, actions):
+  """A reference Story played to its end (then rebuilt, like any env of the
+  trajectory protocol); also records which chapter was current each frame."""
+  chapters = []
+  traj = tj.run_trajectory(
+      make, actions,
+      on_frame=lambda env, out: chapters.append(str(env.the_plot.this_chapter)))
+  save(name, actions=np.array(actions, dtype=np.int32),
+       chapters=np.array(chapters), **traj)
+
+
+def stories():
+  for name, (make, actions) in story_cases().items():
+    story(name, make, actions)
 
 
 def classics():

@@ -102,6 +102,20 @@ def ref_classic_art(kind):
   return list(importlib.import_module('pycolab.examples.classics.' + kind).GAME_ART)
 
 
+def ref_storytelling():
+  """The reference's storytelling module.  It spells `collections.Mapping` /
+  `collections.Sequence` (gone since Python 3.10); alias them for the import —
+  an environment shim, the reference source is untouched."""
+  _import()
+  import collections
+  import collections.abc
+  for name in ('Mapping', 'Sequence'):
+    if not hasattr(collections, name):
+      setattr(collections, name, getattr(collections.abc, name))
+  from pycolab import storytelling
+  return storytelling
+
+
 def ref_warehouse(art, beneath=' ', level=None):
   m = _import()['warehouse_manager']
   if level is not None:
