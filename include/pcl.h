@@ -67,7 +67,10 @@ typedef enum pcl_program {
   PCL_PROG_MARAUDERS = 3,    /* examples/extraterrestrial_marauders.py:91-256  */
   PCL_PROG_FIXTURE = 4,      /* tests/test_things.py TestMazeWalker/TestScrolly */
   PCL_PROG_BETTER_SCROLLY = 5, /* examples/better_scrolly_maze.py:209-324       */
-  PCL_PROG_CLASSICS = 6      /* examples/classics/{four_rooms,cliff_walk,chain_walk}.py */
+  PCL_PROG_CLASSICS = 6,     /* one-walker games: examples/classics/{four_rooms,cliff_walk,
+                                chain_walk}.py, examples/fluvial_natation.py */
+  PCL_PROG_APERTURE = 7      /* examples/aperture.py:118-196; the drape record's AUX0 / AUX1 hold
+                                the two aperture cells (row << 16 | col, -1 = none) */
 } pcl_program;
 
 /* PCL_PROG_CLASSICS: pcl_spec.program_arg[0] selects the rule set; the games
@@ -75,7 +78,10 @@ typedef enum pcl_program {
  * equal int32 value. */
 enum { PCL_CLASSIC_FOUR_ROOMS = 0, /* four_rooms.py:52-80; program_arg[1..2] = goal cell (4, 3) */
        PCL_CLASSIC_CLIFF_WALK = 1, /* cliff_walk.py:46-86 */
-       PCL_CLASSIC_CHAIN_WALK = 2  /* chain_walk.py:44-73 */ };
+       PCL_CLASSIC_CHAIN_WALK = 2, /* chain_walk.py:44-73 */
+       PCL_CLASSIC_FLUVIAL = 3     /* examples/fluvial_natation.py:61-110 (int rewards); program_arg[1..2] =
+                                      first / end row of the flowing backdrop band (1, 4); the
+                                      rotation count is plot word PCL_P_AUX0 */ };
 
 /* Motion codes (prefab_parts/sprites.py:140-150). */
 enum { PCL_M_N = 0, PCL_M_NE, PCL_M_E, PCL_M_SE, PCL_M_S, PCL_M_SW, PCL_M_W,

@@ -394,6 +394,7 @@ class World(object):
     self.z_order = list(z_order)
     self.groups = [list(g) for g in groups]
     self.program = program          # callable(world, char, actions)
+    self.backdrop_program = None    # callable(world, actions): Backdrop.update, engine.py:718-721
     self.plot = PlotRegs()
     self.board = None               # last render (engine._board.board)
     self.game_over = False
@@ -416,6 +417,8 @@ class World(object):
     plot.frame += 1
     plot.update_group = None
     self.staged = []
+    if self.backdrop_program is not None:      # before any entity, on the stale board
+      self.backdrop_program(self, actions)
     for gi, group in enumerate(self.groups):
       plot.update_group = gi
       for ch in group:

@@ -12,6 +12,8 @@ paints `char`.  Reference (under /root/reference/pycolab/):
   examples/better_scrolly_maze.py:209-324     -> make_better_scrolly / better_scrolly_program
   examples/classics/four_rooms.py:45-85, cliff_walk.py:39-86,
   chain_walk.py:37-73                         -> make_classic / classics_program
+  examples/fluvial_natation.py:53-110         -> make_fluvial / fluvial_program
+  examples/aperture.py:118-196                -> make_aperture / aperture_program
   ascii_art.py:31-292                         -> split_art
 """
 
@@ -408,6 +410,102 @@ def classics_program(world, ch, actions):
     elif ent.col == ent.cols - 1:
       plot.add_reward(100.0)
       plot.terminate_episode()
+
+
+# ==========================================================================
+# fluvial_natation: a Backdrop with update() logic.
+# ==========================================================================
+
+def make_fluvial(art):
+  """examples/fluvial_natation.py:53-58."""
+  backdrop, masks = split_art(art, ['P'], ' ')
+  shape = backdrop.shape
+  walker = em.Walker('P', shape, mask_position(masks['P']), impassable='')   # :71-74
+  world = em.World(shape[0], shape[1], backdrop, {'P': walker}, z_order='P',
+                   groups=[['P']], program=fluvial_program)
+  world.backdrop_program = fluvial_backdrop_program
+  return world
+
+
+def fluvial_backdrop_program(world, actions):
+  """RiverBackdrop.update :106-110: rows 1..3 flow one cell west on even frames."""
+  if world.plot.frame % 2 == 0:
+    world.backdrop[1:4, :] = np.roll(world.backdrop[1:4, :], shift=-1, axis=1)
+
+
+def fluvial_program(world, ch, actions):
+  """PlayerSprite.update :76-93."""
+  plot, ent, board = world.plot, world.things[ch], world.board
+  if plot.frame % 2 == 0:
+    em.walker_move(ent, board, plot, em.M_W)
+  if actions == 0:
+    em.walker_move(ent, board, plot, em.M_W)
+  elif actions == 1:
+    em.walker_move(ent, board, plot, em.M_E)
+  if ent.vcol < 0:
+    plot.add_reward(-1)
+    plot.terminate_episode()
+  elif ent.vcol >= board.shape[1]:
+    plot.add_reward(1)
+    plot.terminate_episode()
+
+
+# ==========================================================================
+# aperture (SURVEY.md §8f-4): a blaster that opens teleporting apertures.
+# ==========================================================================
+
+def make_aperture(art):
+  """examples/aperture.py:188-196."""
+  backdrop, masks = split_art(art, ['A', 'X'], ' ')
+  shape = backdrop.shape
+  player = em.Walker('A', shape, mask_position(masks['A']), impassable='#.@')    # :126-128
+  drape = em.PlainDrape('X', masks['X'])
+  drape.aux['apertures'] = [None, None]                                           # :161
+  return em.World(shape[0], shape[1], backdrop, {'A': player, 'X': drape}, z_order='XA',
+                  groups=[['A'], ['X']], program=aperture_program)
+
+
+def aperture_program(world, ch, actions):
+  plot, board = world.plot, world.board
+  player, drape = world.things['A'], world.things['X']
+  if ch == 'A':                                   # PlayerSprite.update :130-149
+    motion = {0: em.M_N, 1: em.M_S, 2: em.M_W, 3: em.M_E}.get(actions) \
+        if actions is not None else None
+    if motion is not None:
+      em.walker_move(player, board, plot, motion)
+    elif actions == 9:
+      plot.terminate_episode()
+    if board[player.position] == ord('C'):        # layers['C'][self.position]
+      plot.add_reward(1)
+      plot.terminate_episode()
+    if board[player.position] == ord('X'):        # layers['X'][self.position]
+      destinations = [p for p in drape.aux['apertures']
+                      if p is not None and p != player.position]
+      if destinations:
+        em.walker_teleport(player, *destinations[0])
+  elif ch == 'X':                                 # ApertureDrape.update :163-190
+    ply_y, ply_x = player.position
+    if actions not in (5, 6, 7, 8):
+      return
+    dx, dy = {5: (0, -1), 6: (-1, 0), 7: (0, 1), 8: (1, 0)}[actions]
+    height, width = board.shape
+    for step in range(1, max(height, width)):
+      cur_x, cur_y = ply_x + dx * step, ply_y + dy * step
+      if cur_x < 0 or cur_x >= width or cur_y < 0 or cur_y >= height:
+        break
+      elif board[cur_y, cur_x] == ord('#'):
+        break
+      elif board[cur_y, cur_x] == ord('X'):
+        break
+      if board[cur_y, cur_x] == ord('@'):
+        drape.aux['apertures'] = drape.aux['apertures'][1:] + [(cur_y, cur_x)]
+        drape.curtain.fill(False)
+        for aperture in drape.aux['apertures']:
+          if aperture is not None:
+            drape.curtain[aperture] = True
+        break
+  else:
+    raise KeyError(ch)
 
 
 # ==========================================================================

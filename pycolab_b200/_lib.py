@@ -29,8 +29,8 @@ ENV_ERR_INDEX = 0x8
 ENV_ERR_BAD_Z = 0x10
 
 PROG_NONE, PROG_SCROLLY_MAZE, PROG_WAREHOUSE, PROG_MARAUDERS, PROG_FIXTURE = 0, 1, 2, 3, 4
-PROG_BETTER_SCROLLY, PROG_CLASSICS = 5, 6
-CLASSIC_FOUR_ROOMS, CLASSIC_CLIFF_WALK, CLASSIC_CHAIN_WALK = 0, 1, 2
+PROG_BETTER_SCROLLY, PROG_CLASSICS, PROG_APERTURE = 5, 6, 7
+CLASSIC_FOUR_ROOMS, CLASSIC_CLIFF_WALK, CLASSIC_CHAIN_WALK, CLASSIC_FLUVIAL = 0, 1, 2, 3
 
 # Record word indices (pcl.h enums).
 S_ROW, S_COL, S_VROW, S_VCOL, S_FLAGS, S_AUX0, S_AUX1, S_AUX2 = range(8)

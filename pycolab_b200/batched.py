@@ -272,6 +272,13 @@ class BatchedEngine(object):
       on = rec[:, :, _lib.S_AUX0] != 0
       b, s = torch.nonzero(on, as_tuple=True)
       out[b, rec[b, s, _lib.S_ROW].long(), rec[b, s, _lib.S_COL].long()] = 1
+    elif self.game.program == _lib.PROG_APERTURE:
+      # ApertureDrape curtain = the (at most two) cells of its `_apertures` list.
+      out.zero_()
+      for word in (_lib.D_AUX0, _lib.D_AUX1):
+        cell = self.drapes[:, d, word]
+        b = torch.nonzero(cell >= 0, as_tuple=True)[0]
+        out[b, (cell[b] >> 16).long(), (cell[b] & 0xffff).long()] = 1
     else:
       _lib.check(self._lib.pcl_export_curtain(self._h, d, out.data_ptr(), self._stream()),
                  'pcl_export_curtain')

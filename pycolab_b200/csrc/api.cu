@@ -137,8 +137,24 @@ int validate(const pcl_spec& s) {
       if (s.sprite_egocentric[0]) return PCL_ERR_UNSUPPORTED;
       const int rule = s.program_arg[0];
       if (rule != PCL_CLASSIC_FOUR_ROOMS && rule != PCL_CLASSIC_CLIFF_WALK &&
-          rule != PCL_CLASSIC_CHAIN_WALK) return PCL_ERR_INVALID;
+          rule != PCL_CLASSIC_CHAIN_WALK && rule != PCL_CLASSIC_FLUVIAL) return PCL_ERR_INVALID;
+      if (rule == PCL_CLASSIC_FLUVIAL) {
+        // The kernel re-stages the flowing rows before the swimmer moves, which is
+        // only equivalent when the swimmer never looks at the board.
+        if (!set_is(s.impassable[0], "")) return PCL_ERR_UNSUPPORTED;
+        if (s.program_arg[1] < 0 || s.program_arg[2] < s.program_arg[1]) return PCL_ERR_INVALID;
+      }
       if (s.rows * s.pitch > 8192) return PCL_ERR_UNSUPPORTED;   // the tile is staged per env in smem
+      return PCL_OK;
+    }
+    case PCL_PROG_APERTURE: {
+      if (s.n_sprites != 1 || s.n_drapes != 1) return PCL_ERR_UNSUPPORTED;
+      if (s.z_order[0] != s.drape_char[0] || s.z_order[1] != s.sprite_char[0]) return PCL_ERR_UNSUPPORTED;
+      if (s.n_groups != 2 || s.group_len[0] != 1 || s.group_len[1] != 1 ||
+          s.group_chars[0] != s.sprite_char[0] || s.group_chars[1] != s.drape_char[0])
+        return PCL_ERR_UNSUPPORTED;
+      if (s.sprite_egocentric[0]) return PCL_ERR_UNSUPPORTED;
+      if (s.rows >= 32768 || s.cols >= 32768 || s.rows * s.pitch > 8192) return PCL_ERR_UNSUPPORTED;
       return PCL_OK;
     }
     case PCL_PROG_FIXTURE: {
@@ -205,6 +221,7 @@ int launch(pcl_handle* h, const StepParams& p, cudaStream_t stream) {
     case PCL_PROG_FIXTURE: e = pcl::launch_fixture(p, stream); break;
     case PCL_PROG_BETTER_SCROLLY: e = pcl::launch_better_scrolly(p, stream); break;
     case PCL_PROG_CLASSICS: e = pcl::launch_classics(p, stream); break;
+    case PCL_PROG_APERTURE: e = pcl::launch_aperture(p, stream); break;
     default: return PCL_ERR_UNSUPPORTED;
   }
   h->launches += 1;

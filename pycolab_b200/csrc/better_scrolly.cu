@@ -197,25 +197,33 @@ better_scrolly_step(const StepParams p) {
   if (lane < 8) g_drapes[lane] = rec[32 + lane];
   if (lane >= 16) g_plot[lane - 16] = rec[32 + lane];
 
-  // ---- final render, z-order a b c @ P
-  uint8_t* board = p.out.d_board + (int64_t)env * tile;
-  const int segs_per_row = pitch >> 4;
-  const int total = H * segs_per_row;
-  for (int seg = lane; seg < total; seg += 32) {
-    const int r = seg / segs_per_row;
-    const int c0 = (seg - r * segs_per_row) << 4;
-    const int ncols = min(16, W - c0);
-    uint4 px = *reinterpret_cast<const uint4*>(s_bd + (size_t)r * pitch + c0);
-    const unsigned coin_bits = ncols > 0 ? bits16(s_coin + r * BW, c0) & ((1u << ncols) - 1u) : 0u;
+  // ---- final render, z-order a b c @ P (engine.py:737-759).  a, b, c lie under
+  // the coins: patch them into the staged tile up front; coins come from the
+  // bit rows (segment sg of a row = its sg-th 16-bit half-word); P is the top
+  // layer, patched into the one segment that holds it.
+  __syncwarp();
+  if (lane == 0) {
 #pragma unroll
-    for (int i = 1; i < kS; ++i) {
-      const unsigned m = sprite_bit(sp[i], r, c0);
-      if (m) paint_bits(px, m, p.sprite_char[i]);
-    }
+    for (int i = 1; i < kS; ++i)
+      if (visible(sp[i])) s_bd[sp[i].row * pitch + sp[i].col] = p.sprite_char[i];
+  }
+  __syncwarp();
+  const int spr = pitch >> 4;
+  const int total = H * spr;
+  const int p_seg = visible(sp[0]) ? sp[0].row * spr + (sp[0].col >> 4) : -1;
+  const unsigned p_bit = 1u << (sp[0].col & 15);
+  const uint4* src = reinterpret_cast<const uint4*>(s_bd);
+  uint4* dst = reinterpret_cast<uint4*>(p.out.d_board + (int64_t)env * tile);
+  int r = lane / spr, sg = lane - r * spr;     // this lane's (row, segment) and its stride
+  const int dr = 32 / spr, dsg = 32 - dr * spr;
+  for (int seg = lane; seg < total; seg += 32) {
+    uint4 px = src[seg];
+    const unsigned coin_bits = reinterpret_cast<const uint16_t*>(s_coin + r * BW)[sg];
     if (coin_bits) paint_bits(px, coin_bits, '@');
-    const unsigned m = sprite_bit(sp[0], r, c0);
-    if (m) paint_bits(px, m, p.sprite_char[0]);
-    *reinterpret_cast<uint4*>(board + (int64_t)r * pitch + c0) = px;
+    if (seg == p_seg) paint_bits(px, p_bit, p.sprite_char[0]);
+    dst[seg] = px;
+    r += dr; sg += dsg;
+    if (sg >= spr) { sg -= spr; ++r; }
   }
 }
 

@@ -1,5 +1,6 @@
-// classics.cu — fused step kernel for examples/classics/{four_rooms,cliff_walk,
-// chain_walk}.py.
+// classics.cu — fused step kernel for the single-walker games: examples/classics/
+// {four_rooms,cliff_walk,chain_walk}.py and examples/fluvial_natation.py
+// (SURVEY.md §8f-4).
 //
 // Each game is one MazeWalker 'P' over a static backdrop: one update group
 // ['P'], z-order 'P', no drapes.  The only board cells the walker ever reads
@@ -14,8 +15,15 @@
 //   PCL_CLASSIC_CHAIN_WALK  actions 0, 1 = W E; col 0: 1.0 + terminate; col W-1:
 //                           100.0 + terminate               (chain_walk.py:60-73)
 //
-// Rewards are float in the reference; d_reward carries the equal integer and
-// the host facade converts back (engine.py).
+//   PCL_CLASSIC_FLUVIAL     examples/fluvial_natation.py:61-110: on even frames the
+//                           backdrop rows [arg[1], arg[2]) rotate one cell west
+//                           (RiverBackdrop.update; the rotation count lives in
+//                           plot aux0, the backdrop array itself stays static)
+//                           and the swimmer drifts west; actions 0, 1 = W E;
+//                           virtual col < 0: -1 + terminate, >= W: +1 + terminate.
+//
+// classics rewards are float in the reference; d_reward carries the equal
+// integer and the host facade converts back (engine.py).
 //
 // One warp per env like the other programs; the records travel through shared
 // memory with coalesced loads, the tile with cp.async.
@@ -89,22 +97,41 @@ classics_step(const StepParams p) {
   Plot plot;
   plot.frame = rec[16 + PCL_P_FRAME] + 1;                    // engine.py:716
   plot.error = rec[16 + PCL_P_ERROR];
-  plot.aux0 = 0;
+  plot.aux0 = rec[16 + PCL_P_AUX0];                          // river rotation count
   plot.order_frame = PCL_NEVER; plot.order_r = plot.order_c = 0; plot.ego_mask = 0;
   Directives dir = fresh_directives();
 
   const int rule = p.program_arg[0];
+  auto blocked = [&](int r, int c) { return in_set(p.impassable[0], s_bd[r * pitch + c]); };
   int motion = PCL_M_NONE;
-  if (rule == PCL_CLASSIC_CHAIN_WALK) {
+  if (rule == PCL_CLASSIC_FLUVIAL) {
+    const bool even = (plot.frame & 1) == 0;
+    // Backdrop.update runs first (engine.py:718-721); the swimmer's set of
+    // impassable characters is empty (checked in pcl_create), so nobody reads the
+    // stale board and the band can be re-staged for the final render right away.
+    if (even) plot.aux0 = plot.aux0 + 1 == W ? 0 : plot.aux0 + 1;
+    const int r0 = min(p.program_arg[1], H), r1 = min(p.program_arg[2], H);
+    const int k = plot.aux0;
+    for (int i = lane; i < (r1 - r0) * W; i += 32) {
+      const int r = r0 + i / W, c = i - (r - r0) * W;
+      int src = c + k;
+      if (src >= W) src -= W;
+      s_bd[r * pitch + c] = __ldg(backdrop + r * pitch + src);
+    }
+    if (even) walker_move(sp, 0, PCL_M_W, plot, H, W, p.confined[0] != 0, false, lane, blocked);
+    motion = action == 0 ? PCL_M_W : action == 1 ? PCL_M_E : PCL_M_NONE;
+  } else if (rule == PCL_CLASSIC_CHAIN_WALK) {
     motion = action == 0 ? PCL_M_W : action == 1 ? PCL_M_E : PCL_M_NONE;
   } else {
     motion = action == 0 ? PCL_M_N : action == 1 ? PCL_M_S : action == 2 ? PCL_M_W
            : action == 3 ? PCL_M_E : PCL_M_NONE;
   }
   if (motion != PCL_M_NONE)
-    walker_move(sp, 0, motion, plot, H, W, p.confined[0] != 0, false, lane,
-                [&](int r, int c) { return in_set(p.impassable[0], s_bd[r * pitch + c]); });
-  if (rule == PCL_CLASSIC_FOUR_ROOMS) {
+    walker_move(sp, 0, motion, plot, H, W, p.confined[0] != 0, false, lane, blocked);
+  if (rule == PCL_CLASSIC_FLUVIAL) {
+    if (sp.vcol < 0) { add_reward(dir, -1); terminate(dir); }
+    else if (sp.vcol >= W) { add_reward(dir, 1); terminate(dir); }
+  } else if (rule == PCL_CLASSIC_FOUR_ROOMS) {
     if (sp.row == p.program_arg[1] && sp.col == p.program_arg[2]) { add_reward(dir, 1); terminate(dir); }
   } else if (rule == PCL_CLASSIC_CLIFF_WALK) {
     if (motion != PCL_M_NONE) {
@@ -122,7 +149,7 @@ classics_step(const StepParams p) {
     rec[PCL_S_ROW] = sp.row; rec[PCL_S_COL] = sp.col;
     rec[PCL_S_VROW] = sp.vrow; rec[PCL_S_VCOL] = sp.vcol; rec[PCL_S_FLAGS] = sp.flags;
     rec[16 + PCL_P_FRAME] = plot.frame; rec[16 + PCL_P_GAME_OVER] = dir.game_over;
-    rec[16 + PCL_P_ERROR] = plot.error;
+    rec[16 + PCL_P_ERROR] = plot.error; rec[16 + PCL_P_AUX0] = plot.aux0;
     p.out.d_reward[env] = dir.reward;
     p.out.d_has_reward[env] = (uint8_t)dir.has_reward;
     p.out.d_discount[env] = dir.discount;

@@ -77,7 +77,8 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 
 __host__ __device__ __forceinline__ size_t warp_smem_bytes(int H, int pitch) {
   // records, backdrop tile, two 4-word window rows per board row, one word per segment
-  return kRecWords * 4 + (size_t)H * pitch + 2 * ((size_t)H * 16) + (size_t)H * (pitch >> 2);
+  return kRecWords * 4 + (size_t)H * pitch + 2 * ((size_t)H * 16) +
+         (((size_t)H * (pitch >> 2) + 15) & ~(size_t)15);      // keep every warp's slice 16-byte aligned
 }
 
 // Programmatic dependent launch: let the next kernel of the stream begin its

@@ -33,13 +33,6 @@ constexpr int kRecWords = 128;      // 11 * 8 sprite words + 8 drape + 16 plot, 
 __device__ __forceinline__ bool in_set(const uint32_t* set, int code) {
   return (set[(code >> 5) & 3] >> (code & 31)) & 1u;
 }
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::
-               "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-}
 __device__ __forceinline__ int motion_of_action(int a) {    // :214-226, :288-295
   return a == 0 ? PCL_M_N : a == 1 ? PCL_M_S : a == 2 ? PCL_M_W : PCL_M_E;
 }
@@ -129,7 +122,6 @@ warehouse_step(const StepParams p) {
   const bool is_box = lane < NB;
   const int32_t* mine = rec + (is_box ? lane : 0) * PCL_SPRITE_WORDS;
   int b_row = mine[PCL_S_ROW], b_col = mine[PCL_S_COL];
-  const int b_x_old = mine[PCL_S_AUX0];
 
   // Character of the stale board (= previous final render) at (r, c): P on top,
   // then a box (drawn 'X' when the judge marked it), else the backdrop.

@@ -35,6 +35,7 @@ class Engine(object):
     self._current_update_group = ''
     self._board = None
     self._batched = None
+    self._backdrop_template = None   # initial curtain of a Backdrop the device animates
 
   # ------------------------------------------------------------ set-up API
   def set_backdrop(self, characters, backdrop_class, *args, **kwargs):
@@ -203,6 +204,12 @@ class Engine(object):
     sprites = b.sprites[0].cpu().numpy()
     drapes = b.drapes[0].cpu().numpy()
     self._the_plot._frame = int(b.plot[0, _lib.P_FRAME])
+    if b.game.backdrop_role == 'river':    # RiverBackdrop.update as a rotation count
+      if self._backdrop_template is None:
+        self._backdrop_template = self._backdrop.curtain.copy()
+      r0, r1 = b.game.program_arg[1], b.game.program_arg[2]
+      self._backdrop.curtain[r0:r1] = np.roll(self._backdrop_template[r0:r1],
+                                              -int(b.plot[0, _lib.P_AUX0]), axis=1)
     if b.z_order is not None:             # Plot.change_z_order happened on the device
       order = [chr(c) for c in b.z_order[0].cpu().numpy()]
       self._sprites_and_drapes = collections.OrderedDict(
@@ -219,6 +226,9 @@ class Engine(object):
         ent._northwest_corner = things.Sprite.Position(int(rec[_lib.D_CORNER_R]),
                                                        int(rec[_lib.D_CORNER_C]))
       np.copyto(ent.curtain, b.curtain(ch)[0].cpu().numpy())
+      if b.game.program == _lib.PROG_APERTURE:       # ApertureDrape._apertures
+        cells = [int(rec[_lib.D_AUX0]), int(rec[_lib.D_AUX1])]
+        ent._apertures = [None if c < 0 else (c >> 16, c & 0xffff) for c in cells]
 
   # ------------------------------------------------------------ properties
   @property

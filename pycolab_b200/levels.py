@@ -167,3 +167,28 @@ def classic_level(kind):
     a[0, 17] = ord('P')
     return _to_art(a)
   raise ValueError(kind)
+
+
+def fluvial_level(rows=7, cols=40, seed=0):
+  """A second river for `examples/fluvial_natation.py` (the rules flow rows 1..3
+  whatever the size, fluvial_natation.py:106-110)."""
+  rs = np.random.RandomState(seed)
+  a = np.full((rows, cols), ord(' '), dtype=np.uint8)
+  a[0, :] = a[-1, :] = ord('=')
+  waves = rs.random_sample((rows - 2, cols)) < 0.15
+  a[1:-1][waves] = rs.choice([ord(c) for c in '.,`:~'], size=int(waves.sum()))
+  a[3, cols // 3] = ord('P')
+  return _to_art(a)
+
+
+def aperture_level():
+  """A small `examples/aperture.py` level: an ooze moat between the player and
+  the cranachan, special walls '@' on both sides to shoot apertures into."""
+  return ['###############',
+          '#@           @#',
+          '#  A   ..     #',
+          '#      ..     #',
+          '#@     ..    @#',
+          '#      ..  C  #',
+          '###@###..##@###',
+          '###############']

@@ -47,6 +47,9 @@ LOWERED_CLASSES = {
     ('four_rooms', 'PlayerSprite'): 'classics.four_rooms',
     ('cliff_walk', 'PlayerSprite'): 'classics.cliff_walk',
     ('chain_walk', 'PlayerSprite'): 'classics.chain_walk',
+    ('fluvial_natation', 'PlayerSprite'): 'classics.fluvial',
+    ('aperture', 'PlayerSprite'): 'aperture.player',
+    ('aperture', 'ApertureDrape'): 'aperture.drape',
     # General entities: the reference's test fixtures and this package's twins.
     ('test_things', 'TestMazeWalker'): 'fixture.walker',
     ('test_things', 'TestScrolly'): 'fixture.scrolly',
@@ -54,6 +57,11 @@ LOWERED_CLASSES = {
     ('fixtures', 'FixtureMazeWalker'): 'fixture.walker',
     ('fixtures', 'FixtureScrolly'): 'fixture.scrolly',
     ('fixtures', 'FixtureDrape'): 'fixture.drape',
+}
+
+# Backdrop subclasses whose update() has a device counterpart.
+LOWERED_BACKDROPS = {
+    ('fluvial_natation', 'RiverBackdrop'): 'river',
 }
 
 _PROGRAM_OF = {'scrolly': _lib.PROG_SCROLLY_MAZE, 'warehouse': _lib.PROG_WAREHOUSE,
@@ -139,6 +147,7 @@ class LoweredGame(object):
     self.dynamic_z = False      # per-env z-order array (Plot.change_z_order)
     self.program_arg = [0] * 8  # pcl_spec.program_arg
     self.reward_type = int      # the reference's reward type (classics pay floats)
+    self.backdrop_role = None   # device counterpart of a Backdrop with update() logic
 
   def signature(self):
     """Everything that must agree between envs sharing one handle."""
@@ -224,8 +233,16 @@ def _common(engine, game, program):
   game.groups = [''.join(e.character for e in entities)
                  for _, entities in sorted(engine._update_groups.items())]
   backdrop = engine.backdrop
+  game.backdrop_role = None
   if type(backdrop).update is not things.Backdrop.update:
-    raise NotLoweredError('Backdrop subclasses with update() logic are not lowered')
+    for klass in type(backdrop).__mro__:
+      key = (klass.__module__.rsplit('.', 1)[-1], klass.__name__)
+      if key in LOWERED_BACKDROPS and type(backdrop).update is klass.update:
+        game.backdrop_role = LOWERED_BACKDROPS[key]
+        break
+    else:
+      raise NotLoweredError('no device program for the update() logic of Backdrop class '
+                            '{}.{}'.format(type(backdrop).__module__, type(backdrop).__name__))
   game.backdrop = np.zeros((engine.rows, game.pitch), dtype=np.uint8)
   game.backdrop[:, :engine.cols] = backdrop.curtain
   game.backdrop_chars = ''.join(sorted(backdrop.palette))
@@ -377,16 +394,52 @@ def _lower_classics(engine, roles):
   rule = roles['P'].split('.')[1]
   game.program_arg[0] = {'four_rooms': _lib.CLASSIC_FOUR_ROOMS,
                          'cliff_walk': _lib.CLASSIC_CLIFF_WALK,
-                         'chain_walk': _lib.CLASSIC_CHAIN_WALK}[rule]
+                         'chain_walk': _lib.CLASSIC_CHAIN_WALK,
+                         'fluvial': _lib.CLASSIC_FLUVIAL}[rule]
   if rule == 'four_rooms':
     game.program_arg[1], game.program_arg[2] = 4, 3
+  if (rule == 'fluvial') != (game.backdrop_role == 'river'):
+    raise NotLoweredError('the river Backdrop and the swimmer are lowered only together')
+  if rule == 'fluvial':
+    game.program_arg[1], game.program_arg[2] = 1, 4      # curtain[1:4, :], fluvial_natation.py:110
   if game.rows * game.pitch > 8192:
     raise NotLoweredError('classics boards are staged whole in shared memory (<= 8 KiB)')
   player = engine.things['P']
   _set_sprites(game, [player], [_sprite_record(player)])
+  if rule == 'fluvial' and any(game.impassable[0]):
+    raise NotLoweredError('the river program needs a swimmer with no impassable characters')
   game.drapes = np.zeros((0, _lib.DRAPE_WORDS), dtype=np.int32)
   game.plot = np.array(_plot_record(), dtype=np.int32)
-  game.reward_type = float
+  game.reward_type = int if rule == 'fluvial' else float
+  return game
+
+
+def _lower_aperture(engine, roles):
+  """examples/aperture.py:188-196: sprite 'A' + the aperture drape.  The drape's
+  state is its `_apertures` list (at most two cells) in the record's AUX words."""
+  players = [c for c, r in roles.items() if r == 'aperture.player']
+  drapes = [c for c, r in roles.items() if r == 'aperture.drape']
+  if len(players) != 1 or len(drapes) != 1 or len(roles) != 2:
+    raise NotLoweredError('aperture program needs one player and one aperture drape '
+                          '(got {})'.format(roles))
+  game = LoweredGame()
+  _common(engine, game, _lib.PROG_APERTURE)
+  player, drape = engine.things[players[0]], engine.things[drapes[0]]
+  if game.z_order != drapes[0] + players[0] or game.groups != [players[0], drapes[0]]:
+    raise NotLoweredError('aperture program needs update groups [[player], [drape]] and the '
+                          'player drawn over the drape')
+  if drape.curtain.any() or list(drape._apertures) != [None, None]:
+    raise NotLoweredError('the aperture drape must start with no apertures')
+  if game.rows * game.pitch > 8192:
+    raise NotLoweredError('aperture boards are staged whole in shared memory (<= 8 KiB)')
+  _set_sprites(game, [player], [_sprite_record(player)])
+  game.drape_chars = drapes[0]
+  game.margins = [(-1, -1)]
+  rec = [0] * _lib.DRAPE_WORDS
+  rec[_lib.D_LAST_FRAME] = _lib.NEVER
+  rec[_lib.D_AUX0] = rec[_lib.D_AUX1] = -1
+  game.drapes = np.array([rec], dtype=np.int32)
+  game.plot = np.array(_plot_record(), dtype=np.int32)
   return game
 
 
@@ -443,16 +496,13 @@ def lower(engine):
   if len(families) != 1:
     raise NotLoweredError('entities from different game programs: {}'.format(roles))
   family = families.pop()
-  if family == 'scrolly':
-    return _lower_scrolly_maze(engine, roles)
-  if family == 'warehouse':
-    return _lower_warehouse(engine, roles)
-  if family == 'marauders':
-    return _lower_marauders(engine, roles)
-  if family == 'fixture':
-    return _lower_fixture(engine, roles)
-  if family == 'classics':
-    return _lower_classics(engine, roles)
-  if family == 'better':
-    return _lower_better_scrolly(engine, roles)
-  raise NotLoweredError(family)
+  lowerers = {'scrolly': _lower_scrolly_maze, 'warehouse': _lower_warehouse,
+              'marauders': _lower_marauders, 'fixture': _lower_fixture,
+              'classics': _lower_classics, 'better': _lower_better_scrolly,
+              'aperture': _lower_aperture}
+  if family not in lowerers:
+    raise NotLoweredError(family)
+  game = lowerers[family](engine, roles)
+  if game.backdrop_role is not None and family != 'classics':
+    raise NotLoweredError('a Backdrop with update() logic is lowered only with its own game')
+  return game

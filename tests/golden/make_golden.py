@@ -367,6 +367,10 @@ def main():
     return classics()
   if sys.argv[1:] == ['stories']:
     return stories()
+  if sys.argv[1:] == ['fluvial']:
+    return fluvials()
+  if sys.argv[1:] == ['aperture']:
+    return apertures()
   # BASELINE.json configs[0]: stock scrolly_maze, 1000 random-action steps.
   for level, T in ((0, 1000), (1, 400), (2, 400)):
     maze, board, beneath = refdriver.ref_stock_scrolly_art(level)
@@ -413,6 +417,8 @@ def main():
   cropper('crop_margins_pad_offset', ' ', (2, 3), (1, -2), False)
   classics()
   stories()
+  fluvials()
+  apertures()
 
 
 # Same-shape (4x12) chapters for a list-style story without croppers.
@@ -472,6 +478,52 @@ def story(name, make, actions):
 def stories():
   for name, (make, actions) in story_cases().items():
     story(name, make, actions)
+
+
+def fluvial(name, art, actions):
+  """examples/fluvial_natation.py; also records the (mutable) backdrop curtain."""
+  sprites, curtains = [], []
+
+  def on_frame(env, out):
+    sprite_recorder('P', sprites)(env, out)
+    curtains.append(env.backdrop.curtain.copy())
+  traj = tj.run_trajectory(lambda: refdriver.ref_fluvial(art), actions, on_frame=on_frame)
+  save(name, art=tj.art_to_u8(art), actions=np.array(actions, dtype=np.int32),
+       sprites=np.array(sprites, dtype=np.int32),
+       backdrops=np.stack(curtains).astype(np.uint8), **traj)
+
+
+def aperture(name, level, actions):
+  """examples/aperture.py stock level; records the player registers and the
+  aperture curtain each frame."""
+  sprites, curtains = [], []
+
+  def on_frame(env, out):
+    sprite_recorder('A', sprites)(env, out)
+    curtains.append(env.things['X'].curtain.copy())
+  traj = tj.run_trajectory(lambda: refdriver.ref_aperture(level), actions, on_frame=on_frame)
+  save(name, art=tj.art_to_u8(refdriver.ref_aperture_art(level)),
+       actions=np.array(actions, dtype=np.int32), sprites=np.array(sprites, dtype=np.int32),
+       curtains=np.stack(curtains).astype(np.uint8), **traj)
+
+
+def apertures():
+  for level in (0, 1, 2):
+    rs = np.random.RandomState(40 + level)
+    actions = rs.choice(list(range(10)), size=900,
+                        p=[.14, .14, .14, .14, .04, .1, .1, .1, .095, .005])
+    aperture('aperture_stock_L%d' % level, level, actions.tolist())
+  aperture('aperture_script_L0', 0, APERTURE_SCRIPT_L0)
+
+
+# Level 0 played to the cranachan: two aperture pairs, two teleports, reward 1.
+APERTURE_SCRIPT_L0 = [8, 7, 1, 1, 2, 1, 1, 1, 1, 1, 6, 8, 3, 3, 1, 1, 1, 3, 4, 0]
+
+
+def fluvials():
+  for which, art in (('stock', refdriver.ref_fluvial_art()), ('other', levels.fluvial_level())):
+    actions = np.random.RandomState(len(which)).choice([0, 1, 2], size=800, p=[.2, .6, .2])
+    fluvial('fluvial_%s' % which, art, actions.tolist())
 
 
 def classics():

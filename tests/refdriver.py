@@ -102,6 +102,44 @@ def ref_classic_art(kind):
   return list(importlib.import_module('pycolab.examples.classics.' + kind).GAME_ART)
 
 
+def ref_fluvial(art=None):
+  _import()
+  from pycolab.examples import fluvial_natation as m
+  if art is None:
+    return m.make_game()
+  saved = m.GAME_ART
+  try:
+    m.GAME_ART = art
+    return m.make_game()
+  finally:
+    m.GAME_ART = saved
+
+
+def ref_fluvial_art():
+  _import()
+  from pycolab.examples import fluvial_natation as m
+  return list(m.GAME_ART)
+
+
+def ref_aperture(level=None, art=None):
+  _import()
+  from pycolab.examples import aperture as m
+  if art is None:
+    return m.make_game(level)
+  saved = m.LEVELS
+  try:
+    m.LEVELS = [art]
+    return m.make_game(0)
+  finally:
+    m.LEVELS = saved
+
+
+def ref_aperture_art(level):
+  _import()
+  from pycolab.examples import aperture as m
+  return list(m.LEVELS[level])
+
+
 def ref_storytelling():
   """The reference's storytelling module.  It spells `collections.Mapping` /
   `collections.Sequence` (gone since Python 3.10); alias them for the import —

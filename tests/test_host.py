@@ -2,6 +2,7 @@
 lowering, compat loading of the reference's example modules."""
 
 import os
+import sys
 import re
 
 import numpy as np
@@ -357,6 +358,43 @@ def test_reference_classics_examples_load_and_lower(compat_examples, kind):
   assert tuple(theirs.sprites[0, :5]) == (w.row, w.col, w.vrow, w.vcol, 1)
   np.testing.assert_array_equal(theirs.backdrop[:, :theirs.cols], world.backdrop)
   assert bool(theirs.confined[0]) == w.confined
+
+
+@needs_ref
+def test_reference_aperture_example_loads_and_lowers(compat_examples):
+  from pycolab_b200.games import aperture as ours_mod
+  mod = compat_examples('aperture')
+  for level in (0, 1, 2):
+    theirs = lowering.lower(mod.make_game(level))
+    ours = lowering.lower(ours_mod.make_game(mod.LEVELS[level]))
+    assert theirs.program == _lib.PROG_APERTURE
+    assert list(theirs.drapes[0, [_lib.D_AUX0, _lib.D_AUX1]]) == [-1, -1]
+    _same_lowering(theirs, ours)
+
+
+@needs_ref
+def test_reference_fluvial_natation_loads_and_lowers(compat_examples):
+  """A Backdrop subclass with update() logic is lowered with its own game only."""
+  from pycolab_b200.games import fluvial_natation as ours_mod
+  mod = compat_examples('fluvial_natation')
+  theirs, ours = lowering.lower(mod.make_game()), lowering.lower(ours_mod.make_game())
+  assert theirs.program == _lib.PROG_CLASSICS and theirs.backdrop_role == 'river'
+  assert list(theirs.program_arg[:3]) == [_lib.CLASSIC_FLUVIAL, 1, 4] and theirs.reward_type is int
+  _same_lowering(theirs, ours)
+  # the river under another game's entities is refused, and so is an unknown Backdrop
+  aa = sys.modules['pycolab.ascii_art']
+  four_rooms = compat_examples(os.path.join('classics', 'four_rooms'))
+  with pytest.raises(NotLoweredError):
+    lowering.lower(aa.ascii_art_to_game(four_rooms.GAME_ART, ' ',
+                                        sprites={'P': four_rooms.PlayerSprite},
+                                        backdrop=mod.RiverBackdrop))
+
+  class Odd(mod.RiverBackdrop):
+    def update(self, *args, **kwargs):
+      pass
+  with pytest.raises(NotLoweredError):
+    lowering.lower(aa.ascii_art_to_game(mod.GAME_ART, ' ', sprites={'P': mod.PlayerSprite},
+                                        backdrop=Odd))
 
 
 @needs_ref

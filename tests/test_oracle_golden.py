@@ -205,3 +205,35 @@ def test_classics(name):
   tj.assert_same_trajectory(g, got, name)
   np.testing.assert_array_equal(g['sprites'], np.array(sprites))
   np.testing.assert_array_equal(g['reward_type'], np.array(types, dtype=np.uint8))
+
+
+@pytest.mark.parametrize('name', gc.names('fluvial_'))
+def test_fluvial_natation(name):
+  g = gc.load(name)
+  art = tj.u8_to_art(g['art'])
+  sprites, curtains = [], []
+
+  def on_frame(env, out):
+    _sprite_sink('P', sprites)(env, out)
+    curtains.append(env.backdrop.copy())
+  got = tj.run_trajectory(lambda: games.make_fluvial(art), g['actions'].tolist(),
+                          on_frame=on_frame)
+  tj.assert_same_trajectory(g, got, name)
+  np.testing.assert_array_equal(g['sprites'], np.array(sprites))
+  np.testing.assert_array_equal(g['backdrops'], np.stack(curtains))
+
+
+@pytest.mark.parametrize('name', gc.names('aperture_'))
+def test_aperture(name):
+  g = gc.load(name)
+  art = tj.u8_to_art(g['art'])
+  sprites, curtains = [], []
+
+  def on_frame(env, out):
+    _sprite_sink('A', sprites)(env, out)
+    curtains.append(env.things['X'].curtain.copy())
+  got = tj.run_trajectory(lambda: games.make_aperture(art), g['actions'].tolist(),
+                          on_frame=on_frame)
+  tj.assert_same_trajectory(g, got, name)
+  np.testing.assert_array_equal(g['sprites'], np.array(sprites))
+  np.testing.assert_array_equal(g['curtains'], np.stack(curtains).astype(np.uint8))

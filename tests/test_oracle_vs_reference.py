@@ -235,6 +235,51 @@ def test_classics(kind, art):
   assert episodes >= 1 and any(r is not None for r in rewards)
 
 
+def aperture_actions(seed, n):
+  """Walks, blaster shots in all directions, idle steps and a rare quit."""
+  rs = np.random.RandomState(seed)
+  return rs.choice(list(range(10)), size=n,
+                   p=[.14, .14, .14, .14, .04, .1, .1, .1, .095, .005]).tolist()
+
+
+@pytest.mark.parametrize('level', [0, 1, 2, 'other'])
+def test_aperture_stock(level):
+  if level == 'other':
+    art = levels.aperture_level()
+    make_ref = lambda: refdriver.ref_aperture(art=art)
+    seed = 43
+  else:
+    art = refdriver.ref_aperture_art(level)
+    make_ref = lambda: refdriver.ref_aperture(level)
+    seed = 40 + level
+  drapes = []
+
+  def check(ref, ora):
+    np.testing.assert_array_equal(ref.things['X'].curtain, ora.things['X'].curtain)
+  ref, ora = make_ref(), games.make_aperture(art)
+  r_out, o_out = ref.its_showtime(), ora.its_showtime()
+  shots = 0
+  for t, a in enumerate(aperture_actions(seed, 3000)):
+    _compare(ref, ora, r_out, o_out, t, True)
+    check(ref, ora)
+    shots += int(ora.things['X'].curtain.sum() > 0)
+    if ref.game_over:
+      ref, ora = make_ref(), games.make_aperture(art)
+      r_out, o_out = ref.its_showtime(), ora.its_showtime()
+      continue
+    r_out, o_out = ref.play(a), ora.play(a)
+  assert shots > 100
+
+
+@pytest.mark.parametrize('art', ['stock', 'other'])
+def test_fluvial_natation(art):
+  from pycolab_b200 import levels
+  art = refdriver.ref_fluvial_art() if art == 'stock' else levels.fluvial_level()
+  actions = np.random.RandomState(5).choice([0, 1, 2], size=1500, p=[.2, .6, .2]).tolist()
+  eps = _lockstep(lambda: refdriver.ref_fluvial(art), lambda: games.make_fluvial(art), actions)
+  assert eps > 5
+
+
 @pytest.mark.parametrize('pad,margins', [(' ', (None, None)), (None, (2, 3)),
                                          (' ', (2, 3))])
 def test_scrolling_cropper(pad, margins):
