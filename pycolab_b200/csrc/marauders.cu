@@ -66,6 +66,14 @@ __device__ __forceinline__ bool same_cell(const Sprite& a, const Sprite& b) {
   return a.row == b.row && a.col == b.col;
 }
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::
+               "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
 constexpr int kRecWords = 96;        // 7 sprites * 8 = 56, 2 drapes * 8 = 16, plot 16, pad
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7)
@@ -89,41 +97,50 @@ marauders_step(const StepParams p) {
   uint32_t* g_mara = p.st.d_bits[1] + (int64_t)env * p.st.bits_bstride[1];
   uint32_t* mt = p.st.d_rng + (int64_t)env * PCL_MT_WORDS;
 
-  const int was_over = g_plot[PCL_P_GAME_OVER];
-  bool restart;
-  if (p.mode == MODE_RESET) {
-    restart = (p.env_mask == nullptr) || (p.env_mask[env] != 0);
-    if (!restart) return;
-  } else {
-    restart = was_over && p.auto_reset;
-    if (was_over && !p.auto_reset) return;
+  // The tile does not depend on anything: start it first (cp.async, no registers).
+  extern __shared__ __align__(16) uint8_t s_tiles[];
+  const int tile = H * p.pitch;
+  uint8_t* s_bd = s_tiles + (threadIdx.x >> 5) * tile;
+  {
+    const uint8_t* backdrop = p.st.d_backdrop + lvl * p.st.backdrop_bstride;
+    for (int i = lane; i < (tile >> 4); i += 32) cp_async16(s_bd + i * 16, backdrop + i * 16);
   }
+  // Live state first, unconditionally, in ONE round trip; whether the env restarts
+  // is decided from the staged plot record (no load waits on another load).
   const int BW = p.BW;
   auto load_row = [&](const uint32_t* base) -> u64 {
     if (lane >= H) return 0;
     const uint32_t* row = base + lane * BW;
     return (u64)row[0] | ((u64)row[1] << 32);
   };
-  u64 brow, xrow;                  // lane r holds row r of the B / X curtain
-  int action;
-  {
-    const int32_t* ss = restart ? p.st.d_sprites_init + lvl * p.st.sprites_init_bstride
-                                : g_sprites;
-    const int32_t* sd = restart ? p.st.d_drapes_init + lvl * p.st.drapes_init_bstride
-                                : g_drapes;
-    const int32_t* sq = restart ? p.st.d_plot_init + lvl * p.st.plot_init_bstride
-                                : g_plot;
-    const int episodes = g_plot[PCL_P_EPISODES], error = g_plot[PCL_P_ERROR];
+  rec[lane] = g_sprites[lane];
+  if (lane < 24) rec[32 + lane] = g_sprites[32 + lane];
+  rec[56 + lane] = lane < 16 ? g_drapes[lane] : g_plot[lane - 16];
+  u64 brow = load_row(g_bunk), xrow = load_row(g_mara);   // lane r holds row r of B / X
+  int action = p.mode == MODE_STEP ? p.actions[(int64_t)env * p.actions_per_env] : PCL_ACTION_NONE;
+  __syncwarp();
+  const int was_over = rec[72 + PCL_P_GAME_OVER];
+  bool restart;
+  if (p.mode == MODE_RESET) {
+    restart = (p.env_mask == nullptr) || (p.env_mask[env] != 0);
+    if (!restart) { cp_async_wait_all(); return; }
+  } else {
+    restart = was_over && p.auto_reset;
+    if (was_over && !p.auto_reset) { cp_async_wait_all(); return; }
+  }
+  if (restart) {                               // a fresh Engine: templates over the live state
+    const int episodes = rec[72 + PCL_P_EPISODES], error = rec[72 + PCL_P_ERROR];
+    __syncwarp();
+    const int32_t* ss = p.st.d_sprites_init + lvl * p.st.sprites_init_bstride;
     rec[lane] = ss[lane];
     if (lane < 24) rec[32 + lane] = ss[32 + lane];
-    if (lane < 16) rec[56 + lane] = sd[lane]; else rec[56 + lane] = sq[lane - 16];
-    brow = load_row(restart ? p.st.d_bits_init[0] + lvl * p.st.bits_init_bstride[0]
-                            : g_bunk);
-    xrow = load_row(restart ? p.st.d_bits_init[1] + lvl * p.st.bits_init_bstride[1]
-                            : g_mara);
-    action = restart ? PCL_ACTION_NONE : p.actions[(int64_t)env * p.actions_per_env];
+    rec[56 + lane] = lane < 16 ? (p.st.d_drapes_init + lvl * p.st.drapes_init_bstride)[lane]
+                               : (p.st.d_plot_init + lvl * p.st.plot_init_bstride)[lane - 16];
+    brow = load_row(p.st.d_bits_init[0] + lvl * p.st.bits_init_bstride[0]);
+    xrow = load_row(p.st.d_bits_init[1] + lvl * p.st.bits_init_bstride[1]);
+    action = PCL_ACTION_NONE;
     __syncwarp();
-    if (restart && lane == 0) { rec[72 + PCL_P_EPISODES] = episodes + 1; rec[72 + PCL_P_ERROR] = error; }
+    if (lane == 0) { rec[72 + PCL_P_EPISODES] = episodes + 1; rec[72 + PCL_P_ERROR] = error; }
     __syncwarp();
   }
   Sprite sp[kS];
@@ -287,28 +304,44 @@ marauders_step(const StepParams p) {
   if (lane < 24) g_sprites[32 + lane] = rec[32 + lane];
   if (lane < 16) g_drapes[lane] = rec[56 + lane]; else g_plot[lane - 16] = rec[56 + lane];
 
-  // ---- final render, z-order P B X a b c d y z
-  const uint8_t* backdrop = p.st.d_backdrop + lvl * p.st.backdrop_bstride;
-  uint8_t* board = p.out.d_board + (int64_t)env * H * p.pitch;
-  const int segs_per_row = p.pitch >> 4;
-  const int total = H * segs_per_row;
-  for (int base = 0; base < total; base += 32) {
-    const int seg = base + lane;
-    const bool active = seg < total;
-    const int r = active ? seg / segs_per_row : 0;
-    const int c0 = active ? (seg - r * segs_per_row) << 4 : 0;
-    const u64 b = __shfl_sync(PCL_FULL, brow, r);
-    const u64 x = __shfl_sync(PCL_FULL, xrow, r);
-    if (active) {
-      uint4 px = __ldg(reinterpret_cast<const uint4*>(backdrop + (int64_t)r * p.pitch + c0));
-      paint_bits(px, sprite_bit(sp[0], r, c0), p.sprite_char[0]);
-      paint_bits(px, (unsigned)(b >> c0) & 0xffffu, 'B');
-      paint_bits(px, (unsigned)(x >> c0) & 0xffffu, 'X');
-#pragma unroll
-      for (int i = 1; i < kS; ++i) paint_bits(px, sprite_bit(sp[i], r, c0), p.sprite_char[i]);
-      *reinterpret_cast<uint4*>(board + (int64_t)r * p.pitch + c0) = px;
+  // ---- final render, z-order P B X a b c d y z (engine.py:737-759): P lies under
+  // both drapes, the bolts over them.  P is patched into the staged tile, the
+  // drape bits are composed over it in place, the six bolt cells are patched on
+  // top, and the tile streams out.
+  cp_async_wait_all();
+  __syncwarp();
+  if (lane == 0 && visible(sp[0])) s_bd[sp[0].row * p.pitch + sp[0].col] = p.sprite_char[0];
+  __syncwarp();
+  const int spr = p.pitch >> 4;
+  const int total = H * spr;
+  uint4* tile4 = reinterpret_cast<uint4*>(s_bd);
+  {
+    int r = lane / spr, sg = lane - r * spr;   // this lane's (row, segment) and its stride
+    const int dr = 32 / spr, dsg = 32 - dr * spr;
+    for (int base = 0; base < total; base += 32) {
+      const int seg = base + lane;
+      const bool active = seg < total;
+      const u64 b = __shfl_sync(PCL_FULL, brow, active ? r : 0);
+      const u64 x = __shfl_sync(PCL_FULL, xrow, active ? r : 0);
+      if (active) {
+        uint4 px = tile4[seg];
+        paint_bits(px, (unsigned)(b >> (sg << 4)) & 0xffffu, 'B');
+        paint_bits(px, (unsigned)(x >> (sg << 4)) & 0xffffu, 'X');
+        tile4[seg] = px;
+      }
+      r += dr; sg += dsg;
+      if (sg >= spr) { sg -= spr; ++r; }
     }
   }
+  __syncwarp();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 1; i < kS; ++i)
+      if (visible(sp[i])) s_bd[sp[i].row * p.pitch + sp[i].col] = p.sprite_char[i];
+  }
+  __syncwarp();
+  uint4* dst = reinterpret_cast<uint4*>(p.out.d_board + (int64_t)env * tile);
+  for (int seg = lane; seg < total; seg += 32) dst[seg] = tile4[seg];
 }
 
 }  // namespace
@@ -318,6 +351,7 @@ cudaError_t launch_marauders(const StepParams& p, cudaStream_t s) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(blocks);
   cfg.blockDim = dim3(kWarpsPerBlock * 32);
+  cfg.dynamicSmemBytes = (size_t)p.H * p.pitch * kWarpsPerBlock;   // one staged tile per warp
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

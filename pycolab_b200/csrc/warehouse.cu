@@ -64,8 +64,14 @@ warehouse_step(const StepParams p) {
   if (lane == 0) mbar_init(bar, 1);
   __syncwarp();
   if (lane == 0) tile_load_bulk(s_bd, backdrop, (uint32_t)tile, bar);
-  // ---- records -> smem
-  const int was_over = g_plot[PCL_P_GAME_OVER];
+  // ---- records -> smem: the live state first, unconditionally, in one round
+  // trip; whether the env restarts is decided from the staged plot record.
+  for (int i = lane; i < S * PCL_SPRITE_WORDS; i += 32) rec[i] = g_sprites[i];
+  if (lane < PCL_DRAPE_WORDS) r_judge[lane] = g_drapes[lane];
+  if (lane >= 16) r_plot[lane - 16] = g_plot[lane - 16];
+  int action = p.mode == MODE_STEP ? p.actions[(int64_t)env * p.actions_per_env] : PCL_ACTION_NONE;
+  __syncwarp();
+  const int was_over = r_plot[PCL_P_GAME_OVER];
   bool restart;
   if (p.mode == MODE_RESET) {
     restart = (p.env_mask == nullptr) || (p.env_mask[env] != 0);
@@ -74,21 +80,19 @@ warehouse_step(const StepParams p) {
     restart = was_over && p.auto_reset;
     if (was_over && !p.auto_reset) { mbar_wait(bar, 0); return; }
   }
-  {
-    const int32_t* ss = restart ? p.st.d_sprites_init + lvl * p.st.sprites_init_bstride
-                                : g_sprites;
-    const int32_t* sd = restart ? p.st.d_drapes_init + lvl * p.st.drapes_init_bstride
-                                : g_drapes;
-    const int32_t* sp = restart ? p.st.d_plot_init + lvl * p.st.plot_init_bstride
-                                : g_plot;
-    const int episodes = g_plot[PCL_P_EPISODES], error = g_plot[PCL_P_ERROR];
+  if (restart) {                               // a fresh Engine: templates over the live state
+    const int episodes = r_plot[PCL_P_EPISODES], error = r_plot[PCL_P_ERROR];
+    __syncwarp();
+    const int32_t* ss = p.st.d_sprites_init + lvl * p.st.sprites_init_bstride;
+    const int32_t* sd = p.st.d_drapes_init + lvl * p.st.drapes_init_bstride;
+    const int32_t* sp = p.st.d_plot_init + lvl * p.st.plot_init_bstride;
     for (int i = lane; i < S * PCL_SPRITE_WORDS; i += 32) rec[i] = ss[i];
     if (lane < PCL_DRAPE_WORDS) r_judge[lane] = sd[lane];
     if (lane >= 16) r_plot[lane - 16] = sp[lane - 16];
+    action = PCL_ACTION_NONE;
     __syncwarp();
-    if (restart && lane == 0) { r_plot[PCL_P_EPISODES] = episodes + 1; r_plot[PCL_P_ERROR] = error; }
+    if (lane == 0) { r_plot[PCL_P_EPISODES] = episodes + 1; r_plot[PCL_P_ERROR] = error; }
   }
-  const int action = restart ? PCL_ACTION_NONE : p.actions[(int64_t)env * p.actions_per_env];
   mbar_wait(bar, 0);
   __syncwarp();
 
