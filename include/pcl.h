@@ -233,6 +233,7 @@ int pcl_export_curtain(pcl_handle* h, int drape_index, uint8_t* d_out, void* str
  * ScrollingCropper.set_engine does for a new Engine (cropping.py:375-391).
  * d_crop_state == NULL selects a single built-in cropper slot in the plot record.
  * sprite_index < 0 is a FixedCropper at (offset_rows, offset_cols). */
+#define PCL_MAX_TRACK 4
 typedef struct pcl_crop_spec {
   int32_t rows, cols;          /* window shape */
   int32_t sprite_index;        /* entity to track (a sprite) */
@@ -240,9 +241,22 @@ typedef struct pcl_crop_spec {
   int32_t margin_rows, margin_cols; /* resolved scroll margins (cropping.py:362-373) */
   int32_t offset_rows, offset_cols; /* initial_offset */
   int32_t saccade;
+  int32_t track[PCL_MAX_TRACK];     /* optional priority list (pcl_crop_tracking): k > 0 = sprite
+                                       k - 1, k < 0 = drape -k - 1, 0 = end; all 0 = [sprite_index] */
 } pcl_crop_spec;
 int pcl_crop(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d_board,
              uint8_t* d_crop, int32_t* d_crop_state, void* stream);
+
+/* pcl_crop for a ScrollingCropper whose `to_track` names several entities
+ * (cropping.py:544-598): the window follows the FIRST entry of crop->track that is
+ * visible — a sprite that is visible, or a drape whose curtain has any cell, in
+ * which case the position is (median row, median column) of its cells, truncated.
+ * d_curtains[i] is the curtain of the drape named by track[i] as u8 [B, rows, pitch]
+ * (what pcl_export_curtain writes); entries for sprites are ignored and may be
+ * NULL.  Boards up to 128 x 128 when a drape is tracked. */
+int pcl_crop_tracking(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d_board,
+                      uint8_t* d_crop, int32_t* d_crop_state,
+                      const uint8_t* const* d_curtains, void* stream);
 
 /* Observation post-processors as one table look-up per cell
  * (rendering.py:304-661): out[b, d, r, c] = table[board[b, r, c]][d].

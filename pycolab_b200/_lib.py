@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libpcl.so')
 ABI_VERSION = 1
 MAX_SPRITES = 16
 MAX_DRAPES = 8
+MAX_TRACK = 4                # entities one ScrollingCropper can follow (pcl_crop_spec.track)
 SPRITE_WORDS = 8
 DRAPE_WORDS = 8
 PLOT_WORDS = 16
@@ -106,7 +107,8 @@ class CropSpec(C.Structure):
   _fields_ = [('rows', C.c_int32), ('cols', C.c_int32), ('sprite_index', C.c_int32),
               ('pad_char', C.c_int32), ('margin_rows', C.c_int32),
               ('margin_cols', C.c_int32), ('offset_rows', C.c_int32),
-              ('offset_cols', C.c_int32), ('saccade', C.c_int32)]
+              ('offset_cols', C.c_int32), ('saccade', C.c_int32),
+              ('track', C.c_int32 * 4)]      # MAX_TRACK priority list, 0-terminated
 
 
 class ObserveSpec(C.Structure):
@@ -132,6 +134,8 @@ SYMBOLS = {
     'pcl_export_curtain': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     'pcl_crop': (C.c_int, [C.c_void_p, C.POINTER(CropSpec), C.c_void_p, C.c_void_p,
                            C.c_void_p, C.c_void_p]),
+    'pcl_crop_tracking': (C.c_int, [C.c_void_p, C.POINTER(CropSpec), C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]),
     'pcl_observe': (C.c_int, [C.c_void_p, C.POINTER(ObserveSpec), C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'pcl_error_codes': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -260,8 +260,11 @@ class BatchedEngine(object):
   # ------------------------------------------------------------- accessors
   def curtain(self, char):
     """Drape.curtain of every env as bool [B, rows, cols] (things.py:213-217)."""
+    return self._curtain_bytes(self.drape_chars.index(char))[:, :, :self.cols].bool()
+
+  def _curtain_bytes(self, d):
+    """Curtain of drape `d` as u8 [B, rows, pitch] (the pcl_export_curtain layout)."""
     torch = _torch()
-    d = self.drape_chars.index(char)
     out = torch.empty((self.batch, self.rows, self.pitch), dtype=torch.uint8,
                       device=self.device)
     if self.game.program == _lib.PROG_WAREHOUSE:
@@ -282,7 +285,7 @@ class BatchedEngine(object):
     else:
       _lib.check(self._lib.pcl_export_curtain(self._h, d, out.data_ptr(), self._stream()),
                  'pcl_export_curtain')
-    return out[:, :, :self.cols].bool()
+    return out
 
   def error_codes(self):
     torch = _torch()
@@ -311,10 +314,21 @@ class BatchedEngine(object):
       if self._crop_out is None or tuple(self._crop_out.shape) != shape:
         self._crop_out = torch.empty(shape, dtype=torch.uint8, device=self.device)
       out = self._crop_out
-    _lib.check(self._lib.pcl_crop(self._h, C.byref(crop_spec), self._board.data_ptr(),
-                                  out.data_ptr(),
-                                  None if state is None else state.data_ptr(),
-                                  self._stream()), 'pcl_crop')
+    state_ptr = None if state is None else state.data_ptr()
+    if any(code < 0 for code in crop_spec.track):
+      # A tracked drape's position is the median of its curtain cells: hand the
+      # kernel the byte curtains (cropping.py:583-596).
+      curtains, ptrs = [], (C.c_void_p * _lib.MAX_TRACK)()
+      for i, code in enumerate(crop_spec.track):
+        if code < 0:
+          curtains.append(self._curtain_bytes(-code - 1))
+          ptrs[i] = curtains[-1].data_ptr()
+      _lib.check(self._lib.pcl_crop_tracking(self._h, C.byref(crop_spec),
+                                             self._board.data_ptr(), out.data_ptr(), state_ptr,
+                                             ptrs, self._stream()), 'pcl_crop_tracking')
+    else:
+      _lib.check(self._lib.pcl_crop(self._h, C.byref(crop_spec), self._board.data_ptr(),
+                                    out.data_ptr(), state_ptr, self._stream()), 'pcl_crop')
     return out
 
   # --- observation post-processors (rendering.py:304-661) over the whole batch
@@ -371,8 +385,10 @@ class BatchedEngine(object):
 
 
 def scrolling_crop_spec(rows, cols, sprite_index, pad_char=None, scroll_margins=(2, 3),
-                        initial_offset=None, saccade=True):
-  """Resolve ScrollingCropper constructor arguments (cropping.py:313-392)."""
+                        initial_offset=None, saccade=True, track=None):
+  """Resolve ScrollingCropper constructor arguments (cropping.py:313-392).
+  `track`: optional priority list replacing `sprite_index` — entries k > 0 mean
+  sprite k - 1, k < 0 drape -k - 1 (`to_track` with several entities)."""
   if ((scroll_margins[0] is None and rows % 2 == 0) or
       (scroll_margins[1] is None and cols % 2 == 0)):
     raise ValueError("A ScrollingCropper can't perform perfectly-egocentric scrolling "
@@ -384,5 +400,12 @@ def scrolling_crop_spec(rows, cols, sprite_index, pad_char=None, scroll_margins=
     raise ValueError("A ScrollingCropper can't use scroll margins which extend to or "
                      'beyond the very centre of the scrolling window.')
   off = initial_offset if initial_offset is not None else (0, 0)
-  return _lib.CropSpec(rows, cols, sprite_index, -1 if pad_char is None else ord(pad_char),
+  spec = _lib.CropSpec(rows, cols, sprite_index, -1 if pad_char is None else ord(pad_char),
                        m0, m1, off[0], off[1], 1 if saccade else 0)
+  if track is not None:
+    if not 0 < len(track) <= _lib.MAX_TRACK or any(code == 0 for code in track):
+      raise ValueError('a device cropper tracks 1..{} entities'.format(_lib.MAX_TRACK))
+    for i, code in enumerate(track):
+      spec.track[i] = int(code)
+    spec.sprite_index = max(0, spec.track[0] - 1)
+  return spec

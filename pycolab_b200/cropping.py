@@ -117,17 +117,21 @@ class ScrollingCropper(ObservationCropper):
 
   def crop(self, observation):
     from pycolab_b200 import batched
-    if len(self._to_track) != 1:
-      raise NotLoweredError('the device cropper tracks exactly one sprite')
-    char = self._to_track[0]
-    if char not in self._engine.things:
-      raise RuntimeError('ScrollingCropper was told to track a nonexistent game entity '
-                         '{!r}.'.format(char))
+    from pycolab_b200 import _lib
     b = self._engine.batched
-    if b is None or char not in b.sprite_chars:
-      raise NotLoweredError('the device cropper tracks sprites only')
-    spec = batched.scrolling_crop_spec(self._rows, self._cols,
-                                       b.sprite_chars.index(char), **self._spec_args)
+    if b is None:
+      raise RuntimeError('crop() called before the Engine entered play mode')
+    if not 0 < len(self._to_track) <= _lib.MAX_TRACK:
+      raise NotLoweredError('the device cropper tracks 1..{} entities'.format(_lib.MAX_TRACK))
+    codes = []                     # priority list: k > 0 sprite k - 1, k < 0 drape -k - 1
+    for char in self._to_track:
+      if char not in self._engine.things:
+        raise RuntimeError('ScrollingCropper was told to track a nonexistent game entity '
+                           '{!r}.'.format(char))
+      codes.append(b.sprite_chars.index(char) + 1 if char in b.sprite_chars
+                   else -(b.drape_chars.index(char) + 1))
+    spec = batched.scrolling_crop_spec(self._rows, self._cols, 0, track=codes,
+                                       **self._spec_args)
     return self._device_crop(spec)
 
   @property

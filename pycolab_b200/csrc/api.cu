@@ -426,6 +426,12 @@ int pcl_export_curtain(pcl_handle* h, int drape_index, uint8_t* d_out, void* str
 
 int pcl_crop(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d_board, uint8_t* d_crop,
              int32_t* d_crop_state, void* stream) {
+  return pcl_crop_tracking(h, crop, d_board, d_crop, d_crop_state, nullptr, stream);
+}
+
+int pcl_crop_tracking(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d_board,
+                      uint8_t* d_crop, int32_t* d_crop_state,
+                      const uint8_t* const* d_curtains, void* stream) {
   if (!h || !crop || !d_board || !d_crop) return PCL_ERR_INVALID;
   if (!h->bound) return PCL_ERR_UNBOUND;
   if (crop->rows <= 0 || crop->cols <= 0 || crop->sprite_index >= h->spec.n_sprites)
@@ -441,6 +447,18 @@ int pcl_crop(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d_board, u
   p.S = h->spec.n_sprites; p.crop = *crop;
   p.sprites = h->st.d_sprites; p.plot = h->st.d_plot; p.board = d_board; p.out = d_crop;
   p.state = d_crop_state;
+  for (int i = 0; i < PCL_MAX_TRACK; ++i) {
+    const int code = crop->track[i];
+    if (code == 0) break;
+    if (crop->sprite_index < 0) return PCL_ERR_INVALID;      // a FixedCropper tracks nothing
+    if (code > 0) {
+      if (code - 1 >= h->spec.n_sprites) return PCL_ERR_INVALID;
+    } else {
+      if (-code - 1 >= h->spec.n_drapes || !d_curtains || !d_curtains[i]) return PCL_ERR_INVALID;
+      if (h->spec.rows > 128 || h->spec.cols > 128) return PCL_ERR_UNSUPPORTED;
+      p.curtains[i] = d_curtains[i];
+    }
+  }
   h->launches += 1;
   return pcl::launch_crop(p, (cudaStream_t)stream) == cudaSuccess ? PCL_OK : PCL_ERR_CUDA;
 }

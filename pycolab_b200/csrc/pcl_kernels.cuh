@@ -84,6 +84,7 @@ struct CropParams {
   int32_t* state;                // i32 [B, 4] per-cropper corner state, or NULL
   const uint8_t* board;
   uint8_t* out;
+  const uint8_t* curtains[PCL_MAX_TRACK];   // byte curtains of tracked drapes (or NULL)
 };
 cudaError_t launch_crop(const CropParams& p, cudaStream_t s);
 

@@ -143,17 +143,68 @@ __global__ void export_curtain_kernel(const ExportParams p) {
   }
 }
 
-// ScrollingCropper.crop (cropping.py:393-426) for one tracked sprite.
+// (median row, median column) of a byte curtain's cells, as `_centroid` computes
+// them for a Drape (cropping.py:583-596: np.median of the nonzero coordinates,
+// truncated).  Warp-wide; `hist` is this warp's 256-int scratch.  false = empty.
+__device__ bool curtain_centroid(const uint8_t* curtain, int H, int W, int pitch, int lane,
+                                 int* hist, int* crow, int* ccol) {
+  int* rows = hist;
+  int* cols = hist + 128;
+  int n = 0;
+  for (int c = lane; c < 128; c += 32) cols[c] = 0;
+  __syncwarp();
+  for (int r = 0; r < H; ++r) {
+    int in_row = 0;
+    for (int c0 = 0; c0 < W; c0 += 32) {
+      const int c = c0 + lane;
+      const bool on = c < W && curtain[(int64_t)r * pitch + c] != 0;
+      in_row += __popc(__ballot_sync(0xffffffffu, on));
+      if (on) cols[c] += 1;                  // lane `c & 31` owns column c
+    }
+    if (lane == 0) rows[r] = in_row;
+    n += in_row;
+  }
+  __syncwarp();
+  if (n == 0) return false;
+  // k-th smallest coordinate from the histograms; the median of an even count is
+  // the mean of the two middle values, truncated (int(np.median(...))).
+  auto kth = [&](const int* h, int len, int k) {
+    int seen = 0;
+    for (int i = 0; i < len; ++i) { seen += h[i]; if (seen > k) return i; }
+    return len - 1;
+  };
+  const int k1 = (n - 1) / 2, k2 = n / 2;
+  *crow = (kth(rows, H, k1) + kth(rows, H, k2)) / 2;
+  *ccol = (kth(cols, W, k1) + kth(cols, W, k2)) / 2;
+  return true;
+}
+
+// ScrollingCropper.crop (cropping.py:393-426): follow the first visible entity of
+// the tracking list.
 __global__ void __launch_bounds__(128) crop_kernel(const CropParams p) {
+  __shared__ int s_hist[4][256];
   const int lane = threadIdx.x & 31;
   const int env = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (env >= p.B) return;
   const pcl_crop_spec& c = p.crop;
   int32_t* plot = p.plot + (int64_t)env * PCL_PLOT_WORDS;
   const bool fixed = c.sprite_index < 0;                  // FixedCropper :229-310
-  const int32_t* rec = p.sprites + ((int64_t)env * p.S + (fixed ? 0 : c.sprite_index)) * PCL_SPRITE_WORDS;
-  const bool have = !fixed && (rec[PCL_S_FLAGS] & 1);     // _centroid :544-598
-  const int crow = fixed ? 0 : rec[PCL_S_ROW], ccol = fixed ? 0 : rec[PCL_S_COL];
+  bool have = false;                                      // _centroid :544-598
+  int crow = 0, ccol = 0;
+  if (!fixed) {
+#pragma unroll
+    for (int e = 0; e < PCL_MAX_TRACK && !have; ++e) {
+      const int code = c.track[0] == 0 ? (e == 0 ? c.sprite_index + 1 : 0) : c.track[e];
+      if (code == 0) break;
+      if (code > 0) {
+        const int32_t* rec = p.sprites + ((int64_t)env * p.S + code - 1) * PCL_SPRITE_WORDS;
+        if (rec[PCL_S_FLAGS] & 1) { have = true; crow = rec[PCL_S_ROW]; ccol = rec[PCL_S_COL]; }
+      } else {
+        have = curtain_centroid(p.curtains[e] + (int64_t)env * p.H * p.pitch, p.H, p.W, p.pitch,
+                                lane, s_hist[threadIdx.x >> 5], &crow, &ccol);
+      }
+    }
+  }
   // Corner state: the caller's per-cropper array, or the plot record's one slot.
   int32_t* state = p.state ? p.state + (int64_t)env * 4 : plot + PCL_P_CROP_R;
   const int episode = plot[PCL_P_EPISODES];
