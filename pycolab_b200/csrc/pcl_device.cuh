@@ -53,33 +53,6 @@ __device__ __forceinline__ void terminate(Directives& d) {          // plot.py:1
   d.game_over = 1; d.discount = 0.0f;
 }
 
-template <typename T>
-__device__ __forceinline__ T load_record(const int32_t* p) {
-  static_assert(sizeof(T) % 16 == 0, "records are int4 multiples");
-  T out;
-  const int4* src = reinterpret_cast<const int4*>(p);
-  int4* dst = reinterpret_cast<int4*>(&out);
-#pragma unroll
-  for (int i = 0; i < (int)(sizeof(T) / 16); ++i) dst[i] = __ldg(src + i);
-  return out;
-}
-template <typename T>
-__device__ __forceinline__ T load_record_rw(const int32_t* p) {
-  T out;
-  const int4* src = reinterpret_cast<const int4*>(p);
-  int4* dst = reinterpret_cast<int4*>(&out);
-#pragma unroll
-  for (int i = 0; i < (int)(sizeof(T) / 16); ++i) dst[i] = src[i];
-  return out;
-}
-template <typename T>
-__device__ __forceinline__ void store_record(int32_t* p, const T& v) {
-  int4* dst = reinterpret_cast<int4*>(p);
-  const int4* src = reinterpret_cast<const int4*>(&v);
-#pragma unroll
-  for (int i = 0; i < (int)(sizeof(T) / 16); ++i) dst[i] = src[i];
-}
-
 // ------------------------------------------------------------- MazeWalker --
 
 __device__ __forceinline__ bool visible(const Sprite& s) { return s.flags & 1; }
@@ -104,9 +77,6 @@ __device__ __forceinline__ void walker_teleport(Sprite& s, int H, int W, int vr,
     s.flags = (s.flags & ~1) | (prior == 2 ? 1 : 0);
   }
 }
-
-__constant__ int kMotionDr[9] = {-1, -1, 0, 1, 1, 1, 0, -1, 0};
-__constant__ int kMotionDc[9] = {0, 1, 1, 1, 0, -1, -1, -1, 0};
 
 // (drow, dcol) of a motion code, two bits per code packed in a constant:
 // N NE E SE S SW W NW STAY -> drow+1 = 0 0 1 2 2 2 1 0 1, dcol+1 = 1 2 2 2 1 0 0 0 1.

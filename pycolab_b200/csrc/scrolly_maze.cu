@@ -18,15 +18,18 @@
 //      final window corners (the '@' drape can only obey an order, never issue
 //      one: by the time it runs, the player's permit is already for frame+1);
 //   3. one batch of loads is issued for everything else the step will read:
-//        - cp.async: the backdrop tile and the two 64-row windows of the
-//          bit-packed patterns (3 words per row) -> smem, no registers held;
+//        - cp.async: the backdrop tile (issued before anything else) and the
+//          two windows of the bit-packed patterns (4 words per row, two 8-byte
+//          copies) -> smem, no registers held;
 //        - plain loads: a 5x5 patch of wall bits around each of the 4 walkers
 //          (covers every cell any _check_motion of this step can consult,
 //          wherever the scroll order moves the walker first) and the 3x3 patch
 //          of coin bits around the player, one cell per lane, 4 per lane;
 //   4. groups 1 and 2 run on registers + ballots of those bits;
-//   5. the paint loop composes 16-byte board segments from smem and streams
-//      them out with uint4 stores; records go back with two coalesced stores.
+//   5. each lane shifts whole window rows once into one word per 16-cell board
+//      segment (wall16 << 16 | coin16); the paint loop then composes 16-byte
+//      segments from smem (prmt with a 256-entry selector table) and streams them
+//      out with uint4 stores; records go back with two coalesced stores.
 // So a step costs ~two dependent DRAM round trips (records, then everything).
 //
 // Sprite order P,a,b,c (indices 0..3); drape order '#','@' (0, 1).
