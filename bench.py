@@ -407,11 +407,27 @@ def main():
     from pycolab_b200 import dist as pdist
     spec = batched.scrolling_crop_spec(9, 9, 0, pad_char=' ', scroll_margins=(None, None))
     states = [e.new_crop_state() for e in engines]
+    crops = [torch.empty((B, 9, 9), dtype=torch.uint8, device=dev) for _ in engines]
+    # Preferred transport: the pack kernel stores every record into all ranks'
+    # gather buffers over NVLink (symmetric memory, no collective call); if this
+    # torch build / box cannot map peer memory, pack + ONE NCCL all-gather.
+    try:
+      handoffs = [pdist.PeerHandoff(e, (9, 9), world * B) for e in engines]
+      handoff_transport = 'p2p stores into symmetric memory (fused into the pack kernel) + 1 barrier'
+    except Exception as err:      # noqa: BLE001 - any failure to set peer mapping up
+      handoffs = [pdist.Handoff(e, (9, 9), world * B) for e in engines]
+      handoff_transport = 'pack kernel + 1 NCCL all-gather (symmetric memory unavailable: %s)' % (
+          str(err).splitlines()[0][:80] if str(err) else type(err).__name__)
+    agree = torch.tensor([0 if handoff_transport.startswith('p2p') else 1], device=dev)
+    dist.all_reduce(agree, op=dist.ReduceOp.MAX)
+    if int(agree.item()) and handoff_transport.startswith('p2p'):   # some rank fell back: all do
+      handoffs = [pdist.Handoff(e, (9, 9), world * B) for e in engines]
+      handoff_transport = 'pack kernel + 1 NCCL all-gather (a peer could not map symmetric memory)'
     def step_and_gather(t):
       e = engines[t % R]
-      res = e.play(actions[W + (t % K)])
-      crop = e.crop(spec, state=states[t % R])
-      return pdist.allgather_outputs([crop, res.reward, res.discount, res.done], world * B)
+      e.play(actions[W + (t % K)])
+      crop = e.crop(spec, state=states[t % R], out=crops[t % R])
+      return handoffs[t % R].gather(crop)
     for t in range(2 * R):
       step_and_gather(t)
     barrier()
@@ -513,8 +529,8 @@ def main():
                                 one_launch_over_all_batches=render_big_roofline(
                                     render_big, eng, peak)),
         'handoff_allgather': None if handoff_ms is None else {
-            'what': 'step + 9x9 crop + NCCL all-gather of (crop, reward, discount, done) '
-                    'to every rank', 'ms_per_step': handoff_ms,
+            'what': 'step + 9x9 crop + hand-off of the packed (crop, reward, discount, done) '
+                    'records to every rank', 'transport': handoff_transport, 'ms_per_step': handoff_ms,
             'value': world * B / (handoff_ms / 1000.0), 'unit': 'env-steps/s'},
         'wall_s_timed_region': wall, 'env_errors': errors}) + "\n")
     real_stdout.flush()

@@ -276,6 +276,29 @@ int pcl_observe(pcl_handle* h, const pcl_observe_spec* spec, const void* d_table
                 const uint8_t* d_valid, const uint8_t* d_board, void* d_out,
                 int32_t* d_unknown, void* stream);
 
+/* Multi-GPU hand-off record: everything one env contributes to the
+ * per-step all-gather, packed so that ONE collective moves it all.
+ *   d_packed u8 [B, record_bytes]; one record = view_bytes of the env's observation
+ *   view (e.g. its 9x9 crop, row-major; d_view is u8 [B, view_bytes]), zero padding
+ *   to a multiple of 4, then reward i32, discount f32, done u8, has_reward u8 and
+ *   2 padding bytes; record_bytes = PCL_HANDOFF_RECORD_BYTES(view_bytes). */
+#define PCL_HANDOFF_RECORD_BYTES(view_bytes) ((((view_bytes) + 3) & ~3) + 12)
+int pcl_pack_handoff(pcl_handle* h, const uint8_t* d_view, int32_t view_bytes,
+                     const pcl_outputs* out, uint8_t* d_packed, void* stream);
+
+/* pcl_pack_handoff with the all-gather fused into the producing kernel: every
+ * record is stored straight into the gather buffer of EVERY rank over NVLink
+ * (peer-to-peer stores), so no collective library call sits between the step and
+ * its consumers.  d_peer_bases (a HOST array of n_peers <= PCL_MAX_PEERS peer-mapped
+ * device pointers, e.g. torch symmetric memory) are the bases of the ranks' gather
+ * buffers u8 [rows, record_bytes]; this handle's env e lands in row first_row + e
+ * of each.  The caller orders steps with a cross-GPU barrier (the records are
+ * complete on every peer once this kernel has finished on every rank). */
+#define PCL_MAX_PEERS 8
+int pcl_pack_handoff_peers(pcl_handle* h, const uint8_t* d_view, int32_t view_bytes,
+                           const pcl_outputs* out, uint8_t* const* d_peer_bases,
+                           int32_t n_peers, int64_t first_row, void* stream);
+
 /* Copy the per-env latched error words (PCL_ENV_ERR_*) to d_out i32 [B]. */
 int pcl_error_codes(pcl_handle* h, int32_t* d_out, void* stream);
 

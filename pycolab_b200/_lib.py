@@ -136,6 +136,11 @@ SYMBOLS = {
                            C.c_void_p, C.c_void_p]),
     'pcl_crop_tracking': (C.c_int, [C.c_void_p, C.POINTER(CropSpec), C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]),
+    'pcl_pack_handoff': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(Outputs),
+                                   C.c_void_p, C.c_void_p]),
+    'pcl_pack_handoff_peers': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(Outputs),
+                                         C.POINTER(C.c_void_p), C.c_int32, C.c_int64,
+                                         C.c_void_p]),
     'pcl_observe': (C.c_int, [C.c_void_p, C.POINTER(ObserveSpec), C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'pcl_error_codes': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

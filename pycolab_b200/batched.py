@@ -331,6 +331,30 @@ class BatchedEngine(object):
                                     out.data_ptr(), state_ptr, self._stream()), 'pcl_crop')
     return out
 
+  def pack_handoff(self, view, packed):
+    """Pack `view` (u8 [B, ...], contiguous) with this step's reward / discount /
+    done into `packed` u8 [>= B, PCL_HANDOFF_RECORD_BYTES] (dist.Handoff)."""
+    torch = _torch()
+    view_bytes = int(view[0].numel())
+    assert view.dtype == torch.uint8 and view.is_contiguous() and view.shape[0] == self.batch
+    assert packed.is_contiguous() and packed.shape[0] >= self.batch
+    assert packed.shape[1] == ((view_bytes + 3) & ~3) + 12
+    _lib.check(self._lib.pcl_pack_handoff(self._h, view.data_ptr(), view_bytes,
+                                          C.byref(self._out), packed.data_ptr(),
+                                          self._stream()), 'pcl_pack_handoff')
+    return packed
+
+  def pack_handoff_peers(self, view, peer_ptrs, first_row):
+    """`pack_handoff` with the all-gather fused in: records go straight into row
+    `first_row + env` of every rank's gather buffer (`peer_ptrs`: peer-mapped
+    device pointers) over NVLink (dist.PeerHandoff)."""
+    torch = _torch()
+    assert view.dtype == torch.uint8 and view.is_contiguous() and view.shape[0] == self.batch
+    ptrs = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+    _lib.check(self._lib.pcl_pack_handoff_peers(
+        self._h, view.data_ptr(), int(view[0].numel()), C.byref(self._out), ptrs,
+        len(peer_ptrs), int(first_row), self._stream()), 'pcl_pack_handoff_peers')
+
   # --- observation post-processors (rendering.py:304-661) over the whole batch
   def to_feature_array(self, layers, permute=None):
     """ObservationToFeatureArray: float32 one-hot planes, [B, C, rows, cols] (or

@@ -463,6 +463,42 @@ int pcl_crop_tracking(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d
   return pcl::launch_crop(p, (cudaStream_t)stream) == cudaSuccess ? PCL_OK : PCL_ERR_CUDA;
 }
 
+int pcl_pack_handoff(pcl_handle* h, const uint8_t* d_view, int32_t view_bytes,
+                     const pcl_outputs* out, uint8_t* d_packed, void* stream) {
+  if (!h || !d_view || !out || !d_packed || view_bytes <= 0) return PCL_ERR_INVALID;
+  if (!out->d_reward || !out->d_has_reward || !out->d_discount || !out->d_done)
+    return PCL_ERR_INVALID;
+  pcl::PackParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = h->batch; p.view_bytes = view_bytes;
+  p.record_bytes = PCL_HANDOFF_RECORD_BYTES(view_bytes);
+  p.view = d_view; p.out = *out; p.packed = d_packed;
+  h->launches += 1;
+  return pcl::launch_pack_handoff(p, (cudaStream_t)stream) == cudaSuccess ? PCL_OK : PCL_ERR_CUDA;
+}
+
+int pcl_pack_handoff_peers(pcl_handle* h, const uint8_t* d_view, int32_t view_bytes,
+                           const pcl_outputs* out, uint8_t* const* d_peer_bases,
+                           int32_t n_peers, int64_t first_row, void* stream) {
+  if (!h || !d_view || !out || !d_peer_bases || view_bytes <= 0 || first_row < 0)
+    return PCL_ERR_INVALID;
+  if (n_peers < 1 || n_peers > PCL_MAX_PEERS) return PCL_ERR_INVALID;
+  if (!out->d_reward || !out->d_has_reward || !out->d_discount || !out->d_done)
+    return PCL_ERR_INVALID;
+  pcl::PackParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = h->batch; p.view_bytes = view_bytes;
+  p.record_bytes = PCL_HANDOFF_RECORD_BYTES(view_bytes);
+  p.view = d_view; p.out = *out;
+  p.n_peers = n_peers; p.first_row = first_row;
+  for (int i = 0; i < n_peers; ++i) {
+    if (!d_peer_bases[i]) return PCL_ERR_INVALID;
+    p.peers[i] = d_peer_bases[i];
+  }
+  h->launches += 1;
+  return pcl::launch_pack_handoff(p, (cudaStream_t)stream) == cudaSuccess ? PCL_OK : PCL_ERR_CUDA;
+}
+
 int pcl_observe(pcl_handle* h, const pcl_observe_spec* spec, const void* d_table,
                 const uint8_t* d_valid, const uint8_t* d_board, void* d_out,
                 int32_t* d_unknown, void* stream) {

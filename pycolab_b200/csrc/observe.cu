@@ -74,4 +74,49 @@ cudaError_t launch_observe(const ObserveParams& p, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+namespace {
+
+// One warp per env: the view bytes stream across the lanes, lane 0 appends the
+// step outputs (include/pcl.h: PCL_HANDOFF_RECORD_BYTES).
+__global__ void __launch_bounds__(128) pack_handoff_kernel(const PackParams p) {
+  const int lane = threadIdx.x & 31;
+  const int env = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (env >= p.B) return;
+  const uint8_t* src = p.view + (int64_t)env * p.view_bytes;
+  const int padded = (p.view_bytes + 3) & ~3;
+  // The record as 32-bit words, one per lane per round: view bytes, then
+  // reward, discount, done | has_reward << 8.
+  const int words = (padded >> 2) + 3;
+  const int n_dst = p.n_peers > 0 ? p.n_peers : 1;
+  for (int w = lane; w < words; w += 32) {
+    uint32_t v;
+    const int b = w << 2;
+    if (b < padded) {
+      v = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (b + k < p.view_bytes) v |= (uint32_t)src[b + k] << (8 * k);
+    } else if (b == padded) {
+      v = (uint32_t)p.out.d_reward[env];
+    } else if (b == padded + 4) {
+      v = __float_as_uint(p.out.d_discount[env]);
+    } else {
+      v = (uint32_t)p.out.d_done[env] | ((uint32_t)p.out.d_has_reward[env] << 8);
+    }
+    // Local buffer, or the same row of every rank's gather buffer over NVLink.
+    for (int d = 0; d < n_dst; ++d) {
+      uint8_t* base = p.n_peers > 0 ? p.peers[d] + (p.first_row + env) * p.record_bytes
+                                    : p.packed + (int64_t)env * p.record_bytes;
+      reinterpret_cast<uint32_t*>(base)[w] = v;
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_pack_handoff(const PackParams& p, cudaStream_t s) {
+  pack_handoff_kernel<<<(p.B + 3) / 4, 128, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
 }  // namespace pcl

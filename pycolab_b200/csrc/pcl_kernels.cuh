@@ -88,4 +88,15 @@ struct CropParams {
 };
 cudaError_t launch_crop(const CropParams& p, cudaStream_t s);
 
+struct PackParams {
+  int B, view_bytes, record_bytes;
+  const uint8_t* view;           // u8 [B, view_bytes]
+  pcl_outputs out;
+  uint8_t* packed;               // u8 [B, record_bytes] (n_peers == 0)
+  int n_peers;                   // > 0: store into every peer's gather buffer instead
+  int64_t first_row;
+  uint8_t* peers[PCL_MAX_PEERS];
+};
+cudaError_t launch_pack_handoff(const PackParams& p, cudaStream_t s);
+
 }  // namespace pcl

@@ -5,9 +5,14 @@ engine.py:216), so the step path shards with NO data-path collective: rank r
 owns the contiguous block of env indices `shard_range(global_batch, r, world)`
 together with their action stream and RNG states (seeded by GLOBAL env index,
 so a sharded run reproduces the single-GPU run env for env).  The only
-exchange is the optional hand-off of the per-step outputs to every rank
-(`allgather_outputs`, one NCCL all-gather per tensor over NVLink/NVSwitch).
+exchange is the optional hand-off of the per-step outputs to every rank:
+`Handoff` packs each env's observation view + reward + discount + done into one
+record on the device (`pcl_pack_handoff`) and moves everything with ONE NCCL
+all-gather per step over NVLink/NVSwitch; `allgather_outputs` is the plain
+one-collective-per-tensor form.
 """
+
+import numpy as np
 
 
 def shard_range(global_batch, rank, world):
@@ -57,3 +62,105 @@ def allgather_outputs(tensors, global_batch, group=None):
       pieces = [gathered[r * biggest: r * biggest + counts[r]] for r in range(world)]
       out.append(torch.cat(pieces))
   return out
+
+
+def handoff_record_bytes(view_bytes):
+  """include/pcl.h: PCL_HANDOFF_RECORD_BYTES."""
+  return ((view_bytes + 3) & ~3) + 12
+
+
+def unpack_handoff(records, view_shape):
+  """Views into packed hand-off records u8 [N, record_bytes] (no copies):
+  (view u8 [N, *view_shape], reward i32 [N], discount f32 [N], done u8 [N],
+  has_reward u8 [N])."""
+  import torch
+  view_bytes = 1
+  for d in view_shape:
+    view_bytes *= int(d)
+  word = ((view_bytes + 3) & ~3) // 4
+  n = records.shape[0]
+  assert records.dtype == torch.uint8 and records.shape[1] == handoff_record_bytes(view_bytes)
+  view = records[:, :view_bytes].reshape((n,) + tuple(view_shape))
+  return (view, records.view(torch.int32)[:, word], records.view(torch.float32)[:, word + 1],
+          records[:, 4 * word + 8], records[:, 4 * word + 9])
+
+
+class Handoff(object):
+  """The per-step hand-off of one rank's shard to every rank with a
+  single collective: pack on the device, one `all_gather_into_tensor`, unpack as
+  views.  Buffers are allocated once."""
+
+  def __init__(self, engine, view_shape, global_batch, group=None):
+    import torch
+    import torch.distributed as dist
+    self.engine, self.group = engine, group
+    self.view_shape = tuple(int(d) for d in view_shape)
+    self.view_bytes = int(np.prod(self.view_shape))
+    world = dist.get_world_size(group)
+    self.counts = [shard_range(global_batch, r, world)[1] for r in range(world)]
+    assert self.counts[dist.get_rank(group)] == engine.batch
+    self.biggest = max(self.counts)
+    rec = handoff_record_bytes(self.view_bytes)
+    self.packed = torch.zeros((self.biggest, rec), dtype=torch.uint8, device=engine.device)
+    self.gathered = torch.empty((world * self.biggest, rec), dtype=torch.uint8,
+                                device=engine.device)
+
+  def gather(self, view):
+    """`view`: u8 [local envs, *view_shape] (contiguous), e.g. `engine.crop(spec)`."""
+    self.engine.pack_handoff(view, self.packed)
+    return self.exchange()
+
+  def exchange(self):
+    import torch
+    import torch.distributed as dist
+    dist.all_gather_into_tensor(self.gathered, self.packed, group=self.group)
+    records = self.gathered
+    if any(c != self.biggest for c in self.counts):       # drop the padding of short shards
+      records = torch.cat([records[r * self.biggest: r * self.biggest + c]
+                           for r, c in enumerate(self.counts)])
+    return unpack_handoff(records, self.view_shape)
+
+
+class PeerHandoff(object):
+  """`Handoff` without a collective call: the gather buffers live in symmetric
+  memory (every rank maps every peer's buffer), the pack kernel stores each record
+  into ALL of them over NVLink (`pcl_pack_handoff_peers`), and one device-side
+  barrier per step tells the consumers that every rank's records have landed.
+  Two buffers alternate, so a step may overwrite only what was consumed (in
+  stream order) before the previous step's barrier."""
+
+  def __init__(self, engine, view_shape, global_batch, group=None):
+    import torch
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm_mem
+    group = group if group is not None else dist.group.WORLD
+    self.engine = engine
+    self.view_shape = tuple(int(d) for d in view_shape)
+    self.view_bytes = int(np.prod(self.view_shape))
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    self.counts = [shard_range(global_batch, r, world)[1] for r in range(world)]
+    assert self.counts[rank] == engine.batch
+    self.biggest = max(self.counts)
+    self.rows, self.rec = world * self.biggest, handoff_record_bytes(self.view_bytes)
+    self.first_row = rank * self.biggest
+    half = self.rows * self.rec
+    self.buffer = symm_mem.empty(2 * half, dtype=torch.uint8, device=engine.device)
+    self.buffer.zero_()
+    self.handle = symm_mem.rendezvous(self.buffer, group)
+    self.peer_ptrs = [[int(p) + k * half for p in self.handle.buffer_ptrs] for k in (0, 1)]
+    self.halves = [self.buffer[k * half:(k + 1) * half].view(self.rows, self.rec)
+                   for k in (0, 1)]
+    self.step = 0
+    self.handle.barrier(channel=0)            # everyone's buffers exist and are zeroed
+
+  def gather(self, view):
+    k = self.step & 1
+    self.step += 1
+    self.engine.pack_handoff_peers(view, self.peer_ptrs[k], self.first_row)
+    self.handle.barrier(channel=0)            # all ranks' stores have been issued and finished
+    records = self.halves[k]
+    if any(c != self.biggest for c in self.counts):
+      import torch
+      records = torch.cat([records[r * self.biggest: r * self.biggest + c]
+                           for r, c in enumerate(self.counts)])
+    return unpack_handoff(records, self.view_shape)

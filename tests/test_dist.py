@@ -59,6 +59,130 @@ def test_allgather_outputs_gloo_world2(total):
   assert list(ok) == [1] * world
 
 
+def pack_records(view, reward, discount, done, has_reward):
+  """NumPy restatement of the hand-off record (include/pcl.h:
+  PCL_HANDOFF_RECORD_BYTES) — test infrastructure."""
+  n = view.shape[0]
+  flat = view.reshape(n, -1)
+  padded = (flat.shape[1] + 3) & ~3
+  rec = np.zeros((n, padded + 12), dtype=np.uint8)
+  rec[:, :flat.shape[1]] = flat
+  rec[:, padded:padded + 4] = reward.astype('<i4').view(np.uint8).reshape(n, 4)
+  rec[:, padded + 4:padded + 8] = discount.astype('<f4').view(np.uint8).reshape(n, 4)
+  rec[:, padded + 8], rec[:, padded + 9] = done, has_reward
+  return rec
+
+
+def _shard_outputs(first, count):
+  ids = np.arange(first, first + count)
+  view = ((ids[:, None, None] * 3 + np.arange(15).reshape(3, 5)) % 251).astype(np.uint8)
+  return (view, (ids * 7 - 3).astype(np.int32), (ids % 2).astype(np.float32),
+          (ids % 3 == 0).astype(np.uint8), (ids % 5 != 0).astype(np.uint8))
+
+
+def test_unpack_handoff_views():
+  import torch
+  outs = _shard_outputs(4, 9)
+  rec = torch.from_numpy(pack_records(*outs))
+  assert rec.shape[1] == pdist.handoff_record_bytes(15) == 28
+  for got, want in zip(pdist.unpack_handoff(rec, (3, 5)), outs):
+    np.testing.assert_array_equal(got.numpy(), want)
+
+
+def _handoff_worker(rank, world, port, total, ok):
+  import torch
+  import torch.distributed as dist
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  first, count = pdist.shard_range(total, rank, world)
+
+  class Shard(object):            # what Handoff needs of a BatchedEngine
+    batch, device = count, torch.device('cpu')
+  handoff = pdist.Handoff(Shard(), (3, 5), total)
+  handoff.packed[:count] = torch.from_numpy(pack_records(*_shard_outputs(first, count)))
+  got = handoff.exchange()        # the ONE all-gather + unpack
+  good = all(np.array_equal(g.numpy(), w) for g, w in zip(got, _shard_outputs(0, total)))
+  ok[rank] = 1 if good else 0
+  dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('total', [10, 11])
+def test_handoff_single_collective_gloo_world2(total):
+  import torch.multiprocessing as mp
+  world = 2
+  ok = mp.get_context('spawn').Array('i', [0] * world)
+  mp.spawn(_handoff_worker, args=(world, _free_port(), total, ok), nprocs=world, join=True)
+  assert list(ok) == [1] * world
+
+
+def _peer_worker(rank, world, port, ok):
+  import torch
+  import torch.distributed as dist
+  from pycolab_b200 import batched, levels
+  from pycolab_b200.games import scrolly_maze
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  torch.cuda.set_device(rank)
+  dist.init_process_group('nccl', rank=rank, world_size=world,
+                          device_id=torch.device('cuda', rank))
+  total, good = 2 * 33 + 1, True               # uneven shards: 34 + 33
+  arts = [levels.scrolly_maze_level(80 + i, world_shape=(65, 65), board_shape=(30, 45))
+          for i in range(3)]
+  eng = pdist.make_shard_engine([scrolly_maze.make_game(*a) for a in arts], total, rank, world,
+                                rank)
+  eng.its_showtime()
+  spec = batched.scrolling_crop_spec(9, 9, 0, pad_char=' ', scroll_margins=(None, None))
+  nccl, peer = pdist.Handoff(eng, (9, 9), total), pdist.PeerHandoff(eng, (9, 9), total)
+  rs = np.random.RandomState(rank)
+  for _ in range(25):
+    eng.play(torch.from_numpy(rs.randint(0, 5, size=eng.batch).astype(np.int32)).cuda())
+    crop = eng.crop(spec).clone()
+    want = [t.clone() for t in nccl.gather(crop)]
+    got = peer.gather(crop)
+    torch.cuda.synchronize()
+    good = good and all(bool((g == w).all()) for g, w in zip(got, want))
+    good = good and got[0].shape == (total, 9, 9)
+  ok[rank] = 1 if good else 0
+  dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_peer_handoff_equals_nccl_handoff_on_two_gpus():
+  """The all-gather fused into the pack kernel (P2P stores into symmetric memory)
+  delivers what pack + NCCL all-gather delivers.  Needs two GPUs."""
+  import torch
+  import torch.multiprocessing as mp
+  if torch.cuda.device_count() < 2:
+    pytest.skip('needs 2 GPUs')
+  ok = mp.get_context('spawn').Array('i', [0, 0])
+  mp.spawn(_peer_worker, args=(2, _free_port(), ok), nprocs=2, join=True)
+  assert list(ok) == [1, 1]
+
+
+@pytest.mark.gpu
+def test_pack_handoff_kernel_matches_the_record_layout():
+  import torch
+  from pycolab_b200 import batched, levels
+  from pycolab_b200.games import scrolly_maze
+  arts = [levels.scrolly_maze_level(70 + i, world_shape=(65, 65), board_shape=(30, 45))
+          for i in range(2)]
+  eng = batched.BatchedEngine([scrolly_maze.make_game(*a) for a in arts], batch=37)
+  eng.its_showtime()
+  rs = np.random.RandomState(1)
+  spec = batched.scrolling_crop_spec(9, 9, 0, pad_char=' ', scroll_margins=(None, None))
+  packed = torch.zeros((40, pdist.handoff_record_bytes(81)), dtype=torch.uint8, device='cuda')
+  for _ in range(40):
+    res = eng.play(torch.from_numpy(rs.randint(0, 5, size=37).astype(np.int32)).cuda())
+    crop = eng.crop(spec)
+    eng.pack_handoff(crop, packed)
+    torch.cuda.synchronize()
+    want = pack_records(crop.cpu().numpy(), res.reward.cpu().numpy(), res.discount.cpu().numpy(),
+                        res.done.cpu().numpy(), res.has_reward.cpu().numpy())
+    np.testing.assert_array_equal(packed[:37].cpu().numpy(), want)
+    assert not packed[37:].any()
+
+
 @pytest.mark.gpu
 def test_two_shards_reproduce_one_engine():
   """Global env i behaves identically whether it lives in a 1-rank or a 2-rank job
