@@ -79,6 +79,60 @@ def test_create_rejects_bad_specs_without_gpu():
   assert lib.pcl_destroy(h) == _lib.OK
 
 
+def _create(spec, batch=4):
+  import ctypes as C
+  lib = _lib.load()
+  h = C.c_void_p()
+  status = lib.pcl_create(C.byref(spec), batch, -1, C.byref(h))   # device -1: no CUDA call
+  if status == _lib.OK:
+    lib.pcl_destroy(h)
+  return status
+
+
+def test_every_lowered_game_passes_create_validation_without_gpu():
+  """lowering -> pcl_spec -> pcl_create's validation, for one level of every
+  device program (no GPU needed: device = -1 skips cudaSetDevice)."""
+  import importlib
+  import golden_cases as gc
+  import trajectory as tj
+  from pycolab_b200.games import aperture, better_scrolly_maze, fluvial_natation
+  games = [g_scrolly.make_game(*levels.scrolly_maze_level(0, world_shape=(33, 33),
+                                                          board_shape=(16, 16))),
+           g_warehouse.make_game(levels.warehouse_level(1), ' '),
+           g_marauders.make_game(levels.marauders_level()),
+           better_scrolly_maze.make_game(tj.u8_to_art(gc.load('better_stock_L0')['art'])),
+           fluvial_natation.make_game(), aperture.make_game(levels.aperture_level())]
+  for kind in ('four_rooms', 'cliff_walk', 'chain_walk'):
+    mod = importlib.import_module('pycolab_b200.games.classics.' + kind)
+    games += [mod.make_game(), mod.make_game(levels.classic_level(kind))]
+  programs = set()
+  for game in games:
+    lowered = lowering.lower(game)
+    programs.add(lowered.program)
+    assert _create(lowered.make_spec(auto_reset=True)) == _lib.OK, lowered.program
+  assert programs == {_lib.PROG_SCROLLY_MAZE, _lib.PROG_WAREHOUSE, _lib.PROG_MARAUDERS,
+                      _lib.PROG_BETTER_SCROLLY, _lib.PROG_CLASSICS, _lib.PROG_APERTURE}
+
+
+def test_create_rejects_malformed_specs_of_the_newer_programs():
+  from pycolab_b200.games import aperture, fluvial_natation
+  from pycolab_b200.games.classics import four_rooms
+  spec = lowering.lower(four_rooms.make_game()).make_spec(True)
+  spec.program_arg[0] = 9                                   # unknown rule set
+  assert _create(spec) == _lib.ERR_INVALID
+  spec = lowering.lower(fluvial_natation.make_game()).make_spec(True)
+  spec.impassable[0][1] = 1 << 3                            # a swimmer that reads the board ('#')
+  assert _create(spec) == _lib.ERR_UNSUPPORTED
+  spec = lowering.lower(aperture.make_game(levels.aperture_level())).make_spec(True)
+  spec.z_order[0], spec.z_order[1] = spec.z_order[1], spec.z_order[0]   # player under the drape
+  assert _create(spec) == _lib.ERR_UNSUPPORTED
+  spec = lowering.lower(aperture.make_game(levels.aperture_level())).make_spec(True)
+  spec.n_groups, spec.group_len[0], spec.group_len[1] = 1, 2, 0         # one update group
+  assert _create(spec) == _lib.ERR_UNSUPPORTED
+  spec = lowering.lower(four_rooms.make_game()).make_spec(True)
+  assert _create(spec, batch=0) == _lib.ERR_INVALID
+
+
 def test_missing_library_fails_loudly(monkeypatch):
   monkeypatch.setattr(_lib, '_lib', None)
   monkeypatch.setattr(_lib, 'LIB_PATH', '/nonexistent/libpcl.so')
