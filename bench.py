@@ -103,7 +103,7 @@ class ClockSampler(object):
            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
   def __init__(self, gpu_index):
-    self.gpu = gpu_index
+    self.gpu = gpu_index            # one index, or a comma-separated list
     self.proc = None
     self.path = None
     self.begin = self.end = None
@@ -345,8 +345,12 @@ def main():
   if world > 1:
     dist.init_process_group('nccl', device_id=dev)
 
-  sampler = ClockSampler(local_rank)
-  sampler.start()
+  # One poller for the whole job (rank 0 watches every GPU of the box): eight
+  # 50 Hz nvidia-smi loops next to eight ranks that synchronise every e2e step is
+  # needless driver traffic.
+  sampler = ClockSampler(','.join(str(i) for i in range(world)) if world > 1 else local_rank)
+  if rank == 0:
+    sampler.start()
   B, K, W = BATCH_PER_GPU, args.steps, max(3, args.warmup)
   R = 1 if args.no_rotate else ROTATION
   arts = make_levels(N_LEVELS)
