@@ -384,6 +384,23 @@ def layers_of(board, chars):
   return {c: board == ord(c) for c in chars}
 
 
+def unoccluded_layers_of(backdrop, things, chars):
+  """rendering.py:187-301 (`BaseUnoccludedObservationRenderer`): every layer is
+  painted on its own — backdrop characters where the backdrop has them, a visible
+  sprite's cell, a drape's whole curtain — so several layers may be set at one
+  position."""
+  layers = {c: np.asarray(backdrop) == ord(c) for c in chars}
+  for ch, ent in things.items():
+    if ent.is_sprite:
+      layer = np.zeros_like(layers[ch])
+      if ent.visible:
+        layer[ent.row, ent.col] = True
+      layers[ch] = layers[ch] | layer
+    else:
+      layers[ch] = layers[ch] | ent.curtain
+  return layers
+
+
 class World(object):
   """One environment = one reference `Engine` (engine.py:38-246)."""
 

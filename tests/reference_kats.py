@@ -53,6 +53,16 @@ def result_code(result):
   return code(result)
 
 
+class InertSprite(object):
+  """A plain `things.Sprite` whose update does nothing (test_things.py TestSprite)."""
+  is_sprite = True
+
+  def __init__(self, position, visible):
+    self.row, self.col = position
+    self.vrow, self.vcol = position
+    self.visible = visible
+
+
 def oracle_world(snap):
   """An oracle World in exactly the state the reference Engine was in."""
   shape = (snap['rows'], snap['cols'])
@@ -72,6 +82,8 @@ def oracle_world(snap):
     things[ch] = drape
   for ch, rows in snap['drapes'].items():
     things[ch] = em.PlainDrape(ch, bits(rows))
+  for ch, s in snap.get('sprites', {}).items():
+    things[ch] = InertSprite(tuple(s['position']), s['visible'])
   world = em.World(shape[0], shape[1], u8(snap['backdrop']), things, z_order=snap['z_order'],
                    groups=snap['groups'], program=games.fixture_program)
   world.plot.frame = snap['frame']
