@@ -29,8 +29,17 @@ def _check(entity, the_plot, group):
                     'use the scrolling protocol.'.format(entity))
   known = the_plot.setdefault('scrolling_everyone', {}).setdefault(entity, group)
   if known != group:
-    raise Error('entity already belongs to scrolling group {!r}, not {!r}'.format(
-        known, group))
+    raise Error('{} has attempted to participate in the scrolling protocol as part of '
+                'scrolling group {}, but is already known to belong to scrolling group '
+                '{}.'.format(_who(entity), repr(group), repr(known)))
+
+
+def _who(entity):
+  """How error messages name an entity (scrolling.py:572-578)."""
+  character = getattr(entity, 'character', None)
+  if character is not None:
+    return 'a Sprite or Drape handling character {}'.format(repr(character))
+  return 'the Backdrop'
 
 
 def participate_as_egocentric(entity, the_plot, scrolling_group=''):
@@ -53,8 +62,8 @@ def get_order(entity, the_plot, scrolling_group=''):
 def permit(entity, the_plot, motions, scrolling_group=''):
   _check(entity, the_plot, scrolling_group)
   if entity not in the_plot.setdefault(_key(scrolling_group, 'egocentrists'), set()):
-    raise Error('entity is not registered as egocentric in scrolling group '
-                '{!r}'.format(scrolling_group))
+    raise Error('{} is not registered as an egocentric entity in scrolling group '
+                '{}'.format(_who(entity), repr(scrolling_group)))
   valid_at = the_plot.frame + 1
   frames = the_plot.setdefault(_key(scrolling_group, 'permitted_frame'), {})
   mine = the_plot.setdefault(_key(scrolling_group, 'permitted'), {}).setdefault(
@@ -78,10 +87,10 @@ def is_possible(entity, the_plot, motion, scrolling_group=''):
 def order(entity, the_plot, motion, scrolling_group='', check_possible=True):
   _check(entity, the_plot, scrolling_group)
   if the_plot.setdefault(_key(scrolling_group, 'order_frame'), None) == the_plot.frame:
-    raise Error('a second scrolling order was issued for scrolling group '
-                '{!r}'.format(scrolling_group))
+    raise Error('{} attempted to issue a second scrolling order for scrolling group {}.'
+                ''.format(_who(entity), repr(scrolling_group)))
   if check_possible and not is_possible(entity, the_plot, motion, scrolling_group):
-    raise Error('impossible scrolling motion {} for scrolling group {!r}'.format(
-        motion, scrolling_group))
+    raise Error('{} attempted to order an impossible scrolling motion "{}" for scrolling '
+                'group {}.'.format(_who(entity), motion, repr(scrolling_group)))
   the_plot[_key(scrolling_group, 'order_frame')] = the_plot.frame
   the_plot[_key(scrolling_group, 'order')] = motion

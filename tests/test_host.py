@@ -452,6 +452,33 @@ def test_reference_fluvial_natation_loads_and_lowers(compat_examples):
 
 
 @needs_ref
+def test_reference_host_only_unit_tests_pass_against_this_package(compat_examples):
+  """The reference's own unit tests that need no step — ascii_art_test.py and
+  scrolling_test.py::testProtocol (the scrolling-protocol helpers incl. their
+  error messages) — run UNMODIFIED with `pycolab` aliased to this package."""
+  import importlib.util
+  import types
+  import unittest
+  base = os.path.join(refdriver.REFERENCE_ROOT, 'pycolab', 'tests')
+  package = sys.modules.setdefault('pycolab.tests', types.ModuleType('pycolab.tests'))
+
+  def load(name):
+    spec = importlib.util.spec_from_file_location('pycolab.tests.' + name,
+                                                  os.path.join(base, name + '.py'))
+    module = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = module
+    setattr(package, name, module)
+    spec.loader.exec_module(module)
+    return module
+  load('test_things')
+  suite = unittest.TestSuite()
+  suite.addTests(unittest.defaultTestLoader.loadTestsFromModule(load('ascii_art_test')))
+  suite.addTest(load('scrolling_test').ScrollingTest('testProtocol'))
+  result = unittest.TextTestRunner(verbosity=0).run(suite)
+  assert result.testsRun == 2 and result.wasSuccessful(), result.failures + result.errors
+
+
+@needs_ref
 def test_reference_test_fixtures_load_and_lower(compat_examples):
   """The reference's own tests/test_things.py fixtures lower to the general
   device program, identically to this package's games/fixtures.py."""
