@@ -151,3 +151,29 @@ def test_constructor_argument_checks():
   clash = lambda: _DrapeP(ogames.make_classic('cliff_walk', ['............'] * 3 + ['P...........']), '.')
   with pytest.raises(ValueError):
     storytelling.Story([cliff, clash])
+
+
+def test_reference_story_tests_pass_against_this_story_class(monkeypatch):
+  """The reference's own `tests/story_test.py` (6 tests: sequences, dicts,
+  cropping, inter-game reward accumulation, stand-ins, compatibility checking),
+  UNMODIFIED, with `storytelling.Story` replaced by this package's class.  The
+  chapters are reference Engines (the tests define entities with Python update
+  logic), so the class is pointed at the reference's `things` / `cropping` /
+  `engine` types for the duration."""
+  import sys
+  import unittest
+  import refdriver
+  if not refdriver.available():
+    pytest.skip('/root/reference not present')
+  refdriver.ref_storytelling()          # the Python 3.12 collections shim + import path
+  from pycolab import cropping as ref_cropping
+  from pycolab import engine as ref_engine
+  from pycolab import things as ref_things
+  from pycolab.tests import story_test
+  monkeypatch.setattr(storytelling, 'cropping', ref_cropping)
+  monkeypatch.setattr(storytelling, 'things', ref_things)
+  monkeypatch.setattr(storytelling, 'engine_lib', ref_engine)
+  monkeypatch.setattr(story_test, 'storytelling', storytelling)
+  suite = unittest.defaultTestLoader.loadTestsFromModule(story_test)
+  result = unittest.TextTestRunner(verbosity=0).run(suite)
+  assert result.testsRun == 6 and result.wasSuccessful(), result.failures + result.errors
