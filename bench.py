@@ -44,6 +44,14 @@ A_STEP_BYTES = 64 * 64 * 6 + 64 * 4 + 64          # 24 896
 LAYOUT_STEP_BYTES = 4096 + 4096 + 2 * 64 * 8 + 2 * (4 * 32 + 2 * 32 + 64)
 
 
+# The pure-Python reference cannot travel to the GPU box, so the CPU arms time the
+# oracle port.  Measured in the build container on this workload, one core: the
+# reference itself 6.8-7.0 k env-steps/s, the port 15.0-16.6 k.
+PORT_VS_REFERENCE = ('the oracle port runs about 2.3x FASTER than the reference itself on this '
+                     'workload (6.9 k vs 15.8 k env-steps/s, one core, build container), so '
+                     'ratios against it understate the gain over pycolab')
+
+
 def make_levels(n, seed0=1000):
   from pycolab_b200 import levels
   return [levels.scrolly_maze_level(seed0 + i, world_shape=WORLD, board_shape=BOARD)
@@ -192,7 +200,7 @@ def run_reference_arm(args, rank, world):
       'dtype': 'u8', 'data': 'synthetic',
       'config': workload_config(args.gpus),
       'cpu_baseline': {'value': value, 'unit': 'env-steps/s', 'cores': cores,
-                       'kind': 'port',
+                       'kind': 'port', 'port_vs_reference': PORT_VS_REFERENCE,
                        'sample': '%d env-steps of the same generated 64x64 levels, one '
                                  'oracle env per host process, %d processes' % (
                                      total_steps, cores)},
@@ -525,7 +533,7 @@ def main():
             'layout_bytes_per_launch': B * LAYOUT_STEP_BYTES,
             'layout_achieved': layout, 'layout_frac': layout / peak},
         'cpu_baseline': {'value': cpu_value, 'unit': 'env-steps/s', 'cores': 1,
-                         'kind': 'port',
+                         'kind': 'port', 'port_vs_reference': PORT_VS_REFERENCE,
                          'sample': '%d env-steps of one oracle env on the same generated '
                                    '64x64 levels' % cpu_steps},
         'render_roofline': dict(render_roofline(render_ms, B, eng, peak),
