@@ -170,6 +170,26 @@ class ClockSampler(object):
     return out
 
 
+def pin_to_gpu_numa_node(torch, index):
+  """Restrict this process (and so its pinned host buffers, first touched later) to
+  the CPUs of the NUMA node its GPU hangs off.  Best effort; silent when the
+  topology cannot be read.  Used to investigate the host-side `e2e` contention
+  seen with 8 ranks."""
+  try:
+    bus = torch.cuda.get_device_properties(index).pci_bus_id.lower()
+    node = int(open('/sys/bus/pci/devices/%s/numa_node' % bus).read())
+    if node < 0:
+      return
+    cpus = set()
+    for part in open('/sys/devices/system/node/node%d/cpulist' % node).read().strip().split(','):
+      lo, _, hi = part.partition('-')
+      cpus.update(range(int(lo), int(hi or lo) + 1))
+    if cpus:
+      os.sched_setaffinity(0, cpus)
+  except (OSError, ValueError, AttributeError):
+    pass
+
+
 # --------------------------------------------------------------------- main
 
 def run_reference_arm(args, rank, world):
@@ -350,6 +370,8 @@ def main():
 
   torch.cuda.set_device(local_rank)
   dev = torch.device('cuda', local_rank)
+  if os.environ.get('PCL_BENCH_NUMA_PIN') == '1':     # experiment switch, off by default
+    pin_to_gpu_numa_node(torch, local_rank)
   if world > 1:
     dist.init_process_group('nccl', device_id=dev)
 
