@@ -176,7 +176,8 @@ def pin_to_gpu_numa_node(torch, index):
   topology cannot be read.  Used to investigate the host-side `e2e` contention
   seen with 8 ranks."""
   try:
-    bus = torch.cuda.get_device_properties(index).pci_bus_id.lower()
+    props = torch.cuda.get_device_properties(index)
+    bus = '%04x:%02x:%02x.0' % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
     node = int(open('/sys/bus/pci/devices/%s/numa_node' % bus).read())
     if node < 0:
       return
