@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PCL_ABI_VERSION 1
+#define PCL_ABI_VERSION 2
 
 #define PCL_MAX_SPRITES 16
 #define PCL_MAX_DRAPES 8
@@ -204,6 +204,16 @@ int pcl_step(pcl_handle* h, const int32_t* d_actions, const pcl_outputs* out,
 int pcl_run(pcl_handle* h, const int32_t* d_actions, int steps,
             const pcl_outputs* out, void* stream);
 
+/* `steps` pcl_step()s issued from one C call over several handles in rotation:
+ * step t advances handles[t % n_handles] with d_actions[t] (HOST array of `steps`
+ * device pointers, each i32 [B, actions_per_env] of that handle) into
+ * outs[t % n_handles].  The batched stand-in for a driver looping over many
+ * Engines (one reference Engine per env, engine.py:583); nothing but kernel
+ * launches sits between the steps, so the sequence can also be captured into a
+ * CUDA graph on `stream`. */
+int pcl_run_many(pcl_handle* const* handles, int n_handles, const int32_t* const* d_actions,
+                 const pcl_outputs* const* outs, int steps, void* stream);
+
 /* Host-buffer form of pcl_step: copies h_actions to the device, steps, copies
  * the outputs back into the h_* buffers (any may be NULL = skip) and
  * synchronises the stream.  `out` names the device staging buffers. */
@@ -211,6 +221,27 @@ int pcl_step_host(pcl_handle* h, const int32_t* h_actions, int32_t* d_actions,
                   const pcl_outputs* out, uint8_t* h_board, int32_t* h_reward,
                   uint8_t* h_has_reward, float* h_discount, uint8_t* h_done,
                   void* stream);
+
+/* Pipelined form of pcl_step_host.  Enqueues H2D(actions) and the step on
+ * `stream`, then the D2H of the requested outputs on a handle-owned copy stream
+ * behind it, and returns WITHOUT synchronising: the copies of this step overlap
+ * whatever is enqueued on `stream` next (another handle's step, or this handle's
+ * next step once its outputs were read).  `slot` (0 .. PCL_HOST_SLOTS - 1) names
+ * the completion event; pcl_host_wait(h, slot) blocks until the h_* buffers of
+ * that call are valid.  Until then the caller must leave h_actions and the h_*
+ * buffers alone, and must not call the synchronous step entry points on `h`.
+ * With `crop` non-NULL the step is followed by pcl_crop(crop, d_crop, d_crop_state)
+ * and h_view receives the crops u8 [B, crop rows, crop cols] instead of the
+ * boards u8 [B, rows, pitch] — only the view the agent consumes crosses PCIe
+ * (cropping.py:393-426 applied before the hand-off). */
+#define PCL_HOST_SLOTS 8
+struct pcl_crop_spec;
+int pcl_step_host_async(pcl_handle* h, const int32_t* h_actions, int32_t* d_actions,
+                        const pcl_outputs* out, const struct pcl_crop_spec* crop,
+                        uint8_t* d_crop, int32_t* d_crop_state, uint8_t* h_view,
+                        int32_t* h_reward, uint8_t* h_has_reward, float* h_discount,
+                        uint8_t* h_done, int slot, void* stream);
+int pcl_host_wait(pcl_handle* h, int slot);
 
 /* Stand-alone renderer = Engine._render() + BaseObservationRenderer
  * (engine.py:737-759, rendering.py:98-179) over reference-layout inputs:
@@ -306,6 +337,9 @@ int pcl_error_codes(pcl_handle* h, int32_t* d_out, void* stream);
 int pcl_launch_count(pcl_handle* h, int64_t* out);
 
 const char* pcl_status_string(int status);
+/* Text of the last CUDA failure behind a PCL_ERR_CUDA of this handle ("" if none);
+ * valid until the next failing call on the handle. */
+const char* pcl_last_error(pcl_handle* h);
 int pcl_abi_version(void);
 
 #ifdef __cplusplus

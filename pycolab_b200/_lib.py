@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libpcl.so')
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_SPRITES = 16
 MAX_DRAPES = 8
 MAX_TRACK = 4                # entities one ScrollingCropper can follow (pcl_crop_spec.track)
@@ -18,6 +18,7 @@ SPRITE_WORDS = 8
 DRAPE_WORDS = 8
 PLOT_WORDS = 16
 MT_WORDS = 625
+HOST_SLOTS = 8               # pcl_step_host_async completion slots
 NEVER = -(2 ** 31)           # INT32_MIN: "-inf"/None frame
 ACTION_NONE = -1
 
@@ -129,6 +130,14 @@ SYMBOLS = {
     'pcl_step_host': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Outputs),
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p]),
+    'pcl_run_many': (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p),
+                               C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
+    'pcl_step_host_async': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Outputs),
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_void_p]),
+    'pcl_host_wait': (C.c_int, [C.c_void_p, C.c_int]),
+    'pcl_last_error': (C.c_char_p, [C.c_void_p]),
     'pcl_render': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                              C.c_void_p, C.c_void_p, C.c_void_p]),
     'pcl_export_curtain': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
@@ -185,6 +194,14 @@ def status_string(status):
     return 'status %d' % status
 
 
-def check(status, what):
+def check(status, what, handle=None):
   if status != OK:
-    raise PclError(status, what)
+    err = PclError(status, what)
+    if status == ERR_CUDA and handle is not None:
+      try:
+        detail = load().pcl_last_error(handle).decode()
+      except Exception:                      # noqa: BLE001 - the status itself still raises
+        detail = ''
+      if detail:
+        err.args = ('%s [%s]' % (err.args[0], detail),)
+    raise err

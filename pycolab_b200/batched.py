@@ -42,13 +42,15 @@ class StepResult(object):
 class BatchedEngine(object):
 
   def __init__(self, games, batch=None, device=0, auto_reset=True, rng_seed=0,
-               env_offset=0, rng_states=None):
+               env_offset=0, rng_states=None, share_levels=True):
     """games: list of lowered games (`lowering.LoweredGame`) or set-up `Engine`s.
     Env e uses games[e % len(games)]; with a single game the static level data
     (backdrop, immutable patterns, reset templates) is shared by all envs.
     env_offset: global index of this shard's env 0 (per-env RNG streams are
     seeded rng_seed + global env index); rng_states: explicit u32 [B, 625]
-    MT19937 states (624 key words + position) instead of seeds."""
+    MT19937 states (624 key words + position) instead of seeds.
+    share_levels=False stores the static level data once PER ENV instead of once
+    per level (the reference's layout: every Engine owns its backdrop)."""
     torch = _torch()
     self._lib = _lib.load()
     if not torch.cuda.is_available():
@@ -84,6 +86,9 @@ class BatchedEngine(object):
 
     def bstride(t):
       return 0 if t.shape[0] == 1 else t[0].numel()
+
+    if not share_levels:
+      tiled, shared = per_env, True     # every array env-indexed, no level table
 
     self._keep = []             # every tensor the handle points at
     st = _lib.State()
@@ -160,7 +165,9 @@ class BatchedEngine(object):
                              self.has_reward.data_ptr(), self.discount.data_ptr(),
                              self.done.data_ptr())
     self._actions = torch.zeros((B * self.actions_per_env,), dtype=torch.int32, device=dev)
-    self._host = None           # pinned staging for play_host()
+    self._host = None           # pinned staging for play_host() / play_host_async(), per slot
+    self._slot_shape = {}
+    self._crop_dev = None
     self._crop_out = None
 
     self._spec = g0.make_spec(self.auto_reset)
@@ -190,7 +197,7 @@ class BatchedEngine(object):
                          'been called')
     self._showtime = True
     _lib.check(self._lib.pcl_reset(self._h, None, C.byref(self._out), self._stream()),
-               'pcl_reset')
+               'pcl_reset', self._h)
     return self._result()
 
   def reset(self, env_mask=None):
@@ -201,7 +208,7 @@ class BatchedEngine(object):
     if env_mask is not None:
       mask = env_mask.to(device=self.device, dtype=_torch().uint8).contiguous()
     _lib.check(self._lib.pcl_reset(self._h, None if mask is None else mask.data_ptr(),
-                                   C.byref(self._out), self._stream()), 'pcl_reset')
+                                   C.byref(self._out), self._stream()), 'pcl_reset', self._h)
     return self._result()
 
   def play(self, actions):
@@ -221,7 +228,7 @@ class BatchedEngine(object):
       raise ValueError('expected %d action words, got %d' % (
           self.batch * self.actions_per_env, actions.numel()))
     _lib.check(self._lib.pcl_step(self._h, actions.data_ptr(), C.byref(self._out),
-                                  self._stream()), 'pcl_step')
+                                  self._stream()), 'pcl_step', self._h)
     return self._result()
 
   def run(self, actions):
@@ -230,32 +237,73 @@ class BatchedEngine(object):
     assert actions.is_cuda and actions.dtype == torch.int32 and actions.is_contiguous()
     assert actions.dim() >= 2 and actions[0].numel() == self.batch * self.actions_per_env
     _lib.check(self._lib.pcl_run(self._h, actions.data_ptr(), int(actions.shape[0]),
-                                 C.byref(self._out), self._stream()), 'pcl_run')
+                                 C.byref(self._out), self._stream()), 'pcl_run', self._h)
     return self._result()
+
+  def _host_buffers(self, slot, view_shape):
+    """Pinned staging of one pipeline slot (allocated on first use)."""
+    torch = _torch()
+    key = (slot, tuple(view_shape))
+    if self._host is None:
+      self._host = {}
+    if key not in self._host:
+      pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()
+      t = dict(actions=pin((self.batch * self.actions_per_env,), torch.int32),
+               view=pin(tuple(view_shape), torch.uint8),
+               reward=pin((self.batch,), torch.int32), has_reward=pin((self.batch,), torch.uint8),
+               discount=pin((self.batch,), torch.float32), done=pin((self.batch,), torch.uint8))
+      self._host[key] = (t, {k: v.numpy() for k, v in t.items()})
+    return self._host[key]
 
   def play_host(self, actions, want_board=True):
     """Host-buffer step through `pcl_step_host`: int32 [B] numpy actions in,
     numpy (board [B, rows, pitch] padded, reward, has_reward, discount, done)
     views of pinned host buffers out; synchronises."""
-    torch = _torch()
-    if self._host is None:
-      pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()
-      self._host = dict(
-          actions=pin((self.batch * self.actions_per_env,), torch.int32),
-          board=pin((self.batch, self.rows, self.pitch), torch.uint8),
-          reward=pin((self.batch,), torch.int32), has_reward=pin((self.batch,), torch.uint8),
-          discount=pin((self.batch,), torch.float32), done=pin((self.batch,), torch.uint8))
-      self._host_np = {k: v.numpy() for k, v in self._host.items()}
-    h = self._host
-    self._host_np['actions'][:] = np.asarray(actions, dtype=np.int32).reshape(-1)
+    h, n = self._host_buffers(0, (self.batch, self.rows, self.pitch))
+    n['actions'][:] = np.asarray(actions, dtype=np.int32).reshape(-1)
     _lib.check(self._lib.pcl_step_host(
         self._h, h['actions'].data_ptr(), self._actions.data_ptr(), C.byref(self._out),
-        h['board'].data_ptr() if want_board else None, h['reward'].data_ptr(),
+        h['view'].data_ptr() if want_board else None, h['reward'].data_ptr(),
         h['has_reward'].data_ptr(), h['discount'].data_ptr(), h['done'].data_ptr(),
-        self._stream()), 'pcl_step_host')
-    n = self._host_np
-    return (n['board'][:, :, :self.cols], n['reward'], n['has_reward'], n['discount'],
+        self._stream()), 'pcl_step_host', self._h)
+    return (n['view'][:, :, :self.cols], n['reward'], n['has_reward'], n['discount'],
             n['done'])
+
+  def play_host_async(self, actions, slot=0, crop_spec=None, crop_state=None):
+    """Pipelined host-buffer step (`pcl_step_host_async`): enqueue H2D(actions),
+    the step (and, with `crop_spec`, the cropper) and the D2H of the outputs on
+    the engine's copy stream, and return at once.  `host_wait(slot)` blocks until
+    this call's results are valid and returns them.  With a crop spec only the
+    cropped view u8 [B, rows, cols] crosses PCIe."""
+    if not self._showtime:
+      raise RuntimeError('play() cannot be called until its_showtime() has been called')
+    if crop_spec is None:
+      shape = (self.batch, self.rows, self.pitch)
+    else:
+      shape = (self.batch, crop_spec.rows, crop_spec.cols)
+      if self._crop_dev is None or tuple(self._crop_dev.shape) != shape:
+        self._crop_dev = _torch().empty(shape, dtype=_torch().uint8, device=self.device)
+    h, n = self._host_buffers(slot, shape)
+    n['actions'][:] = np.asarray(actions, dtype=np.int32).reshape(-1)
+    _lib.check(self._lib.pcl_step_host_async(
+        self._h, h['actions'].data_ptr(), self._actions.data_ptr(), C.byref(self._out),
+        None if crop_spec is None else C.addressof(crop_spec),
+        None if crop_spec is None else self._crop_dev.data_ptr(),
+        None if crop_state is None else crop_state.data_ptr(),
+        h['view'].data_ptr(), h['reward'].data_ptr(), h['has_reward'].data_ptr(),
+        h['discount'].data_ptr(), h['done'].data_ptr(), int(slot), self._stream()),
+        'pcl_step_host_async', self._h)
+    self._slot_shape[slot] = shape
+
+  def host_wait(self, slot=0):
+    """Results of the `play_host_async` call that used `slot`: numpy views of its
+    pinned buffers (view, reward, has_reward, discount, done)."""
+    _lib.check(self._lib.pcl_host_wait(self._h, int(slot)), 'pcl_host_wait', self._h)
+    _, n = self._host_buffers(slot, self._slot_shape[slot])
+    view = n['view']
+    if view.shape[1:] == (self.rows, self.pitch):
+      view = view[:, :, :self.cols]
+    return view, n['reward'], n['has_reward'], n['discount'], n['done']
 
   # ------------------------------------------------------------- accessors
   def curtain(self, char):
@@ -284,14 +332,14 @@ class BatchedEngine(object):
         out[b, (cell[b] >> 16).long(), (cell[b] & 0xffff).long()] = 1
     else:
       _lib.check(self._lib.pcl_export_curtain(self._h, d, out.data_ptr(), self._stream()),
-                 'pcl_export_curtain')
+                 'pcl_export_curtain', self._h)
     return out
 
   def error_codes(self):
     torch = _torch()
     out = torch.empty((self.batch,), dtype=torch.int32, device=self.device)
     _lib.check(self._lib.pcl_error_codes(self._h, out.data_ptr(), self._stream()),
-               'pcl_error_codes')
+               'pcl_error_codes', self._h)
     return out
 
   def launch_count(self):
@@ -325,10 +373,10 @@ class BatchedEngine(object):
           ptrs[i] = curtains[-1].data_ptr()
       _lib.check(self._lib.pcl_crop_tracking(self._h, C.byref(crop_spec),
                                              self._board.data_ptr(), out.data_ptr(), state_ptr,
-                                             ptrs, self._stream()), 'pcl_crop_tracking')
+                                             ptrs, self._stream()), 'pcl_crop_tracking', self._h)
     else:
       _lib.check(self._lib.pcl_crop(self._h, C.byref(crop_spec), self._board.data_ptr(),
-                                    out.data_ptr(), state_ptr, self._stream()), 'pcl_crop')
+                                    out.data_ptr(), state_ptr, self._stream()), 'pcl_crop', self._h)
     return out
 
   def pack_handoff(self, view, packed):
@@ -341,7 +389,7 @@ class BatchedEngine(object):
     assert packed.shape[1] == ((view_bytes + 3) & ~3) + 12
     _lib.check(self._lib.pcl_pack_handoff(self._h, view.data_ptr(), view_bytes,
                                           C.byref(self._out), packed.data_ptr(),
-                                          self._stream()), 'pcl_pack_handoff')
+                                          self._stream()), 'pcl_pack_handoff', self._h)
     return packed
 
   def pack_handoff_peers(self, view, peer_ptrs, first_row):
@@ -353,7 +401,7 @@ class BatchedEngine(object):
     ptrs = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
     _lib.check(self._lib.pcl_pack_handoff_peers(
         self._h, view.data_ptr(), int(view[0].numel()), C.byref(self._out), ptrs,
-        len(peer_ptrs), int(first_row), self._stream()), 'pcl_pack_handoff_peers')
+        len(peer_ptrs), int(first_row), self._stream()), 'pcl_pack_handoff_peers', self._h)
 
   # --- observation post-processors (rendering.py:304-661) over the whole batch
   def to_feature_array(self, layers, permute=None):
@@ -433,3 +481,25 @@ def scrolling_crop_spec(rows, cols, sprite_index, pad_char=None, scroll_margins=
       spec.track[i] = int(code)
     spec.sprite_index = max(0, spec.track[0] - 1)
   return spec
+
+
+def run_rotating(engines, actions, stream=None):
+  """`len(actions)` steps from ONE C call (`pcl_run_many`): step t advances
+  engines[t % len(engines)] with actions[t] (int32 device tensors).  No Python
+  runs between the launches, so the call can sit inside a CUDA-graph capture."""
+  torch = _torch()
+  n, steps = len(engines), len(actions)
+  handles = (C.c_void_p * n)(*[e._h.value for e in engines])
+  outs = (C.c_void_p * n)(*[C.addressof(e._out) for e in engines])
+  ptrs = (C.c_void_p * steps)()
+  for t, a in enumerate(actions):
+    e = engines[t % n]
+    assert a.is_cuda and a.dtype == torch.int32 and a.is_contiguous()
+    assert a.numel() == e.batch * e.actions_per_env
+    if not e._showtime:
+      raise RuntimeError('play() cannot be called until its_showtime() has been called')
+    ptrs[t] = a.data_ptr()
+  if stream is None:
+    stream = engines[0]._stream()
+  _lib.check(engines[0]._lib.pcl_run_many(handles, n, ptrs, outs, steps, stream),
+             'pcl_run_many', engines[0]._h)

@@ -1,11 +1,13 @@
 // api.cu — the extern "C" boundary declared in include/pcl.h.
 #include <cuda_runtime.h>
+#include <stdio.h>
 #include <string.h>
 
 #include <new>
 
 #include "pcl_device.cuh"
 #include "pcl_kernels.cuh"
+
 
 struct pcl_handle {
   pcl_spec spec;
@@ -15,16 +17,31 @@ struct pcl_handle {
   int actions_per_env;
   pcl_state st;
   long long launches;
+  pcl::StepParams base;          // everything fill_params derives from spec + state, built once at bind
+  char last_error[256];          // text of the last failed CUDA call (pcl_last_error)
+  // pcl_step_host_async: a copy stream so that the D2H of one step overlaps the next kernel
+  cudaStream_t copy_stream;
+  cudaEvent_t ev_step[PCL_HOST_SLOTS];   // step kernel finished (compute stream)
+  cudaEvent_t ev_done[PCL_HOST_SLOTS];   // host buffers of that slot are valid (copy stream)
+  int host_ready;
+  int pending_slot;              // slot of this handle's last async step whose D2H may still run, or -1
 };
 
 namespace {
 
 using pcl::StepParams;
 
-#define PCL_CUDA(call)                                   \
-  do {                                                   \
-    cudaError_t e_ = (call);                             \
-    if (e_ != cudaSuccess) { return PCL_ERR_CUDA; }      \
+// Remember what failed: PCL_ERR_CUDA alone says nothing (pcl_last_error).
+int cuda_failed(pcl_handle* h, cudaError_t e, const char* what) {
+  if (h) snprintf(h->last_error, sizeof(h->last_error), "%s: %s (%s)", what,
+                  cudaGetErrorString(e), cudaGetErrorName(e));
+  return PCL_ERR_CUDA;
+}
+
+#define PCL_CUDA(h, call)                                        \
+  do {                                                           \
+    cudaError_t e_ = (call);                                     \
+    if (e_ != cudaSuccess) return cuda_failed((h), e_, #call);   \
   } while (0)
 
 bool chars_are(const uint8_t* got, int n, const char* want) {
@@ -224,8 +241,16 @@ int launch(pcl_handle* h, const StepParams& p, cudaStream_t stream) {
     case PCL_PROG_APERTURE: e = pcl::launch_aperture(p, stream); break;
     default: return PCL_ERR_UNSUPPORTED;
   }
+  if (e != cudaSuccess) return cuda_failed(h, e, "step kernel launch");
+  h->launches += 1;              // only launches that were accepted count
+  return PCL_OK;
+}
+
+// Status of a non-step kernel launch; counts it when it went through.
+int launched(pcl_handle* h, cudaError_t e, const char* what) {
+  if (e != cudaSuccess) return cuda_failed(h, e, what);
   h->launches += 1;
-  return e == cudaSuccess ? PCL_OK : PCL_ERR_CUDA;
+  return PCL_OK;
 }
 
 int check_ready(const pcl_handle* h, const pcl_outputs* out) {
@@ -263,7 +288,7 @@ int pcl_create(const pcl_spec* spec, int batch, int device, pcl_handle** out) {
   if (!spec || !out || batch <= 0) return PCL_ERR_INVALID;
   const int v = validate(*spec);
   if (v != PCL_OK) return v;
-  if (device >= 0) PCL_CUDA(cudaSetDevice(device));
+  if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return PCL_ERR_CUDA;
   pcl_handle* h = new (std::nothrow) pcl_handle();
   if (!h) return PCL_ERR_NOMEM;
   h->spec = *spec;
@@ -272,14 +297,26 @@ int pcl_create(const pcl_spec* spec, int batch, int device, pcl_handle** out) {
   h->bound = 0;
   h->actions_per_env = spec->program == PCL_PROG_FIXTURE ? spec->n_sprites + spec->n_drapes + 4 : 1;
   h->launches = 0;
+  h->last_error[0] = 0;
+  h->host_ready = 0;
+  h->pending_slot = -1;
   *out = h;
   return PCL_OK;
 }
 
 int pcl_destroy(pcl_handle* h) {
+  if (h && h->host_ready) {
+    for (int i = 0; i < PCL_HOST_SLOTS; ++i) {
+      cudaEventDestroy(h->ev_step[i]);
+      cudaEventDestroy(h->ev_done[i]);
+    }
+    cudaStreamDestroy(h->copy_stream);
+  }
   delete h;
   return PCL_OK;
 }
+
+const char* pcl_last_error(pcl_handle* h) { return h ? h->last_error : ""; }
 
 int pcl_bind_state(pcl_handle* h, const pcl_state* st) {
   if (!h || !st) return PCL_ERR_INVALID;
@@ -305,6 +342,7 @@ int pcl_bind_state(pcl_handle* h, const pcl_state* st) {
     }
   }
   h->st = *st;
+  fill_params(h, &h->base);      // the per-step calls only patch mode / actions / outputs
   h->bound = 1;
   return PCL_OK;
 }
@@ -312,8 +350,7 @@ int pcl_bind_state(pcl_handle* h, const pcl_state* st) {
 int pcl_reset(pcl_handle* h, const uint8_t* d_env_mask, const pcl_outputs* out, void* stream) {
   const int r = check_ready(h, out);
   if (r != PCL_OK) return r;
-  StepParams p;
-  fill_params(h, &p);
+  StepParams p = h->base;
   p.mode = pcl::MODE_RESET;
   p.env_mask = d_env_mask;
   p.out = *out;
@@ -324,8 +361,7 @@ int pcl_step(pcl_handle* h, const int32_t* d_actions, const pcl_outputs* out, vo
   const int r = check_ready(h, out);
   if (r != PCL_OK) return r;
   if (!d_actions) return PCL_ERR_INVALID;
-  StepParams p;
-  fill_params(h, &p);
+  StepParams p = h->base;
   p.mode = pcl::MODE_STEP;
   p.actions = d_actions;
   p.out = *out;
@@ -337,8 +373,7 @@ int pcl_run(pcl_handle* h, const int32_t* d_actions, int steps, const pcl_output
   const int r = check_ready(h, out);
   if (r != PCL_OK) return r;
   if (!d_actions || steps < 0) return PCL_ERR_INVALID;
-  StepParams p;
-  fill_params(h, &p);
+  StepParams p = h->base;
   p.mode = pcl::MODE_STEP;
   p.out = *out;
   for (int t = 0; t < steps; ++t) {
@@ -349,6 +384,64 @@ int pcl_run(pcl_handle* h, const int32_t* d_actions, int steps, const pcl_output
   return PCL_OK;
 }
 
+int pcl_run_many(pcl_handle* const* handles, int n_handles, const int32_t* const* d_actions,
+                 const pcl_outputs* const* outs, int steps, void* stream) {
+  if (!handles || !d_actions || !outs || n_handles < 1 || steps < 0) return PCL_ERR_INVALID;
+  for (int i = 0; i < n_handles; ++i) {
+    const int r = check_ready(handles[i], outs[i]);
+    if (r != PCL_OK) return r;
+  }
+  for (int t = 0; t < steps; ++t) {
+    if (!d_actions[t]) return PCL_ERR_INVALID;
+    pcl_handle* h = handles[t % n_handles];
+    StepParams p = h->base;
+    p.mode = pcl::MODE_STEP;
+    p.out = *outs[t % n_handles];
+    p.actions = d_actions[t];
+    const int e = launch(h, p, (cudaStream_t)stream);
+    if (e != PCL_OK) return e;
+  }
+  return PCL_OK;
+}
+
+namespace {
+
+// H2D of the action words, then the step, both on `s`.
+int step_host_enqueue(pcl_handle* h, const int32_t* h_actions, int32_t* d_actions,
+                      const pcl_outputs* out, cudaStream_t s) {
+  const size_t B = (size_t)h->batch;
+  PCL_CUDA(h, cudaMemcpyAsync(d_actions, h_actions, B * h->actions_per_env * sizeof(int32_t),
+                              cudaMemcpyHostToDevice, s));
+  return pcl_step(h, d_actions, out, (void*)s);
+}
+
+int copy_outputs(pcl_handle* h, const pcl_outputs* out, const uint8_t* d_view, size_t view_bytes,
+                 uint8_t* h_view, int32_t* h_reward, uint8_t* h_has_reward, float* h_discount,
+                 uint8_t* h_done, cudaStream_t s) {
+  const size_t B = (size_t)h->batch;
+  if (h_view) PCL_CUDA(h, cudaMemcpyAsync(h_view, d_view, view_bytes, cudaMemcpyDeviceToHost, s));
+  if (h_reward) PCL_CUDA(h, cudaMemcpyAsync(h_reward, out->d_reward, B * 4, cudaMemcpyDeviceToHost, s));
+  if (h_has_reward)
+    PCL_CUDA(h, cudaMemcpyAsync(h_has_reward, out->d_has_reward, B, cudaMemcpyDeviceToHost, s));
+  if (h_discount)
+    PCL_CUDA(h, cudaMemcpyAsync(h_discount, out->d_discount, B * 4, cudaMemcpyDeviceToHost, s));
+  if (h_done) PCL_CUDA(h, cudaMemcpyAsync(h_done, out->d_done, B, cudaMemcpyDeviceToHost, s));
+  return PCL_OK;
+}
+
+int host_pipeline_ready(pcl_handle* h) {
+  if (h->host_ready) return PCL_OK;
+  PCL_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < PCL_HOST_SLOTS; ++i) {
+    PCL_CUDA(h, cudaEventCreateWithFlags(&h->ev_step[i], cudaEventDisableTiming));
+    PCL_CUDA(h, cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+  }
+  h->host_ready = 1;
+  return PCL_OK;
+}
+
+}  // namespace
+
 int pcl_step_host(pcl_handle* h, const int32_t* h_actions, int32_t* d_actions,
                   const pcl_outputs* out, uint8_t* h_board, int32_t* h_reward,
                   uint8_t* h_has_reward, float* h_discount, uint8_t* h_done, void* stream) {
@@ -356,20 +449,54 @@ int pcl_step_host(pcl_handle* h, const int32_t* h_actions, int32_t* d_actions,
   if (r != PCL_OK) return r;
   if (!h_actions || !d_actions) return PCL_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
-  const size_t B = (size_t)h->batch;
-  PCL_CUDA(cudaMemcpyAsync(d_actions, h_actions, B * h->actions_per_env * sizeof(int32_t),
-                           cudaMemcpyHostToDevice, s));
-  const int e = pcl_step(h, d_actions, out, stream);
-  if (e != PCL_OK) return e;
   const size_t plane = (size_t)h->spec.rows * h->spec.pitch;
-  if (h_board) PCL_CUDA(cudaMemcpyAsync(h_board, out->d_board, B * plane, cudaMemcpyDeviceToHost, s));
-  if (h_reward) PCL_CUDA(cudaMemcpyAsync(h_reward, out->d_reward, B * 4, cudaMemcpyDeviceToHost, s));
-  if (h_has_reward)
-    PCL_CUDA(cudaMemcpyAsync(h_has_reward, out->d_has_reward, B, cudaMemcpyDeviceToHost, s));
-  if (h_discount)
-    PCL_CUDA(cudaMemcpyAsync(h_discount, out->d_discount, B * 4, cudaMemcpyDeviceToHost, s));
-  if (h_done) PCL_CUDA(cudaMemcpyAsync(h_done, out->d_done, B, cudaMemcpyDeviceToHost, s));
-  PCL_CUDA(cudaStreamSynchronize(s));
+  int e = step_host_enqueue(h, h_actions, d_actions, out, s);
+  if (e != PCL_OK) return e;
+  e = copy_outputs(h, out, out->d_board, (size_t)h->batch * plane, h_board, h_reward, h_has_reward,
+                   h_discount, h_done, s);
+  if (e != PCL_OK) return e;
+  PCL_CUDA(h, cudaStreamSynchronize(s));
+  return PCL_OK;
+}
+
+int pcl_step_host_async(pcl_handle* h, const int32_t* h_actions, int32_t* d_actions,
+                        const pcl_outputs* out, const pcl_crop_spec* crop, uint8_t* d_crop,
+                        int32_t* d_crop_state, uint8_t* h_view, int32_t* h_reward,
+                        uint8_t* h_has_reward, float* h_discount, uint8_t* h_done, int slot,
+                        void* stream) {
+  const int r = check_ready(h, out);
+  if (r != PCL_OK) return r;
+  if (!h_actions || !d_actions || slot < 0 || slot >= PCL_HOST_SLOTS) return PCL_ERR_INVALID;
+  if (crop && !d_crop) return PCL_ERR_INVALID;
+  int e = host_pipeline_ready(h);
+  if (e != PCL_OK) return e;
+  cudaStream_t s = (cudaStream_t)stream;
+  // This step overwrites the device outputs: the D2H of this handle's previous
+  // async step must have read them.  Other handles sharing `s` are not held up.
+  if (h->pending_slot >= 0) PCL_CUDA(h, cudaStreamWaitEvent(s, h->ev_done[h->pending_slot], 0));
+  e = step_host_enqueue(h, h_actions, d_actions, out, s);
+  if (e != PCL_OK) return e;
+  const uint8_t* d_view = out->d_board;
+  size_t view_bytes = (size_t)h->batch * h->spec.rows * h->spec.pitch;
+  if (crop) {                    // only the cropped view crosses PCIe
+    e = pcl_crop(h, crop, out->d_board, d_crop, d_crop_state, stream);
+    if (e != PCL_OK) return e;
+    d_view = d_crop;
+    view_bytes = (size_t)h->batch * crop->rows * crop->cols;
+  }
+  PCL_CUDA(h, cudaEventRecord(h->ev_step[slot], s));
+  PCL_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_step[slot], 0));
+  e = copy_outputs(h, out, d_view, view_bytes, h_view, h_reward, h_has_reward, h_discount, h_done,
+                   h->copy_stream);
+  if (e != PCL_OK) return e;
+  PCL_CUDA(h, cudaEventRecord(h->ev_done[slot], h->copy_stream));
+  h->pending_slot = slot;
+  return PCL_OK;
+}
+
+int pcl_host_wait(pcl_handle* h, int slot) {
+  if (!h || slot < 0 || slot >= PCL_HOST_SLOTS || !h->host_ready) return PCL_ERR_INVALID;
+  PCL_CUDA(h, cudaEventSynchronize(h->ev_done[slot]));
   return PCL_OK;
 }
 
@@ -387,8 +514,7 @@ int pcl_render(pcl_handle* h, const uint8_t* d_backdrop, int64_t backdrop_bstrid
   p.curtains = d_curtains; p.sprites = d_sprites; p.z_order = d_z_order; p.board = d_board;
   memcpy(p.sprite_char, h->spec.sprite_char, sizeof(p.sprite_char));
   memcpy(p.drape_char, h->spec.drape_char, sizeof(p.drape_char));
-  h->launches += 1;
-  return pcl::launch_render(p, (cudaStream_t)stream) == cudaSuccess ? PCL_OK : PCL_ERR_CUDA;
+  return launched(h, pcl::launch_render(p, (cudaStream_t)stream), "launch_render");
 }
 
 int pcl_export_curtain(pcl_handle* h, int drape_index, uint8_t* d_out, void* stream) {
@@ -420,8 +546,7 @@ int pcl_export_curtain(pcl_handle* h, int drape_index, uint8_t* d_out, void* str
   } else {
     return PCL_ERR_UNSUPPORTED;
   }
-  h->launches += 1;
-  return pcl::launch_export_curtain(p, (cudaStream_t)stream) == cudaSuccess ? PCL_OK : PCL_ERR_CUDA;
+  return launched(h, pcl::launch_export_curtain(p, (cudaStream_t)stream), "launch_export_curtain");
 }
 
 int pcl_crop(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d_board, uint8_t* d_crop,
@@ -459,8 +584,7 @@ int pcl_crop_tracking(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d
       p.curtains[i] = d_curtains[i];
     }
   }
-  h->launches += 1;
-  return pcl::launch_crop(p, (cudaStream_t)stream) == cudaSuccess ? PCL_OK : PCL_ERR_CUDA;
+  return launched(h, pcl::launch_crop(p, (cudaStream_t)stream), "launch_crop");
 }
 
 int pcl_pack_handoff(pcl_handle* h, const uint8_t* d_view, int32_t view_bytes,
@@ -473,8 +597,7 @@ int pcl_pack_handoff(pcl_handle* h, const uint8_t* d_view, int32_t view_bytes,
   p.B = h->batch; p.view_bytes = view_bytes;
   p.record_bytes = PCL_HANDOFF_RECORD_BYTES(view_bytes);
   p.view = d_view; p.out = *out; p.packed = d_packed;
-  h->launches += 1;
-  return pcl::launch_pack_handoff(p, (cudaStream_t)stream) == cudaSuccess ? PCL_OK : PCL_ERR_CUDA;
+  return launched(h, pcl::launch_pack_handoff(p, (cudaStream_t)stream), "launch_pack_handoff");
 }
 
 int pcl_pack_handoff_peers(pcl_handle* h, const uint8_t* d_view, int32_t view_bytes,
@@ -495,8 +618,7 @@ int pcl_pack_handoff_peers(pcl_handle* h, const uint8_t* d_view, int32_t view_by
     if (!d_peer_bases[i]) return PCL_ERR_INVALID;
     p.peers[i] = d_peer_bases[i];
   }
-  h->launches += 1;
-  return pcl::launch_pack_handoff(p, (cudaStream_t)stream) == cudaSuccess ? PCL_OK : PCL_ERR_CUDA;
+  return launched(h, pcl::launch_pack_handoff(p, (cudaStream_t)stream), "launch_pack_handoff");
 }
 
 int pcl_observe(pcl_handle* h, const pcl_observe_spec* spec, const void* d_table,
@@ -514,8 +636,7 @@ int pcl_observe(pcl_handle* h, const pcl_observe_spec* spec, const void* d_table
   p.stride_r = spec->stride_r * p.words; p.stride_c = spec->stride_c * p.words;
   p.table = d_table; p.valid = d_valid; p.board = d_board; p.out = d_out;
   p.unknown = d_unknown;
-  h->launches += 1;
-  return pcl::launch_observe(p, (cudaStream_t)stream) == cudaSuccess ? PCL_OK : PCL_ERR_CUDA;
+  return launched(h, pcl::launch_observe(p, (cudaStream_t)stream), "launch_observe");
 }
 
 int pcl_error_codes(pcl_handle* h, int32_t* d_out, void* stream) {
@@ -523,8 +644,7 @@ int pcl_error_codes(pcl_handle* h, int32_t* d_out, void* stream) {
   if (!h->bound) return PCL_ERR_UNBOUND;
   gather_errors<<<(h->batch + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->st.d_plot, d_out,
                                                                            h->batch);
-  h->launches += 1;
-  return cudaGetLastError() == cudaSuccess ? PCL_OK : PCL_ERR_CUDA;
+  return launched(h, cudaGetLastError(), "gather_errors");
 }
 
 int pcl_launch_count(pcl_handle* h, int64_t* out) {

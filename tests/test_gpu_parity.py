@@ -40,7 +40,7 @@ def test_facade_scrolly_golden(name):
   g = gc.load(name)
   maze, board, beneath = gc.scrolly_art(g)
   sprites = []
-  n = min(len(g['actions']), 400)
+  n = len(g['actions'])            # the whole golden (BASELINE configs[0]: 1000 steps)
   got = tj.run_trajectory(lambda: scrolly_maze.make_game(maze, board, beneath),
                           g['actions'][:n].tolist(),
                           on_frame=_facade_sprites('Pabc', sprites))
@@ -57,7 +57,7 @@ def test_facade_warehouse_golden(name):
   art, wlb = gc.warehouse_art(g)
   chars = bytes(g['sprite_chars']).decode()
   sprites = []
-  n = min(len(g['actions']), 300)
+  n = len(g['actions'])
   got = tj.run_trajectory(lambda: warehouse_manager.make_game(art, wlb),
                           g['actions'][:n].tolist(),
                           on_frame=_facade_sprites(chars, sprites))
@@ -74,7 +74,7 @@ def test_facade_marauders_golden(name):
   art = tj.u8_to_art(g['art'])
   np.random.seed(int(g['rng_seed'][0]))     # facade mirrors the global NumPy RNG
   sprites = []
-  n = min(len(g['actions']), 500)
+  n = len(g['actions'])
   got = tj.run_trajectory(lambda: marauders.make_game(art), g['actions'][:n].tolist(),
                           on_frame=_facade_sprites('Pabcdyz', sprites))
   want = {k: g[k][:n + 1] for k in ('boards', 'reward', 'has_reward', 'discount',
