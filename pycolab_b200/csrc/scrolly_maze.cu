@@ -94,38 +94,125 @@ __device__ __forceinline__ void pdl_wait_prior_grids() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// Selector table of the paint loop (see the kernel): 256 x u16, built at compile
+// time and pulled into shared memory with one cp.async per lane of warp 0.
+struct SelTable { uint16_t v[256]; };
+constexpr SelTable make_sel_table() {
+  SelTable t = {};
+  for (int idx = 0; idx < 256; ++idx) {
+    unsigned sel = 0;
+    for (int k = 0; k < 4; ++k) {
+      const unsigned nib = ((idx >> (4 + k)) & 1) ? 5u : ((idx >> k) & 1) ? 4u : (unsigned)k;
+      sel |= nib << (4 * k);
+    }
+    t.v[idx] = (uint16_t)sel;
+  }
+  return t;
+}
+__device__ __align__(16) const SelTable g_sel = make_sel_table();
+
+// 3x3 "blocked" mask (bit (dr+1)*3 + dc+1, sprites.py:495-507) around the virtual
+// position (vrow, vcol) of a walker whose 5x5 wall patch `field` is centred on
+// (r0, c0): a cell blocks iff it is on the board, the wall curtain covers it and the
+// player is not painted over it (z-order ... '#' 'P').  Pure per-lane arithmetic.
+__device__ __forceinline__ unsigned blocked3x3(int vrow, int vcol, int r0, int c0, unsigned field,
+                                               int H, int W, bool p_vis, int p_row, int p_col) {
+  const int br = vrow - r0 + 1, bc = vcol - c0 + 1;    // 3x3 origin inside the 5x5: 0..2
+  if ((unsigned)br > 2u || (unsigned)bc > 2u) return 0u;   // cannot happen (|order|, |move| <= 1)
+  unsigned colmask = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) colmask |= ((unsigned)(vcol - 1 + i) < (unsigned)W ? 1u : 0u) << i;
+  unsigned blk = 0;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    unsigned bits = (field >> ((br + j) * 5 + bc)) & colmask;
+    if ((unsigned)(vrow - 1 + j) >= (unsigned)H) bits = 0;
+    blk |= bits << (3 * j);
+  }
+  const int dr = p_row - vrow + 1, dc = p_col - vcol + 1;
+  if (p_vis && (unsigned)dr <= 2u && (unsigned)dc <= 2u) blk &= ~(1u << (dr * 3 + dc));
+  return blk;
+}
+
+// All eight motions of sprites.py:479-546 at once: bit m set = motion code m is
+// legal (N NE E SE S SW W NW), plus STAY.
+__device__ __forceinline__ int legal_motions(unsigned b) {
+  const unsigned nw = b & 1u, n = (b >> 1) & 1u, ne = (b >> 2) & 1u, w = (b >> 3) & 1u,
+                 e = (b >> 5) & 1u, sw = (b >> 6) & 1u, s = (b >> 7) & 1u, se = (b >> 8) & 1u;
+  const unsigned blocked = n | ((ne | (n & e)) << 1) | (e << 2) | ((se | (s & e)) << 3) |
+                           (s << 4) | ((sw | (s & w)) << 5) | (w << 6) | ((nw | (n & w)) << 7);
+  return (int)((~blocked & 0xffu) | (1u << PCL_M_STAY));
+}
+
+// drapes.py:487-659 `_maybe_move` when the player is the only possible egocentric
+// participant (validated in pcl_create): same decisions as pcl::scrolly_move.
+__device__ __forceinline__ void scrolly_move_p(Drape& d, const ScrollyCfg& cfg, int motion,
+                                               Plot& plot, int p_row, int p_col, int p_permit,
+                                               int p_permit_frame) {
+  if (d.last_frame < plot.frame) {
+    d.last_frame = plot.frame;
+    d.pre_r = d.corner_r; d.pre_c = d.corner_c;
+  }
+  const int dr = motion_dr(motion), dc = motion_dc(motion);
+  if (plot.order_frame == plot.frame) {          // obey an existing order :513-535
+    if (dr != plot.order_r && dc != plot.order_c) plot.error |= PCL_ENV_ERR_ORDER_MISMATCH;
+    d.corner_r += plot.order_r; d.corner_c += plot.order_c;
+    return;
+  }
+  if (motion == PCL_M_STAY) return;
+  const bool ego = plot.ego_mask & 1;
+  const bool possible = !ego || (p_permit_frame == plot.frame && ((p_permit >> motion) & 1));
+  int orr, occ;
+  if (!cfg.have_margins) {                       // :598-623
+    if (!possible) return;
+    const int nr = d.corner_r + dr, nc = d.corner_c + dc;
+    orr = (0 <= nr && nr <= cfg.limit_r) ? dr : 0;
+    occ = (0 <= nc && nc <= cfg.limit_c) ? dc : 0;
+  } else {                                       // :625-687
+    if (!ego) return;
+    const int nr = p_row + dr, nc = p_col + dc;  // TRUE position
+    const bool want_v = (p_row > nr && nr <= cfg.m_north) || (p_row < nr && nr >= cfg.m_south);
+    const bool want_h = (p_col > nc && nc <= cfg.m_west) || (p_col < nc && nc >= cfg.m_east);
+    if (!(want_v || want_h)) return;
+    orr = want_v ? dr : 0; occ = want_h ? dc : 0;
+    const int cr = d.corner_r + orr, cc = d.corner_c + occ;
+    if (!((0 <= cr && cr <= cfg.limit_r) && (0 <= cc && cc <= cfg.limit_c)) || !possible) return;
+  }
+  d.corner_r += orr; d.corner_c += occ;
+  plot.order_r = orr; plot.order_c = occ; plot.order_frame = plot.frame;
+}
+
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7)
 scrolly_maze_step(const StepParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   // Byte-permute selectors for 4 cells at once: index = wall nibble << 4 | coin
   // nibble; selector nibble k picks byte 5 ('#') if wall_k, else byte 4 ('@') if
   // coin_k, else byte k of the backdrop word (z-order ... '@' '#' ...).
-  __shared__ uint16_t s_sel[256];
-  for (int idx = threadIdx.x; idx < 256; idx += blockDim.x) {
-    unsigned sel = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const unsigned nib = ((idx >> (4 + k)) & 1) ? 5u : ((idx >> k) & 1) ? 4u : (unsigned)k;
-      sel |= nib << (4 * k);
-    }
-    s_sel[idx] = (uint16_t)sel;
-  }
+  __shared__ __align__(16) uint16_t s_sel[256];
+  if (threadIdx.x < 32)
+    cp_async16(reinterpret_cast<uint8_t*>(s_sel) + threadIdx.x * 16,
+               reinterpret_cast<const uint8_t*>(g_sel.v) + threadIdx.x * 16);
   pdl_launch_dependents();
-  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int env = blockIdx.x * kWarpsPerBlock + warp;
-  if (env >= p.B) return;
+  const bool live = env < p.B;
   const int H = p.H, W = p.W, PWW = p.PWW;
+  const int pitch = p.pitch;
 
-  uint8_t* my = smem_raw + warp * warp_smem_bytes(H, p.pitch);
+  uint8_t* my = smem_raw + warp * warp_smem_bytes(H, pitch);
   int32_t* rec = reinterpret_cast<int32_t*>(my);
   uint8_t* s_bd = my + kRecWords * 4;
-  uint32_t* s_wall = reinterpret_cast<uint32_t*>(s_bd + (size_t)H * p.pitch);
+  uint32_t* s_wall = reinterpret_cast<uint32_t*>(s_bd + (size_t)H * pitch);
   uint32_t* s_coin = s_wall + H * 4;
-  // Everything above ran without touching global memory; from here on the
-  // kernel reads state earlier work in the stream may have produced.
+  // Everything above ran without touching state earlier kernels may have
+  // produced (g_sel is a constant); from here on the kernel reads such state.
   pdl_wait_prior_grids();
+  if (!live) {                 // ragged last block: only the selector copy to drain
+    cp_async_wait_all();
+    __syncthreads();
+    return;
+  }
   const int64_t lvl = p.st.d_level ? p.st.d_level[env] : env;   // index of static level data
 
   int32_t* g_sprites = p.st.d_sprites + (int64_t)env * kS * PCL_SPRITE_WORDS;
@@ -133,12 +220,14 @@ scrolly_maze_step(const StepParams p) {
   int32_t* g_plot = p.st.d_plot + (int64_t)env * PCL_PLOT_WORDS;
   const uint32_t* wall_pat = p.st.d_pattern[0] + lvl * p.st.pattern_bstride[0];
   uint32_t* coin_pat = p.st.d_pattern[1] + (int64_t)env * p.st.pattern_bstride[1];
-  const uint8_t* backdrop = p.st.d_backdrop + lvl * p.st.backdrop_bstride;
 
   // ---- 0. the backdrop tile depends on nothing: get it moving first --------
   {
-    const int n16 = (H * p.pitch) >> 4;
-    for (int i = lane; i < n16; i += 32) cp_async16(s_bd + i * 16, backdrop + i * 16);
+    const uint8_t* src = p.st.d_backdrop + lvl * p.st.backdrop_bstride + lane * 16;
+    uint8_t* dst = s_bd + lane * 16;
+    const int n16 = (H * pitch) >> 4;
+#pragma unroll 4
+    for (int i = lane; i < n16; i += 32, src += 512, dst += 512) cp_async16(dst, src);
   }
   // ---- 1. records -> smem (coalesced) ------------------------------------
   rec[lane] = g_sprites[lane];
@@ -146,15 +235,18 @@ scrolly_maze_step(const StepParams p) {
   __syncwarp();
   const int was_over = rec[48 + PCL_P_GAME_OVER];
   bool restart;                              // engine.py:520-581, 619-624
+  bool frozen = false;
   if (p.mode == MODE_RESET) {
     restart = (p.env_mask == nullptr) || (p.env_mask[env] != 0);
-    if (!restart) { cp_async_wait_all(); return; }
+    frozen = !restart;
   } else {
     restart = was_over && p.auto_reset;
-    if (was_over && !p.auto_reset) {         // reference raises; env stays frozen
-      cp_async_wait_all();
-      return;
-    }
+    frozen = was_over && !p.auto_reset;      // reference raises; env stays frozen
+  }
+  if (frozen) {                              // warp-uniform
+    cp_async_wait_all();
+    __syncthreads();                         // the block barrier below is taken by all warps
+    return;
   }
   int action;
   if (restart) {
@@ -177,16 +269,22 @@ scrolly_maze_step(const StepParams p) {
     action = p.actions[(int64_t)env * p.actions_per_env];
   }
 
-  // ---- only the fields this game uses live in registers ------------------
-  Sprite sp[kS];
-#pragma unroll
-  for (int i = 0; i < kS; ++i) {
-    const int32_t* r = rec + i * PCL_SPRITE_WORDS;
-    sp[i].row = r[PCL_S_ROW]; sp[i].col = r[PCL_S_COL];
-    sp[i].vrow = r[PCL_S_VROW]; sp[i].vcol = r[PCL_S_VCOL];
-    sp[i].flags = r[PCL_S_FLAGS]; sp[i].aux0 = r[PCL_S_AUX0];
-    sp[i].aux1 = (i == 0) ? r[PCL_S_AUX1] : 0; sp[i].aux2 = 0;
+  // ---- registers: the drapes / plot / player fields every lane needs, plus ONE
+  // walker per lane (lane & 3: P, a, b, c) for the SIMT part of group 1 ---------
+  const int me = lane & 3;
+  Sprite mine;
+  {
+    const int32_t* r = rec + me * PCL_SPRITE_WORDS;
+    mine.row = r[PCL_S_ROW]; mine.col = r[PCL_S_COL];
+    mine.vrow = r[PCL_S_VROW]; mine.vcol = r[PCL_S_VCOL];
+    mine.flags = r[PCL_S_FLAGS]; mine.aux0 = r[PCL_S_AUX0]; mine.aux1 = r[PCL_S_AUX1];
+    mine.aux2 = 0;
   }
+  // The player as every lane sees it (previous render + permits).
+  const int p_row = rec[PCL_S_ROW], p_col = rec[PCL_S_COL];
+  const int p_vrow = rec[PCL_S_VROW], p_vcol = rec[PCL_S_VCOL];
+  const bool p_vis = rec[PCL_S_FLAGS] & 1;
+  const int p_permit = rec[PCL_S_AUX0], p_permit_frame = rec[PCL_S_AUX1];
   Drape walls, coins;
   {
     const int32_t* r = rec + 32;
@@ -216,7 +314,8 @@ scrolly_maze_step(const StepParams p) {
   plot.frame += 1;                                           // engine.py:716
 
   // ---- 2. update group 0: '#' MazeDrape (scrolly_maze.py:308-329) --------
-  if (motion != PCL_M_NONE) scrolly_move(walls, wcfg, motion, plot, sp);
+  if (motion != PCL_M_NONE)
+    scrolly_move_p(walls, wcfg, motion, plot, p_row, p_col, p_permit, p_permit_frame);
   const bool ordered = plot.order_frame == plot.frame;
   const int wr = walls.corner_r, wc = walls.corner_c;
   // Where the '@' window will be after it obeys the same order (checked below).
@@ -233,95 +332,136 @@ scrolly_maze_step(const StepParams p) {
       cp_async8(s_coin + i * 2, coin_pat + (int64_t)(cr_pred + r) * PWW + ce + k);
     }
   }
-  // Walker start positions: every look-up below is relative to these.
-  int vr0[kS], vc0[kS];
-#pragma unroll
-  for (int i = 0; i < kS; ++i) { vr0[i] = sp[i].vrow; vc0[i] = sp[i].vcol; }
   scrolly_touch_prescroll(coins, plot);      // '@' has not moved yet this frame
-  unsigned patch[4];                         // 128 look-up bits, one per (lane, round)
+  // Look-up bits, one pattern ROW per lane: lanes 0..19 = row k of the 5x5 wall
+  // patch of walker w (lane = 5 w + k; covers every cell any _check_motion of this
+  // step can consult, wherever the scroll order moves the walker first), lanes
+  // 20..22 = the 3 rows of the coin patch around the player, lane 23 = the coin
+  // bit at the pre-scroll corner (an off-board player sits at (0, 0)).
+  unsigned rowbits = 0;
+  {
+    const uint32_t* row = nullptr;
+    int c_first = 0, limit = 0;              // first pattern column, words in the row
+    if (lane < 20) {
+      const int w = lane / 5, k = lane - w * 5;
+      const int pr = wr + rec[w * PCL_SPRITE_WORDS + PCL_S_VROW] + k - 2;
+      c_first = wc + rec[w * PCL_SPRITE_WORDS + PCL_S_VCOL] - 2;
+      if ((unsigned)pr < (unsigned)p.PH) { row = wall_pat + (int64_t)pr * PWW; limit = PWW; }
+    } else if (lane < 23) {
+      const int r = p_vrow + (lane - 20) - 1;
+      c_first = coins.pre_c + p_vcol - 1;
+      if ((unsigned)r < (unsigned)H) { row = coin_pat + (int64_t)(coins.pre_r + r) * PWW; limit = PWW; }
+    } else if (lane == 23) {
+      c_first = coins.pre_c;
+      row = coin_pat + (int64_t)coins.pre_r * PWW; limit = PWW;
+    }
+    if (row != nullptr) {
+      const int wi = c_first >> 5;           // floor, may be -1
+      const uint32_t lo = (unsigned)wi < (unsigned)limit ? row[wi] : 0u;
+      const uint32_t hi = (unsigned)(wi + 1) < (unsigned)limit ? row[wi + 1] : 0u;
+      rowbits = __funnelshift_r(lo, hi, c_first & 31) & 31u;
+    }
+  }
+  // Pattern columns past PW are zero padding and negative ones read as zero, so
+  // the wall bits need no further masking; coin bits are masked to the board.
+  unsigned field = 0;                        // my walker's 5x5 patch, bit (dr+2)*5 + dc+2
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int j = q * 32 + lane;
-    bool bit = false;
-    if (j < 100) {                           // wall patch of walker j / 25
-      const int i = j / 25, k = j - i * 25;
-      int vr = vr0[0], vc = vc0[0];
+  for (int k = 0; k < 5; ++k) field |= __shfl_sync(PCL_FULL, rowbits, me * 5 + k) << (5 * k);
+  unsigned coin9 = 0;                        // 3x3 around the player's start + the (0,0) cell
+  {
+    unsigned colmask = 0;
 #pragma unroll
-      for (int t = 1; t < kS; ++t) if (i == t) { vr = vr0[t]; vc = vc0[t]; }
-      const int pr = wr + vr + k / 5 - 2, pc = wc + vc + k % 5 - 2;
+    for (int i = 0; i < 3; ++i)
+      colmask |= ((unsigned)(p_vcol - 1 + i) < (unsigned)W ? 1u : 0u) << i;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) coin9 |= (__shfl_sync(PCL_FULL, rowbits, 20 + k) & colmask) << (3 * k);
+    coin9 |= (__shfl_sync(PCL_FULL, rowbits, 23) & 1u) << 9;
+  }
+
+  // ---- 4a. update group 1: patrollers a, b, c then P, ONE WALKER PER LANE ----
+  // The four walkers do not interact within a frame: each reads the board of
+  // render #1 (walls at the new corner, P painted where the previous render put it)
+  // and the shared plot; P moves last, so patrollers compare with its OLD virtual
+  // position.  (sprites.py:356-477, scrolly_maze.py:258-305.)
+  const int r0 = mine.vrow, c0 = mine.vcol;
+  const bool is_p = me == 0;
+  const bool even = (plot.frame % 2) == 0;
+  if (even) scrolly_touch_prescroll(walls, plot);           // PatrollerSprite :291
+  int my_err = 0;
+  bool hit = false;
+  int mot;                                   // this lane's motion this frame
+  if (is_p) {
+    mot = motion;                            // PCL_M_NONE: P does not move at all (:258)
+  } else if (!even) {
+    mot = PCL_M_STAY;
+  } else {
+    const int step = mine.aux0 ? 1 : -1;
+    int pr = r0 + walls.pre_r, pc = c0 + walls.pre_c + step;
+    bool next_to_wall = false;
+    if ((unsigned)pr < (unsigned)p.PH && (unsigned)pc < (unsigned)p.PW) {
+      // Same cell seen from the post-scroll corner: inside the 5x5 patch.
+      const int dr = pr - wr - r0 + 2, dc = pc - wc - c0 + 2;
+      next_to_wall = (field >> (dr * 5 + dc)) & 1u;
+    } else {
+      // NumPy indexing: negatives wrap once, anything else is an IndexError.
+      if (pr < 0) pr += p.PH;
+      if (pc < 0) pc += p.PW;
       if ((unsigned)pr < (unsigned)p.PH && (unsigned)pc < (unsigned)p.PW)
-        bit = bit_at(wall_pat + (int64_t)pr * PWW, pc);
-    } else if (j < 110) {                    // coin patch around the player
-      const int k = j - 100;
-      int r = k < 9 ? vr0[0] + k / 3 - 1 : 0, c = k < 9 ? vc0[0] + k % 3 - 1 : 0;
-      if (on_board(r, c, H, W))
-        bit = bit_at(coin_pat + (int64_t)(coins.pre_r + r) * PWW, coins.pre_c + c);
+        next_to_wall = bit_at(wall_pat + (int64_t)pr * PWW, pc);
+      else
+        my_err |= PCL_ENV_ERR_INDEX;
     }
-    patch[q] = __ballot_sync(PCL_FULL, bit);
+    if (next_to_wall) mine.aux0 = !mine.aux0;
+    mot = mine.aux0 ? PCL_M_E : PCL_M_W;
   }
-  unsigned wall5[kS];                        // 25-bit 5x5 patches
-  wall5[0] = patch[0] & 0x1ffffffu;
-  wall5[1] = __funnelshift_r(patch[0], patch[1], 25) & 0x1ffffffu;
-  wall5[2] = __funnelshift_r(patch[1], patch[2], 18) & 0x1ffffffu;
-  wall5[3] = __funnelshift_r(patch[2], patch[3], 11) & 0x1ffffffu;
-  const unsigned coin9 = (patch[3] >> 4) & 0x3ffu;     // 3x3 + the (0,0) cell
-
-  // Board of render #1 as far as MazeWalkers care: is cell (r, c) a '#'?
-  // P is still painted where the previous render put it.
-  const bool p_vis = visible(sp[0]);
-  const int p_row = sp[0].row, p_col = sp[0].col;
-
-  // ---- 4a. update group 1: patrollers a, b, c then P ---------------------
-  const int p_vrow = sp[0].vrow, p_vcol = sp[0].vcol;   // P moves after them
-#pragma unroll
-  for (int i = 0; i < kS; ++i) {
-    const int idx = (i + 1) & 3;             // order a, b, c, P = 1, 2, 3, 0
-    const unsigned field = wall5[idx];
-    const int r0 = vr0[idx], c0 = vc0[idx];
-    auto is_wall = [&](int r, int c) -> bool {
-      if (p_vis && r == p_row && c == p_col) return false;
-      const int dr = r - r0 + 2, dc = c - c0 + 2;
-      if ((unsigned)dr > 4u || (unsigned)dc > 4u) return false;   // cannot happen
-      return (field >> (dr * 5 + dc)) & 1u;
-    };
-    if (idx != 0) {                          // PatrollerSprite :284-305
-      if (plot.frame % 2) {
-        walker_move(sp[idx], idx, PCL_M_STAY, plot, H, W, false, false, lane, is_wall);
-      } else {
-        scrolly_touch_prescroll(walls, plot);
-        const int step = sp[idx].aux0 ? 1 : -1;
-        int pr = r0 + walls.pre_r, pc = c0 + walls.pre_c + step;
-        bool next_to_wall = false;
-        if ((unsigned)pr < (unsigned)p.PH && (unsigned)pc < (unsigned)p.PW) {
-          // Same cell seen from the post-scroll corner: inside the 5x5 patch.
-          const int dr = pr - wr - r0 + 2, dc = pc - wc - c0 + 2;
-          next_to_wall = (field >> (dr * 5 + dc)) & 1u;
-        } else {
-          // NumPy indexing: negatives wrap once, anything else is an IndexError.
-          if (pr < 0) pr += p.PH;
-          if (pc < 0) pc += p.PW;
-          if ((unsigned)pr < (unsigned)p.PH && (unsigned)pc < (unsigned)p.PW)
-            next_to_wall = bit_at(wall_pat + (int64_t)pr * PWW, pc);
-          else
-            plot.error |= PCL_ENV_ERR_INDEX;
-        }
-        if (next_to_wall) sp[idx].aux0 = !sp[idx].aux0;
-        walker_move(sp[idx], idx, sp[idx].aux0 ? PCL_M_E : PCL_M_W, plot, H, W, false,
-                    false, lane, is_wall);
-        if (sp[idx].vrow == p_vrow && sp[idx].vcol == p_vcol) terminate(dir);
-      }
-    } else if (motion != PCL_M_NONE) {       // PlayerSprite :258-271
-      walker_move(sp[0], 0, motion, plot, H, W, false, true, lane, is_wall);
+  if (mot != PCL_M_NONE) {                   // sprites.py:356-389 `_move`
+    const int dr = motion_dr(mot), dc = motion_dc(mot);
+    if (ordered) {                           // _obey_scrolling_order :413-454
+      walker_teleport(mine, H, W, mine.vrow - plot.order_r, mine.vcol - plot.order_c);
+      if (is_p && plot.order_r != dr && plot.order_c != dc) my_err |= PCL_ENV_ERR_ORDER_MISMATCH;
+    }
+    bool legal = true;
+    unsigned blk = 0;
+    if (mot != PCL_M_STAY || is_p) {
+      blk = blocked3x3(mine.vrow, mine.vcol, r0, c0, field, H, W, p_vis, p_row, p_col);
+      legal = motion_legal(blk, mot);
+    }
+    if (legal && mot != PCL_M_STAY) {
+      walker_teleport(mine, H, W, mine.vrow + dr, mine.vcol + dc);      // _raw_move :391
+      if (is_p) blk = blocked3x3(mine.vrow, mine.vcol, r0, c0, field, H, W, p_vis, p_row, p_col);
+    }
+    if (is_p) {                              // :456-477 + scrolling.py:373-434
+      const int valid_at = plot.frame + 1;
+      if (mine.aux1 != valid_at) { mine.aux1 = valid_at; mine.aux0 = 0; }
+      mine.aux0 |= legal_motions(blk);
+    } else if (even) {
+      hit = mine.vrow == p_vrow && mine.vcol == p_vcol;     // PatrollerSprite :303-305
     }
   }
+  if (lane < 4) {                            // write my walker back
+    int32_t* r = rec + me * PCL_SPRITE_WORDS;
+    r[PCL_S_ROW] = mine.row; r[PCL_S_COL] = mine.col;
+    r[PCL_S_VROW] = mine.vrow; r[PCL_S_VCOL] = mine.vcol;
+    r[PCL_S_FLAGS] = mine.flags; r[PCL_S_AUX0] = mine.aux0;
+    if (is_p) r[PCL_S_AUX1] = mine.aux1;
+  }
+  if (motion != PCL_M_NONE) plot.ego_mask |= 1;             // sprites.py:443 (P only)
+  plot.error |= __reduce_or_sync(PCL_FULL, (unsigned)(lane < 4 ? my_err : 0));
+  if (__any_sync(PCL_FULL, lane < 4 && hit)) terminate(dir);
+  // The player after its move, for everything below.
+  Sprite pl;
+  pl.row = __shfl_sync(PCL_FULL, mine.row, 0); pl.col = __shfl_sync(PCL_FULL, mine.col, 0);
+  pl.vrow = __shfl_sync(PCL_FULL, mine.vrow, 0); pl.vcol = __shfl_sync(PCL_FULL, mine.vcol, 0);
+  pl.flags = __shfl_sync(PCL_FULL, mine.flags, 0);
+  pl.aux0 = __shfl_sync(PCL_FULL, mine.aux0, 0); pl.aux1 = __shfl_sync(PCL_FULL, mine.aux1, 0);
 
   // ---- 4b. update group 2: '@' CashDrape (scrolly_maze.py:341-364) -------
   int picked_r = -1, picked_c = -1;          // pattern cell cleared this frame
   {
-    const int dr = sp[0].row - vr0[0], dc = sp[0].col - vc0[0];
+    const int dr = pl.row - p_vrow, dc = pl.col - p_vcol;
     bool coin;
-    const int pr = coins.pre_r + sp[0].row, pc = coins.pre_c + sp[0].col;
-    if (sp[0].row == 0 && sp[0].col == 0 && !on_board(sp[0].vrow, sp[0].vcol, H, W))
+    const int pr = coins.pre_r + pl.row, pc = coins.pre_c + pl.col;
+    if (pl.row == 0 && pl.col == 0 && !on_board(pl.vrow, pl.vcol, H, W))
       coin = (coin9 >> 9) & 1u;              // off-board player sits at (0, 0)
     else if ((unsigned)(dr + 1) <= 2u && (unsigned)(dc + 1) <= 2u)
       coin = (coin9 >> ((dr + 1) * 3 + dc + 1)) & 1u;
@@ -333,11 +473,11 @@ scrolly_maze_step(const StepParams p) {
       picked_r = pr; picked_c = pc;
       plot.aux0 -= 1;
       if (plot.aux0 == 0) terminate(dir);
-      coins.aux0 = sp[0].row; coins.aux1 = sp[0].col;   // stale until next refresh
+      coins.aux0 = pl.row; coins.aux1 = pl.col;         // stale until next refresh
     }
   }
   if (motion != PCL_M_NONE) {
-    scrolly_move(coins, ccfg, motion, plot, sp);
+    scrolly_move_p(coins, ccfg, motion, plot, pl.row, pl.col, pl.aux0, pl.aux1);
     coins.aux0 = -1; coins.aux1 = -1;                    // _update_curtain :689
   } else if (action == 5) {
     terminate(dir);
@@ -347,14 +487,6 @@ scrolly_maze_step(const StepParams p) {
   cp_async_wait_all();
   __syncwarp();
   if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < kS; ++i) {
-      int32_t* r = rec + i * PCL_SPRITE_WORDS;
-      r[PCL_S_ROW] = sp[i].row; r[PCL_S_COL] = sp[i].col;
-      r[PCL_S_VROW] = sp[i].vrow; r[PCL_S_VCOL] = sp[i].vcol;
-      r[PCL_S_FLAGS] = sp[i].flags; r[PCL_S_AUX0] = sp[i].aux0;
-      if (i == 0) r[PCL_S_AUX1] = sp[i].aux1;
-    }
     int32_t* r = rec + 32;
     r[PCL_D_CORNER_R] = walls.corner_r; r[PCL_D_CORNER_C] = walls.corner_c;
     r[PCL_D_PRE_R] = walls.pre_r; r[PCL_D_PRE_C] = walls.pre_c;
@@ -399,7 +531,6 @@ scrolly_maze_step(const StepParams p) {
   // aligned to the board: each lane shifts whole rows once, so the streaming loop
   // below does no bit addressing at all.  Cells past W and the stale coin
   // (drapes.py:689 has not refreshed the curtain yet) are folded in here.
-  const int pitch = p.pitch;
   const int spr = pitch >> 4;                // 16-byte segments per row
   uint32_t* s_seg = s_coin + H * 4;
   {
@@ -425,23 +556,24 @@ scrolly_maze_step(const StepParams p) {
     }
   }
   // a, b, c lie under both drapes, so they are patched into the staged backdrop
-  // up front (in z-order, by one lane); the player is the top layer and is
-  // patched into the one segment that holds it.
+  // up front, in z-order (a lane each, one after the other); the player is the top
+  // layer and is patched into the one segment that holds it.
   __syncwarp();
-  if (lane == 0) {
-    if (coins.aux0 >= 0) s_seg[coins.aux0 * spr + (coins.aux1 >> 4)] |= 1u << (coins.aux1 & 15);
+  if (lane == 0 && coins.aux0 >= 0)
+    s_seg[coins.aux0 * spr + (coins.aux1 >> 4)] |= 1u << (coins.aux1 & 15);
 #pragma unroll
-    for (int i = 1; i < kS; ++i)
-      if (visible(sp[i])) s_bd[sp[i].row * pitch + sp[i].col] = p.sprite_char[i];
+  for (int i = 1; i < kS; ++i) {
+    if (lane == i && visible(mine)) s_bd[mine.row * pitch + mine.col] = p.sprite_char[i];
+    __syncwarp();
   }
-  __syncwarp();
+  __syncthreads();                           // s_sel has landed for every warp of the block
   // 5b. The streaming loop: 16 cells per lane per iteration, segment index ==
   // 16-byte index into both the staged tile and the board (pitch = 16 * spr).
   const int total = H * spr;
-  const int p_seg = visible(sp[0]) ? sp[0].row * spr + (sp[0].col >> 4) : -1;
-  const int p_word = (sp[0].col & 15) >> 2;
-  const uint32_t p_keep = ~(0xffu << ((sp[0].col & 3) * 8));
-  const uint32_t p_char = (uint32_t)p.sprite_char[0] << ((sp[0].col & 3) * 8);
+  const int p_seg = visible(pl) ? pl.row * spr + (pl.col >> 4) : -1;
+  const int p_word = (pl.col & 15) >> 2;
+  const uint32_t p_keep = ~(0xffu << ((pl.col & 3) * 8));
+  const uint32_t p_char = (uint32_t)p.sprite_char[0] << ((pl.col & 3) * 8);
   const unsigned drape_chars = ('#' << 8) | '@';           // bytes 4 and 5 of the permute
   const uint4* src = reinterpret_cast<const uint4*>(s_bd);
   uint4* dst = reinterpret_cast<uint4*>(p.out.d_board + (int64_t)env * H * pitch);

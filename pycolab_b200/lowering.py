@@ -68,6 +68,52 @@ _PROGRAM_OF = {'scrolly': _lib.PROG_SCROLLY_MAZE, 'warehouse': _lib.PROG_WAREHOU
                'marauders': _lib.PROG_MARAUDERS}
 
 
+def source_fingerprint(text):
+  """sha256 over the token stream of `text` (a class definition): comments,
+  blank lines and the amount of indentation do not count, everything else does."""
+  import hashlib
+  import io
+  import textwrap
+  import tokenize
+  skip = (tokenize.COMMENT, tokenize.NL, tokenize.NEWLINE, tokenize.ENCODING,
+          tokenize.ENDMARKER)
+  h = hashlib.sha256()
+  for tok in tokenize.generate_tokens(io.StringIO(textwrap.dedent(text)).readline):
+    if tok.type in skip:
+      continue
+    if tok.type in (tokenize.INDENT, tokenize.DEDENT):
+      h.update(b'<%d>' % tok.type)
+    else:
+      h.update(tok.string.encode('utf-8') + b'\0')
+  return h.hexdigest()
+
+
+def _is_known_implementation(klass, key):
+  """Is `klass` one of the implementations the device program was written from?
+
+  Classes of this package (`pycolab_b200.games.*`: set-up twins whose update()
+  only says "runs on the device") are trusted by module.  Any other module —
+  the reference's own example file loaded through `compat`, or a user's copy of
+  it — must match the reference's source for that class token for token: a copy
+  with an edited update() (another reward, rule or termination) would otherwise
+  be silently replaced by the stock kernel."""
+  if klass.__module__.startswith('pycolab_b200.'):
+    return True
+  from pycolab_b200 import _fingerprints
+  want = _fingerprints.KNOWN.get(key)
+  if want is None:
+    return False
+  import inspect
+  try:
+    text = inspect.getsource(klass)
+  except (OSError, TypeError):
+    return False
+  try:
+    return source_fingerprint(text) == want
+  except Exception:              # noqa: BLE001 - unparsable source is not a known class
+    return False
+
+
 def role_of(entity):
   """Device role of `entity`, or raise NotLoweredError."""
   cls = type(entity)
@@ -78,6 +124,11 @@ def role_of(entity):
         raise NotLoweredError(
             '{} overrides update() of the lowered class {}.{}'.format(
                 cls.__name__, *key))
+      if not _is_known_implementation(klass, key):
+        raise NotLoweredError(
+            'class {}.{} is named like the lowered class {}.{} but its source differs '
+            'from the implementation the device program restates; edited copies are not '
+            'replaced by the stock kernel'.format(klass.__module__, klass.__name__, *key))
       return LOWERED_CLASSES[key]
   raise NotLoweredError(
       'no device program for entity class {}.{} (character {!r}); lowered classes: '
@@ -237,7 +288,8 @@ def _common(engine, game, program):
   if type(backdrop).update is not things.Backdrop.update:
     for klass in type(backdrop).__mro__:
       key = (klass.__module__.rsplit('.', 1)[-1], klass.__name__)
-      if key in LOWERED_BACKDROPS and type(backdrop).update is klass.update:
+      if (key in LOWERED_BACKDROPS and type(backdrop).update is klass.update and
+          _is_known_implementation(klass, key)):
         game.backdrop_role = LOWERED_BACKDROPS[key]
         break
     else:

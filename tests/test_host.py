@@ -357,6 +357,28 @@ def test_reference_scrolly_maze_example_loads_and_lowers(compat_examples):
 
 
 @needs_ref
+def test_edited_copy_of_an_example_is_refused_not_replaced(compat_examples, tmp_path):
+  """A user's copy of scrolly_maze.py lowers while it is token-for-token the
+  reference's; with an edited update() (reward 7 instead of 100) the class is
+  named like a lowered class but is NOT that class: NotLoweredError, never the
+  stock kernel (lowering._is_known_implementation)."""
+  from pycolab_b200 import compat
+  from pycolab_b200.errors import NotLoweredError
+  src = open(os.path.join(refdriver.REFERENCE_ROOT, 'pycolab', 'examples',
+                          'scrolly_maze.py')).read()
+  same = tmp_path / 'same' / 'scrolly_maze.py'
+  same.parent.mkdir()
+  same.write_text('# my copy\n' + src.replace('\n\n', '\n\n\n', 1))   # comments/blank lines only
+  lowering.lower(compat.load_example(str(same)).make_game(0))
+  assert 'the_plot.add_reward(100)' in src
+  edited = tmp_path / 'edited' / 'scrolly_maze.py'
+  edited.parent.mkdir()
+  edited.write_text(src.replace('the_plot.add_reward(100)', 'the_plot.add_reward(7)'))
+  with pytest.raises(NotLoweredError, match='source differs'):
+    lowering.lower(compat.load_example(str(edited)).make_game(0))
+
+
+@needs_ref
 def test_reference_warehouse_example_loads_and_lowers(compat_examples):
   mod = compat_examples('warehouse_manager')
   for level in (0, 1, 2):

@@ -1,0 +1,11 @@
+#!/bin/bash
+# Retry a gpurun call while the pod answers "busy" (exit code 3: nothing charged).
+#   tools/gpurun_retry.sh <timeout-seconds> '<command>' [extra gpurun flags...]
+t=$1; shift; cmd=$1; shift
+for i in $(seq 1 40); do
+  /usr/local/graft/bin/gpurun "$@" --timeout "$t" -- "$cmd"
+  rc=$?
+  if [ $rc -ne 3 ]; then exit $rc; fi
+  sleep 90
+done
+exit 3
