@@ -83,6 +83,15 @@ enum { PCL_CLASSIC_FOUR_ROOMS = 0, /* four_rooms.py:52-80; program_arg[1..2] = g
                                       first / end row of the flowing backdrop band (1, 4); the
                                       rotation count is plot word PCL_P_AUX0 */ };
 
+/* Plot directives as action words of PCL_PROG_FIXTURE (plot.py:136-260). */
+#define PCL_FIXTURE_DIRECTIVES 4
+enum { PCL_DIR_NONE = 0,
+       PCL_DIR_ADD_REWARD = 1,        /* arg = int32 reward (plot.py:201-214) */
+       PCL_DIR_TERMINATE = 2,         /* arg = f32 bits of the discount in [0, 1] (plot.py:176-199) */
+       PCL_DIR_DEFAULT_DISCOUNT = 3,  /* arg = f32 bits (plot.py:247-260; upstream resets the default
+                                         to 1.0 after every step, plot.py:345-356) */
+       PCL_DIR_Z_ORDER = 4 };         /* arg = move_this | in_front_of << 8, 0 = None (plot.py:136-174) */
+
 /* Motion codes (prefab_parts/sprites.py:140-150). */
 enum { PCL_M_N = 0, PCL_M_NE, PCL_M_E, PCL_M_SE, PCL_M_S, PCL_M_SW, PCL_M_W,
        PCL_M_NW, PCL_M_STAY, PCL_M_NONE = -1 };
@@ -170,7 +179,8 @@ typedef struct pcl_outputs {
   uint8_t* d_board;       /* u8 [B, rows, pitch]; Observation.board */
   int32_t* d_reward;      /* i32 [B]; summed reward (plot.py:201-214), 0 if none */
   uint8_t* d_has_reward;  /* u8 [B]; 0 = reference returned reward None */
-  float*   d_discount;    /* f32 [B]; 1.0 running / 0.0 terminated (plot.py:104,176) */
+  float*   d_discount;    /* f32 [B]; 1.0 running / 0.0 terminated unless a directive said otherwise
+                             (plot.py:104,176-199,247-260) */
   uint8_t* d_done;        /* u8 [B]; Engine.game_over after this step */
 } pcl_outputs;
 
@@ -193,9 +203,10 @@ int pcl_reset(pcl_handle* h, const uint8_t* d_env_mask, const pcl_outputs* out,
 /* Engine.play(actions) (engine.py:583-639) for all envs in lockstep: one fused
  * kernel = _update_and_render + _apply_and_clear_plot.  d_actions is
  * i32 [B, actions_per_env]: actions_per_env = 1 for the example games;
- * PCL_PROG_FIXTURE takes n_sprites + n_drapes + 4 words per env: one motion code
- * per entity in update order, then reward (INT32_MIN = none), terminate (0/1),
- * z_move_this (char or -1), z_in_front_of (char, 0 = None). */
+ * PCL_PROG_FIXTURE takes n_sprites + n_drapes + 2 * PCL_FIXTURE_DIRECTIVES words per
+ * env: one motion code per entity in update order, then PCL_FIXTURE_DIRECTIVES
+ * (opcode, argument) pairs — the Plot directives the entities issued this step, in
+ * call order (the last discount-setting call wins, as upstream). */
 int pcl_step(pcl_handle* h, const int32_t* d_actions, const pcl_outputs* out,
              void* stream);
 
@@ -254,6 +265,16 @@ int pcl_render(pcl_handle* h, const uint8_t* d_backdrop, int64_t backdrop_bstrid
 /* Byte-per-cell view of drape `drape_index`'s current curtain (Drape.curtain,
  * things.py:213-217): u8 [B, rows, pitch]. */
 int pcl_export_curtain(pcl_handle* h, int drape_index, uint8_t* d_out, void* stream);
+
+/* Layers of BaseUnoccludedObservationRenderer (rendering.py:187-301, selected by
+ * Engine(occlusion_in_layers=False), engine.py:564-570) for the whole batch: plane k
+ * of d_out u8 [B, n_chars, rows, pitch] is 1 wherever the owner of chars[k] places it,
+ * occluded or not — the backdrop where it holds that character, a drape's whole
+ * curtain, a visible sprite's cell.  `chars` is a HOST array of n_chars <= 32 ASCII
+ * codes.  PCL_ERR_UNSUPPORTED for programs whose drape curtain is implicit
+ * (warehouse 'X', aperture). */
+int pcl_layers(pcl_handle* h, const uint8_t* chars, int32_t n_chars, uint8_t* d_out,
+               void* stream);
 
 /* ScrollingCropper.crop (cropping.py:393-426): track sprite `sprite_index`,
  * update the per-env window corner and copy the crop_rows x crop_cols window of

@@ -18,6 +18,8 @@ SPRITE_WORDS = 8
 DRAPE_WORDS = 8
 PLOT_WORDS = 16
 MT_WORDS = 625
+FIXTURE_DIRECTIVES = 4       # (opcode, argument) pairs per PROG_FIXTURE action row
+DIR_NONE, DIR_ADD_REWARD, DIR_TERMINATE, DIR_DEFAULT_DISCOUNT, DIR_Z_ORDER = range(5)
 HOST_SLOTS = 8               # pcl_step_host_async completion slots
 NEVER = -(2 ** 31)           # INT32_MIN: "-inf"/None frame
 ACTION_NONE = -1
@@ -140,6 +142,7 @@ SYMBOLS = {
     'pcl_last_error': (C.c_char_p, [C.c_void_p]),
     'pcl_render': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                              C.c_void_p, C.c_void_p, C.c_void_p]),
+    'pcl_layers': (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.c_void_p, C.c_void_p]),
     'pcl_export_curtain': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     'pcl_crop': (C.c_int, [C.c_void_p, C.POINTER(CropSpec), C.c_void_p, C.c_void_p,
                            C.c_void_p, C.c_void_p]),

@@ -139,7 +139,8 @@ class BatchedEngine(object):
       self._z_init = tiled(zs, np.uint8)
       st.d_z_order, st.d_z_order_init = self.z_order.data_ptr(), self._z_init.data_ptr()
       st.z_order_init_bstride = bstride(self._z_init)
-    self.actions_per_env = (len(g0.sprite_chars) + len(g0.drape_chars) + 4
+    self.actions_per_env = (len(g0.sprite_chars) + len(g0.drape_chars) +
+                            2 * _lib.FIXTURE_DIRECTIVES
                             if g0.program == _lib.PROG_FIXTURE else 1)
     self.rng = None
     if g0.needs_rng:
@@ -334,6 +335,19 @@ class BatchedEngine(object):
       _lib.check(self._lib.pcl_export_curtain(self._h, d, out.data_ptr(), self._stream()),
                  'pcl_export_curtain', self._h)
     return out
+
+  def unoccluded_layers(self, chars=None):
+    """Layers of `BaseUnoccludedObservationRenderer` (rendering.py:187-301) for
+    every env: bool [B, len(chars), rows, cols], plane k = everywhere the owner of
+    chars[k] places it, occluded or not.  Default chars: every character of the
+    game, sorted (`self.chars`).  One kernel over the packed device state."""
+    torch = _torch()
+    chars = self.chars if chars is None else ''.join(chars)
+    out = torch.empty((self.batch, len(chars), self.rows, self.pitch), dtype=torch.uint8,
+                      device=self.device)
+    _lib.check(self._lib.pcl_layers(self._h, chars.encode('ascii'), len(chars), out.data_ptr(),
+                                    self._stream()), 'pcl_layers', self._h)
+    return out[:, :, :, :self.cols].bool()
 
   def error_codes(self):
     torch = _torch()

@@ -295,7 +295,7 @@ int pcl_create(const pcl_spec* spec, int batch, int device, pcl_handle** out) {
   h->batch = batch;
   h->device = device;
   h->bound = 0;
-  h->actions_per_env = spec->program == PCL_PROG_FIXTURE ? spec->n_sprites + spec->n_drapes + 4 : 1;
+  h->actions_per_env = spec->program == PCL_PROG_FIXTURE ? spec->n_sprites + spec->n_drapes + 2 * PCL_FIXTURE_DIRECTIVES : 1;
   h->launches = 0;
   h->last_error[0] = 0;
   h->host_ready = 0;
@@ -547,6 +547,47 @@ int pcl_export_curtain(pcl_handle* h, int drape_index, uint8_t* d_out, void* str
     return PCL_ERR_UNSUPPORTED;
   }
   return launched(h, pcl::launch_export_curtain(p, (cudaStream_t)stream), "launch_export_curtain");
+}
+
+int pcl_layers(pcl_handle* h, const uint8_t* chars, int32_t n_chars, uint8_t* d_out,
+               void* stream) {
+  if (!h || !chars || !d_out || n_chars < 1 || n_chars > PCL_MAX_LAYER_CHARS)
+    return PCL_ERR_INVALID;
+  if (!h->bound) return PCL_ERR_UNBOUND;
+  const pcl_spec& sp = h->spec;
+  pcl::LayersParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = h->batch; p.H = sp.rows; p.W = sp.cols; p.pitch = sp.pitch;
+  p.S = sp.n_sprites; p.D = sp.n_drapes; p.n_chars = n_chars;
+  p.backdrop = h->st.d_backdrop; p.backdrop_bstride = h->st.backdrop_bstride;
+  p.level = h->st.d_level; p.sprites = h->st.d_sprites; p.drapes = h->st.d_drapes;
+  p.out = d_out;
+  for (int d = 0; d < sp.n_drapes; ++d) {
+    // Where each program keeps a drape's curtain (as pcl_export_curtain).
+    if (sp.program == PCL_PROG_SCROLLY_MAZE ||
+        (sp.program == PCL_PROG_FIXTURE && sp.drape_kind[d])) {
+      p.scrolly[d] = 1;
+      p.bits[d] = h->st.d_pattern[d]; p.bits_bstride[d] = h->st.pattern_bstride[d];
+      p.row_words[d] = sp.pattern_words;
+      const bool coins = sp.program == PCL_PROG_SCROLLY_MAZE && d == 1;
+      p.stale_slot[d] = coins;
+      p.per_level[d] = !coins && h->st.d_level != nullptr;   // read-only patterns: per level
+    } else if (sp.program == PCL_PROG_MARAUDERS || sp.program == PCL_PROG_BETTER_SCROLLY ||
+               sp.program == PCL_PROG_FIXTURE) {
+      p.bits[d] = h->st.d_bits[d]; p.bits_bstride[d] = h->st.bits_bstride[d];
+      p.row_words[d] = sp.bits_words;
+    } else {
+      return PCL_ERR_UNSUPPORTED;       // curtain held implicitly (warehouse 'X', aperture)
+    }
+    if (!p.bits[d]) return PCL_ERR_INVALID;
+  }
+  for (int k = 0; k < n_chars; ++k) {
+    p.chars[k] = chars[k];
+    p.sprite_of[k] = -1; p.drape_of[k] = -1;
+    for (int s = 0; s < sp.n_sprites; ++s) if (sp.sprite_char[s] == chars[k]) p.sprite_of[k] = (int8_t)s;
+    for (int d = 0; d < sp.n_drapes; ++d) if (sp.drape_char[d] == chars[k]) p.drape_of[k] = (int8_t)d;
+  }
+  return launched(h, pcl::launch_layers(p, (cudaStream_t)stream), "launch_layers");
 }
 
 int pcl_crop(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d_board, uint8_t* d_crop,

@@ -17,9 +17,11 @@
 // group (engine.py:735) is materialised in shared memory, because an arbitrary
 // walker may test any character.  One warp per env; speed is not the point.
 //
-// Action row (i32 [n_entities + 4]): motion code per entity in UPDATE order,
-// then reward (INT32_MIN = none), terminate (0/1), z_move_this (char or -1),
-// z_in_front_of (char, 0 = None).
+// Action row (i32 [n_entities + 2 * PCL_FIXTURE_DIRECTIVES]): motion code per entity
+// in UPDATE order, then up to PCL_FIXTURE_DIRECTIVES (opcode, argument) pairs applied
+// in order, i.e. in the order the entities issued them (include/pcl.h PCL_DIR_*):
+// add_reward(int), terminate_episode(f32 discount), change_default_discount(f32),
+// change_z_order(move_this | in_front_of << 8).
 #include "pcl_device.cuh"
 #include "pcl_kernels.cuh"
 
@@ -257,35 +259,47 @@ fixture_step(const StepParams p) {
 
   // ---- Plot directives (plot.py:136-260) + _apply_and_clear_plot (engine.py:761-847)
   if (act) {
-    const int reward = act[n], term = act[n + 1], z_this = act[n + 2], z_that = act[n + 3];
-    if (reward != INT_MIN) add_reward(dir, reward);
-    if (term) terminate(dir);
-    if (z_this >= 0) {
-      bool have_this = false, have_that = (z_that == 0);
-      for (int i = 0; i < n; ++i) {
-        have_this |= st->z[i] == z_this;
-        have_that |= st->z[i] == z_that;
-      }
-      if (!have_this || !have_that) {
-        plot.error |= PCL_ENV_ERR_BAD_Z;     // engine.py:802-812 raises RuntimeError
-      } else {
-        __syncwarp();
-        if (lane == 0) {
-          uint8_t fresh[kMaxEnt];
-          int m = 0;
-          if (z_that == 0) fresh[m++] = (uint8_t)z_this;
-          for (int i = 0; i < n; ++i) {
-            const uint8_t chz = st->z[i];
-            if (chz == z_this) continue;
-            fresh[m++] = chz;
-            if (chz == z_that) fresh[m++] = (uint8_t)z_this;
-          }
-          for (int i = 0; i < n; ++i) st->z[i] = fresh[i];
+    bool z_changed = false;
+    for (int i = 0; i < PCL_FIXTURE_DIRECTIVES; ++i) {
+      const int op = act[n + 2 * i], arg = act[n + 2 * i + 1];
+      if (op == PCL_DIR_ADD_REWARD) {
+        add_reward(dir, arg);                                    // plot.py:201-214
+      } else if (op == PCL_DIR_TERMINATE) {
+        terminate(dir, __int_as_float(arg));                     // plot.py:176-199
+      } else if (op == PCL_DIR_DEFAULT_DISCOUNT) {
+        change_default_discount(dir, __int_as_float(arg));       // plot.py:247-260
+      } else if (op == PCL_DIR_Z_ORDER) {                        // plot.py:136-174
+        const int z_this = arg & 0xff, z_that = (arg >> 8) & 0xff;   // 0 = None (rearmost)
+        bool have_this = false, have_that = (z_that == 0);
+        for (int k2 = 0; k2 < n; ++k2) {
+          have_this |= st->z[k2] == z_this;
+          have_that |= st->z[k2] == z_that;
         }
-        __syncwarp();
-        render(c);                           // should_rerender, engine.py:636
+        // Moving an entity in front of itself makes upstream DROP it from the
+        // catalogue (engine.py:826-832 skips it and never re-inserts it); that is
+        // reported as a bad directive here instead of corrupting the z-order.
+        if (!have_this || !have_that || z_this == z_that) {
+          plot.error |= PCL_ENV_ERR_BAD_Z;   // engine.py:802-812 raises RuntimeError
+        } else {
+          __syncwarp();
+          if (lane == 0) {
+            uint8_t fresh[kMaxEnt];
+            int m = 0;
+            if (z_that == 0) fresh[m++] = (uint8_t)z_this;
+            for (int k2 = 0; k2 < n; ++k2) {
+              const uint8_t chz = st->z[k2];
+              if (chz == z_this) continue;
+              fresh[m++] = chz;
+              if (chz == z_that) fresh[m++] = (uint8_t)z_this;
+            }
+            for (int k2 = 0; k2 < n; ++k2) st->z[k2] = fresh[k2];
+          }
+          __syncwarp();
+          z_changed = true;
+        }
       }
     }
+    if (z_changed) render(c);                // should_rerender, engine.py:636
   }
 
   __syncwarp();

@@ -49,8 +49,13 @@ __device__ __forceinline__ Directives fresh_directives() {
 __device__ __forceinline__ void add_reward(Directives& d, int r) {  // plot.py:201
   d.reward += r; d.has_reward = 1;
 }
-__device__ __forceinline__ void terminate(Directives& d) {          // plot.py:176
-  d.game_over = 1; d.discount = 0.0f;
+__device__ __forceinline__ void terminate(Directives& d, float discount = 0.0f) {  // plot.py:176-199
+  d.game_over = 1; d.discount = discount;
+}
+// plot.py:247-260.  Upstream rebuilds the directives (discount 1.0) after every
+// step (plot.py:345-356, engine.py:845), so the "default" lasts for this step only.
+__device__ __forceinline__ void change_default_discount(Directives& d, float discount) {
+  d.discount = discount;
 }
 
 // ------------------------------------------------------------- MazeWalker --

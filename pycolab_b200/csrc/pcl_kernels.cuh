@@ -64,6 +64,27 @@ struct ExportParams {
 };
 cudaError_t launch_export_curtain(const ExportParams& p, cudaStream_t s);
 
+// Unoccluded layers (rendering.py:187-301): one mask per requested character.
+#define PCL_MAX_LAYER_CHARS 32
+struct LayersParams {
+  int B, H, W, pitch, S, D, n_chars;
+  uint8_t chars[PCL_MAX_LAYER_CHARS];
+  int8_t sprite_of[PCL_MAX_LAYER_CHARS];   // sprite index painting that char, or -1
+  int8_t drape_of[PCL_MAX_LAYER_CHARS];    // drape index painting that char, or -1
+  // per drape: where its curtain lives in the packed state (as ExportParams)
+  const uint32_t* bits[PCL_MAX_DRAPES]; int64_t bits_bstride[PCL_MAX_DRAPES];
+  int row_words[PCL_MAX_DRAPES];           // uint32 words per bit row
+  int scrolly[PCL_MAX_DRAPES];             // 1: window of a pattern at the drape's corner
+  int per_level[PCL_MAX_DRAPES];           // 1: `bits` is static per-level data
+  int stale_slot[PCL_MAX_DRAPES];          // 1: the drape record's AUX0/1 hold a stale cell
+  const uint8_t* backdrop; int64_t backdrop_bstride;
+  const int32_t* level;
+  const int32_t* sprites;
+  const int32_t* drapes;
+  uint8_t* out;                            // u8 [B, n_chars, H, pitch]
+};
+cudaError_t launch_layers(const LayersParams& p, cudaStream_t s);
+
 struct ObserveParams {
   int B, H, W, pitch, depth, dtype;
   int words;                     // 32-bit words per element (2 for int64 / float64)

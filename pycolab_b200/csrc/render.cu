@@ -143,6 +143,56 @@ __global__ void export_curtain_kernel(const ExportParams p) {
   }
 }
 
+// BaseUnoccludedObservationRenderer's layers (rendering.py:187-301): the mask of
+// character k shows where its OWNER places it, occluded or not — a backdrop
+// character where the backdrop holds it (paint_all_of :222-236), a drape's whole
+// curtain (paint_drape :262-282 overwrites the layer), a visible sprite's cell on
+// top of the backdrop term (paint_sprite :238-260).  One block per env streams
+// n_chars planes of H * pitch bytes (0 / 1), 16 cells per thread per store.
+__global__ void __launch_bounds__(256) layers_kernel(const LayersParams p) {
+  const int env = blockIdx.x;
+  const int segs_per_row = p.pitch >> 4;
+  const int plane_segs = p.H * segs_per_row;
+  const int64_t lvl = p.level ? p.level[env] : env;
+  const uint8_t* backdrop = p.backdrop + lvl * p.backdrop_bstride;
+  uint8_t* out = p.out + (int64_t)env * p.n_chars * p.H * p.pitch;
+  for (int i = threadIdx.x; i < p.n_chars * plane_segs; i += blockDim.x) {
+    const int k = i / plane_segs, seg = i - k * plane_segs;
+    const int r = seg / segs_per_row, c0 = (seg - r * segs_per_row) << 4;
+    const int ncols = min(16, p.W - c0);
+    uint4 px = make_uint4(0, 0, 0, 0);
+    const int d = p.drape_of[k];
+    if (d >= 0) {
+      const int32_t* drec = p.drapes + ((int64_t)env * p.D + d) * PCL_DRAPE_WORDS;
+      const int cr = p.scrolly[d] ? drec[PCL_D_CORNER_R] : 0;
+      const int cc = p.scrolly[d] ? drec[PCL_D_CORNER_C] : 0;
+      const uint32_t* bits = p.bits[d] + (p.per_level[d] ? lvl : (int64_t)env) * p.bits_bstride[d];
+      unsigned b = bits16(bits + (int64_t)(cr + r) * p.row_words[d], cc + c0) &
+                   ((1u << ncols) - 1u);
+      if (p.stale_slot[d]) {
+        const int sr = drec[PCL_D_AUX0], sc = drec[PCL_D_AUX1];
+        if (r == sr && (unsigned)(sc - c0) < 16u) b |= 1u << (sc - c0);
+      }
+      paint_bits(px, b, 1);
+    } else {
+      const uint4 bd = *reinterpret_cast<const uint4*>(backdrop + (int64_t)r * p.pitch + c0);
+      const uint32_t ch4 = p.chars[k] * 0x01010101u;
+      px.x = __vcmpeq4(bd.x, ch4) & 0x01010101u; px.y = __vcmpeq4(bd.y, ch4) & 0x01010101u;
+      px.z = __vcmpeq4(bd.z, ch4) & 0x01010101u; px.w = __vcmpeq4(bd.w, ch4) & 0x01010101u;
+      const int sidx = p.sprite_of[k];
+      if (sidx >= 0) {
+        const int32_t* rec = p.sprites + ((int64_t)env * p.S + sidx) * PCL_SPRITE_WORDS;
+        const int dc = rec[PCL_S_COL] - c0;
+        if ((rec[PCL_S_FLAGS] & 1) && rec[PCL_S_ROW] == r && (unsigned)dc < 16u) {
+          uint32_t* w = dc < 4 ? &px.x : dc < 8 ? &px.y : dc < 12 ? &px.z : &px.w;
+          *w |= 1u << ((dc & 3) * 8);
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(out + ((int64_t)k * p.H + r) * p.pitch + c0) = px;
+  }
+}
+
 // (median row, median column) of a byte curtain's cells, as `_centroid` computes
 // them for a Drape (cropping.py:583-596: np.median of the nonzero coordinates,
 // truncated).  Warp-wide; `hist` is this warp's 256-int scratch.  false = empty.
@@ -279,6 +329,10 @@ cudaError_t launch_render(const RenderParams& p, cudaStream_t s) {
 }
 cudaError_t launch_export_curtain(const ExportParams& p, cudaStream_t s) {
   export_curtain_kernel<<<p.B, 128, 0, s>>>(p);
+  return cudaGetLastError();
+}
+cudaError_t launch_layers(const LayersParams& p, cudaStream_t s) {
+  layers_kernel<<<p.B, 256, 0, s>>>(p);
   return cudaGetLastError();
 }
 cudaError_t launch_crop(const CropParams& p, cudaStream_t s) {

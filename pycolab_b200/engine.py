@@ -193,8 +193,11 @@ class Engine(object):
     if self._occlusion_in_layers:
       layers = rendering.LazyLayers(board, self._chars)
     else:
-      layers = rendering.UnoccludedLayers(self._backdrop.curtain,
-                                          dict(self._sprites_and_drapes), self._chars)
+      # BaseUnoccludedObservationRenderer (rendering.py:187-301) on the device:
+      # one kernel paints every character's un-occluded mask from the packed state.
+      order = ''.join(sorted(self._chars))
+      planes = self._batched.unoccluded_layers(order)[0].cpu().numpy()
+      layers = {ch: planes[k] for k, ch in enumerate(order)}
     self._board = rendering.Observation(board=board, layers=layers)
     return self._board, reward, discount
 

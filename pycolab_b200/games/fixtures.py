@@ -14,6 +14,7 @@ builds the reference fixture game, the oracle world and the device game.
 
 import numpy as np
 
+from pycolab_b200 import _lib
 from pycolab_b200 import ascii_art
 from pycolab_b200 import things as plab_things
 from pycolab_b200.prefab_parts import drapes as prefab_drapes
@@ -64,15 +65,46 @@ def make_game(art, what_lies_beneath, walkers, scrollys=None, drapes='',
                                      occlusion_in_layers=occlusion_in_layers)
 
 
-def action_rows(game_or_lowered, motions, reward=None, terminate=False, z=None):
+def action_rows(game_or_lowered, motions, reward=None, terminate=False, z=None,
+                directives=None):
   """One device action row: motions {char: code} (missing = stay) in update
-  order, then the directive words."""
+  order, then the Plot directives of the step as (opcode, argument) pairs.
+
+  directives: ordered list of calls, e.g. [('add_reward', 3),
+  ('terminate_episode', 0.5), ('change_default_discount', 0.9),
+  ('change_z_order', 'b', None)]; or the shorthands reward / terminate / z
+  (applied in that order)."""
+  import struct
   order = ''.join(game_or_lowered.groups)
   row = [int(motions.get(ch, 8)) for ch in order]
-  row.append(NO_REWARD if reward is None else int(reward))
-  row.append(1 if terminate else 0)
-  if z is None:
-    row += [-1, 0]
-  else:
-    row += [ord(z[0]), 0 if z[1] is None else ord(z[1])]
+  if directives is None:
+    directives = []
+    if reward is not None:
+      directives.append(('add_reward', reward))
+    if terminate:
+      directives.append(('terminate_episode', 0.0))
+    if z is not None:
+      directives.append(('change_z_order', z[0], z[1]))
+  if len(directives) > _lib.FIXTURE_DIRECTIVES:
+    raise ValueError('at most {} Plot directives per step are lowered'.format(
+        _lib.FIXTURE_DIRECTIVES))
+  f32 = lambda x: struct.unpack('<i', struct.pack('<f', float(x)))[0]
+  for call in directives:
+    name, args = call[0], call[1:]
+    if name == 'add_reward':
+      row += [_lib.DIR_ADD_REWARD, int(args[0])]
+    elif name == 'terminate_episode':
+      discount = args[0] if args else 0.0
+      if not 0.0 <= discount <= 1.0:
+        raise ValueError('Discount must be in range [0,1].')
+      row += [_lib.DIR_TERMINATE, f32(discount)]
+    elif name == 'change_default_discount':
+      if not 0.0 <= args[0] <= 1.0:
+        raise ValueError('Default discount must be in range [0,1].')
+      row += [_lib.DIR_DEFAULT_DISCOUNT, f32(args[0])]
+    elif name == 'change_z_order':
+      row += [_lib.DIR_Z_ORDER, ord(args[0]) | ((0 if args[1] is None else ord(args[1])) << 8)]
+    else:
+      raise ValueError('unknown Plot directive {!r}'.format(name))
+  row += [_lib.DIR_NONE, 0] * (_lib.FIXTURE_DIRECTIVES - len(directives))
   return row

@@ -46,40 +46,6 @@ class LazyLayers(collections.abc.Mapping):
     return len(self._chars)
 
 
-class UnoccludedLayers(collections.abc.Mapping):
-  """Layers of `BaseUnoccludedObservationRenderer` (rendering.py:187-301): every
-  character's mask shows where its owner PLACES it, hidden or not — backdrop
-  characters where the backdrop holds them, a drape's whole curtain, a visible
-  sprite's cell.  Built on demand from the entity state mirrored off the device."""
-
-  def __init__(self, backdrop, things, chars):
-    self._backdrop = backdrop
-    self._things = things
-    self._chars = frozenset(chars)
-    self._cache = {}
-
-  def __getitem__(self, char):
-    if char not in self._chars:
-      raise KeyError(char)
-    if char not in self._cache:
-      mask = self._backdrop == ord(char)
-      ent = self._things.get(char)
-      if ent is not None:
-        if hasattr(ent, 'curtain'):
-          mask = mask | np.asarray(ent.curtain, dtype=bool)
-        elif ent.visible:
-          mask = mask.copy()
-          mask[tuple(ent.position)] = True
-      self._cache[char] = mask
-    return self._cache[char]
-
-  def __iter__(self):
-    return iter(self._chars)
-
-  def __len__(self):
-    return len(self._chars)
-
-
 class BaseObservationRenderer(object):
   """GPU-backed canvas with the reference's painter API (rendering.py:69-184)."""
 

@@ -26,7 +26,8 @@ def device_game(snap):
   from pycolab_b200 import _lib, batched, engine as engine_lib, lowering, things
   from pycolab_b200.games import fixtures
   backdrop = rk.u8(snap['backdrop'])
-  eng = engine_lib.Engine(snap['rows'], snap['cols'])
+  eng = engine_lib.Engine(snap['rows'], snap['cols'],
+                          occlusion_in_layers=snap.get('occlusion_in_layers', True))
   eng.set_prefilled_backdrop(sorted(set(chr(c) for c in backdrop.ravel())), backdrop,
                              things.Backdrop)
   shape = (snap['rows'], snap['cols'])
@@ -40,7 +41,13 @@ def device_game(snap):
                                 egocentric_scroller=w['egocentric'])
         sprite._virtual_row, sprite._virtual_col = w['virtual_position']
         sprite._visible, sprite._prior_visible = w['visible'], w['prior_visible']
-      elif ch in snap['scrollys']:
+      elif ch in snap.get('sprites', {}):
+        # A plain things.Sprite whose update does nothing (test_things.TestSprite):
+        # a walker that is always told to stay.
+        w = snap['sprites'][ch]
+        sprite = eng.add_sprite(ch, tuple(w['position']), fixtures.FixtureMazeWalker)
+        sprite._visible = w['visible']
+      elif ch in snap.get('scrollys', {}):
         s = snap['scrollys'][ch]
         eng.add_drape(ch, fixtures.FixtureScrolly, board_shape=shape,
                       whole_pattern=rk.bits(s['pattern']),
@@ -54,14 +61,14 @@ def device_game(snap):
   # Registers the entity objects do not carry: pre-scroll corners, the frame, and
   # the default scrolling group's blackboard (protocols/scrolling.py:198-241).
   for d, ch in enumerate(game.drape_chars):
-    if ch in snap['scrollys']:
+    if ch in snap.get('scrollys', {}):
       s = snap['scrollys'][ch]
       game.drapes[d, _lib.D_PRE_R], game.drapes[d, _lib.D_PRE_C] = s['prescroll']
       game.drapes[d, _lib.D_LAST_FRAME] = (_lib.NEVER if s['last_move_frame'] is None
                                            else s['last_move_frame'])
   game.plot[_lib.P_FRAME] = snap['frame']
-  regs = snap['scrolling'].get('', None)
-  assert set(snap['scrolling']) <= {''}, 'only the default scrolling group is lowered'
+  regs = snap.get('scrolling', {}).get('', None)
+  assert set(snap.get('scrolling', {})) <= {''}, 'only the default scrolling group is lowered'
   if regs is not None:
     if regs['order'] is not None:
       game.plot[_lib.P_ORDER_R], game.plot[_lib.P_ORDER_C] = regs['order']
