@@ -40,6 +40,8 @@ extern "C" {
 #define PCL_DRAPE_WORDS 8    /* int32 words per drape record  */
 #define PCL_PLOT_WORDS 16    /* int32 words per env plot record */
 #define PCL_MT_WORDS 625     /* MT19937: 624 state words + position */
+#define PCL_MAX_SCROLL_GROUPS 4 /* scrolling groups of one game (protocols/scrolling.py:198-241) */
+#define PCL_GROUP_WORDS 4    /* int32 words per scrolling-group record */
 
 typedef enum pcl_status {
   PCL_OK = 0,
@@ -118,6 +120,11 @@ enum { PCL_P_FRAME = 0, PCL_P_GAME_OVER, PCL_P_ERROR, PCL_P_EPISODES,
        PCL_P_AUX0, PCL_P_AUX1, PCL_P_AUX2, PCL_P_AUX3,
        PCL_P_CROP_R, PCL_P_CROP_C, PCL_P_CROP_INIT, PCL_P_RESERVED };
 
+/* Scrolling-group record layout, int32[PCL_GROUP_WORDS]: the per-group part of the
+ * blackboard of protocols/scrolling.py:198-241.  Group 0 lives in the plot record
+ * (PCL_P_ORDER_R .. PCL_P_EGO_MASK); groups 1.. in pcl_state.d_groups. */
+enum { PCL_G_ORDER_R = 0, PCL_G_ORDER_C, PCL_G_ORDER_FRAME, PCL_G_EGO_MASK };
+
 /* Static description of one game (what Engine's set-up API collected:
  * engine.py:248-518).  All envs of a handle share it. */
 typedef struct pcl_spec {
@@ -142,6 +149,12 @@ typedef struct pcl_spec {
   uint8_t group_chars[PCL_MAX_SPRITES + PCL_MAX_DRAPES]; /* update order, concatenated */
   int32_t drape_kind[PCL_MAX_DRAPES];      /* 0 = plain bool curtain (d_bits), 1 = Scrolly (d_pattern) */
   int32_t program_arg[8];                  /* per-program constants (see pcl_program); else 0 */
+  /* Scrolling groups (`scrolling_group` of MazeWalker / Scrolly, sprites.py:176,
+   * drapes.py:309): index of each entity's group, 0 .. n_scroll_groups - 1.  Only
+   * PCL_PROG_FIXTURE accepts more than one group; 0 groups means 1. */
+  int32_t n_scroll_groups;
+  int32_t sprite_group[PCL_MAX_SPRITES];
+  int32_t drape_group[PCL_MAX_DRAPES];
 } pcl_spec;
 
 /* Device buffers of one handle (all caller-owned).  A "*_bstride" is the
@@ -165,6 +178,10 @@ typedef struct pcl_state {
   /* per-env z-order (chars, back to front) for programs whose entities issue
    * Plot.change_z_order (engine.py:796-835): u8 [B, n_sprites + n_drapes]; NULL = spec z_order */
   uint8_t* d_z_order;  const uint8_t* d_z_order_init; int64_t z_order_init_bstride;
+  /* Scrolling groups 1 .. n_scroll_groups - 1 (group 0 is in the plot record):
+   * i32 [B, PCL_MAX_SCROLL_GROUPS, PCL_GROUP_WORDS], slot 0 unused; NULL when the
+   * game has a single group. */
+  int32_t* d_groups;   const int32_t* d_groups_init;  int64_t groups_init_bstride;
   /* Level sharing: envs that play the same level need only one copy of its
    * static data.  When d_level (i32 [B]) is non-NULL, every array the step never
    * writes — d_backdrop, read-only patterns, every *_init template — is indexed

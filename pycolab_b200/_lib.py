@@ -18,6 +18,9 @@ SPRITE_WORDS = 8
 DRAPE_WORDS = 8
 PLOT_WORDS = 16
 MT_WORDS = 625
+MAX_SCROLL_GROUPS = 4
+GROUP_WORDS = 4
+G_ORDER_R, G_ORDER_C, G_ORDER_FRAME, G_EGO_MASK = range(4)
 FIXTURE_DIRECTIVES = 4       # (opcode, argument) pairs per PROG_FIXTURE action row
 DIR_NONE, DIR_ADD_REWARD, DIR_TERMINATE, DIR_DEFAULT_DISCOUNT, DIR_Z_ORDER = range(5)
 HOST_SLOTS = 8               # pcl_step_host_async completion slots
@@ -77,6 +80,9 @@ class Spec(C.Structure):
       ('group_chars', C.c_uint8 * _N),
       ('drape_kind', C.c_int32 * MAX_DRAPES),
       ('program_arg', C.c_int32 * 8),
+      ('n_scroll_groups', C.c_int32),
+      ('sprite_group', C.c_int32 * MAX_SPRITES),
+      ('drape_group', C.c_int32 * MAX_DRAPES),
   ]
 
 
@@ -96,6 +102,8 @@ class State(C.Structure):
       ('d_rng', C.c_void_p),
       ('d_z_order', C.c_void_p), ('d_z_order_init', C.c_void_p),
       ('z_order_init_bstride', C.c_int64),
+      ('d_groups', C.c_void_p), ('d_groups_init', C.c_void_p),
+      ('groups_init_bstride', C.c_int64),
       ('d_level', C.c_void_p),
   ]
 

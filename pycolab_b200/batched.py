@@ -139,6 +139,12 @@ class BatchedEngine(object):
       self._z_init = tiled(zs, np.uint8)
       st.d_z_order, st.d_z_order_init = self.z_order.data_ptr(), self._z_init.data_ptr()
       st.z_order_init_bstride = bstride(self._z_init)
+    self.groups = None          # scrolling groups >= 1 (group 0 is in the plot record)
+    if len(g0.scroll_groups) > 1:
+      self.groups = per_env([g.group_records for g in games], np.int32)
+      self._groups_init = tiled([g.group_records for g in games], np.int32)
+      st.d_groups, st.d_groups_init = self.groups.data_ptr(), self._groups_init.data_ptr()
+      st.groups_init_bstride = bstride(self._groups_init)
     self.actions_per_env = (len(g0.sprite_chars) + len(g0.drape_chars) +
                             2 * _lib.FIXTURE_DIRECTIVES
                             if g0.program == _lib.PROG_FIXTURE else 1)

@@ -75,6 +75,17 @@ int validate(const pcl_spec& s) {
   if (s.rows <= 0 || s.cols <= 0 || s.pitch < s.cols || (s.pitch & 15)) return PCL_ERR_INVALID;
   if (s.n_sprites < 0 || s.n_sprites > PCL_MAX_SPRITES) return PCL_ERR_INVALID;
   if (s.n_drapes < 0 || s.n_drapes > PCL_MAX_DRAPES) return PCL_ERR_INVALID;
+  {
+    // Scrolling groups: every entity names one of the declared groups; only the
+    // general program keeps more than one group's blackboard.
+    const int ng = s.n_scroll_groups < 1 ? 1 : s.n_scroll_groups;
+    if (ng > PCL_MAX_SCROLL_GROUPS) return PCL_ERR_UNSUPPORTED;
+    if (ng > 1 && s.program != PCL_PROG_FIXTURE) return PCL_ERR_UNSUPPORTED;
+    for (int i = 0; i < s.n_sprites; ++i)
+      if (s.sprite_group[i] < 0 || s.sprite_group[i] >= ng) return PCL_ERR_INVALID;
+    for (int i = 0; i < s.n_drapes; ++i)
+      if (s.drape_group[i] < 0 || s.drape_group[i] >= ng) return PCL_ERR_INVALID;
+  }
   switch (s.program) {
     case PCL_PROG_NONE:
       return PCL_OK;
@@ -223,6 +234,9 @@ void fill_params(const pcl_handle* h, StepParams* p) {
   memcpy(p->egocentric, s.sprite_egocentric, sizeof(p->egocentric));
   memcpy(p->drape_kind, s.drape_kind, sizeof(p->drape_kind));
   memcpy(p->program_arg, s.program_arg, sizeof(p->program_arg));
+  p->n_scroll_groups = s.n_scroll_groups < 1 ? 1 : s.n_scroll_groups;
+  memcpy(p->sprite_group, s.sprite_group, sizeof(p->sprite_group));
+  memcpy(p->drape_group, s.drape_group, sizeof(p->drape_group));
   p->n_groups = s.n_groups;
   memcpy(p->group_len, s.group_len, sizeof(p->group_len));
   memcpy(p->group_chars, s.group_chars, sizeof(p->group_chars));
@@ -335,6 +349,7 @@ int pcl_bind_state(pcl_handle* h, const pcl_state* st) {
   if (h->spec.program == PCL_PROG_BETTER_SCROLLY) {
     if (!st->d_bits[0] || !st->d_bits_init[0] || st->bits_bstride[0] == 0) return PCL_ERR_INVALID;
   }
+  if (h->spec.n_scroll_groups > 1 && (!st->d_groups || !st->d_groups_init)) return PCL_ERR_INVALID;
   if (h->spec.program == PCL_PROG_FIXTURE) {
     if (!st->d_z_order || !st->d_z_order_init) return PCL_ERR_INVALID;
     for (int d = 0; d < h->spec.n_drapes; ++d) {

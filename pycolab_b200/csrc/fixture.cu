@@ -37,8 +37,27 @@ struct WarpState {                   // lives in shared memory, one per warp
   int32_t drapes[PCL_MAX_DRAPES][PCL_DRAPE_WORDS];
   int32_t plot[PCL_PLOT_WORDS];
   uint32_t impassable[PCL_MAX_SPRITES][4];
+  // One record per scrolling group (protocols/scrolling.py:198-241): the group an
+  // entity belongs to is swapped into the `Plot` registers around its update.
+  int32_t groups[PCL_MAX_SCROLL_GROUPS][PCL_GROUP_WORDS];
   uint8_t z[kMaxEnt + 8];
 };
+
+// The order / egocentric-set registers of scrolling group g <-> `plot`.
+__device__ __forceinline__ void group_in(Plot& plot, const WarpState* st, int g) {
+  plot.order_r = st->groups[g][PCL_G_ORDER_R]; plot.order_c = st->groups[g][PCL_G_ORDER_C];
+  plot.order_frame = st->groups[g][PCL_G_ORDER_FRAME];
+  plot.ego_mask = st->groups[g][PCL_G_EGO_MASK];
+}
+__device__ __forceinline__ void group_out(const Plot& plot, WarpState* st, int g, int lane) {
+  __syncwarp();
+  if (lane == 0) {
+    st->groups[g][PCL_G_ORDER_R] = plot.order_r; st->groups[g][PCL_G_ORDER_C] = plot.order_c;
+    st->groups[g][PCL_G_ORDER_FRAME] = plot.order_frame;
+    st->groups[g][PCL_G_EGO_MASK] = plot.ego_mask;
+  }
+  __syncwarp();
+}
 
 __device__ __forceinline__ bool in_set(const uint32_t* set, int code) {
   return (set[(code >> 5) & 3] >> (code & 31)) & 1u;
@@ -214,6 +233,18 @@ fixture_step(const StepParams p) {
   for (int i = lane; i < S * 4; i += 32) (&st->impassable[0][0])[i] = p.impassable[i >> 2][i & 3];
   for (int i = lane; i < (int)board_bytes; i += 32) c.board[i] = 0;
   __syncwarp();
+  // Scrolling groups: group 0 is the plot record's own order / egocentric words,
+  // the others come from (or are restored into) pcl_state.d_groups.
+  const int n_sg = p.n_scroll_groups;
+  int32_t* g_groups = p.st.d_groups
+      ? p.st.d_groups + (int64_t)env * PCL_MAX_SCROLL_GROUPS * PCL_GROUP_WORDS : nullptr;
+  if (lane < PCL_GROUP_WORDS) st->groups[0][lane] = st->plot[PCL_P_ORDER_R + lane];
+  if (g_groups && n_sg > 1) {
+    const int32_t* src_g = restart ? p.st.d_groups_init + lvl * p.st.groups_init_bstride : g_groups;
+    if (lane >= PCL_GROUP_WORDS && lane < n_sg * PCL_GROUP_WORDS)
+      (&st->groups[0][0])[lane] = src_g[lane];
+  }
+  __syncwarp();
   if (restart) {
     if (lane == 0) { st->plot[PCL_P_EPISODES] = episodes + 1; st->plot[PCL_P_ERROR] = old_error; }
     __syncwarp();
@@ -229,8 +260,7 @@ fixture_step(const StepParams p) {
   Plot plot;
   plot.frame = st->plot[PCL_P_FRAME] + 1;    // engine.py:716
   plot.error = st->plot[PCL_P_ERROR];
-  plot.order_r = st->plot[PCL_P_ORDER_R]; plot.order_c = st->plot[PCL_P_ORDER_C];
-  plot.order_frame = st->plot[PCL_P_ORDER_FRAME]; plot.ego_mask = st->plot[PCL_P_EGO_MASK];
+  group_in(plot, st, 0);
   Directives dir = fresh_directives();
   const int32_t* act = restart ? nullptr : p.actions + (int64_t)env * p.actions_per_env;
 
@@ -247,12 +277,19 @@ fixture_step(const StepParams p) {
         const uint32_t* imp = st->impassable[s];
         const uint8_t* board = c.board;
         const int pitch = p.pitch;
+        group_in(plot, st, p.sprite_group[s]);
         walker_move(sp, s, motion, plot, H, W, p.confined[s] != 0, p.egocentric[s] != 0, lane,
                     [&](int r, int col) { return in_set(imp, board[r * pitch + col]); });
+        group_out(plot, st, p.sprite_group[s], lane);
         store_sprite(st->sprites[s], sp, lane);
       }
-      for (int d = 0; d < D; ++d)
-        if (p.drape_char[d] == ch && p.drape_kind[d]) scrolly_move_dyn(c, d, motion, plot);
+      for (int d = 0; d < D; ++d) {
+        if (p.drape_char[d] == ch && p.drape_kind[d]) {
+          group_in(plot, st, p.drape_group[d]);
+          scrolly_move_dyn(c, d, motion, plot);
+          group_out(plot, st, p.drape_group[d], lane);
+        }
+      }
     }
     render(c);
   }
@@ -306,8 +343,7 @@ fixture_step(const StepParams p) {
   if (lane == 0) {
     st->plot[PCL_P_FRAME] = plot.frame; st->plot[PCL_P_GAME_OVER] = dir.game_over;
     st->plot[PCL_P_ERROR] = plot.error;
-    st->plot[PCL_P_ORDER_R] = plot.order_r; st->plot[PCL_P_ORDER_C] = plot.order_c;
-    st->plot[PCL_P_ORDER_FRAME] = plot.order_frame; st->plot[PCL_P_EGO_MASK] = plot.ego_mask;
+    for (int w = 0; w < PCL_GROUP_WORDS; ++w) st->plot[PCL_P_ORDER_R + w] = st->groups[0][w];
     p.out.d_reward[env] = dir.reward;
     p.out.d_has_reward[env] = (uint8_t)dir.has_reward;
     p.out.d_discount[env] = dir.discount;
@@ -317,6 +353,8 @@ fixture_step(const StepParams p) {
   for (int i = lane; i < S * PCL_SPRITE_WORDS; i += 32) g_sprites[i] = (&st->sprites[0][0])[i];
   for (int i = lane; i < D * PCL_DRAPE_WORDS; i += 32) g_drapes[i] = (&st->drapes[0][0])[i];
   if (lane < PCL_PLOT_WORDS) g_plot[lane] = st->plot[lane];
+  if (g_groups && n_sg > 1 && lane >= PCL_GROUP_WORDS && lane < n_sg * PCL_GROUP_WORDS)
+    g_groups[lane] = (&st->groups[0][0])[lane];
   if (lane < n) g_z[lane] = st->z[lane];
   const int n16 = (H * p.pitch) >> 4;
   for (int i = lane; i < n16; i += 32)

@@ -25,6 +25,9 @@ struct StepParams {
   int egocentric[PCL_MAX_SPRITES];
   int drape_kind[PCL_MAX_DRAPES];
   int program_arg[8];
+  int n_scroll_groups;
+  int sprite_group[PCL_MAX_SPRITES];
+  int drape_group[PCL_MAX_DRAPES];
   int n_groups;
   int group_len[PCL_MAX_SPRITES + PCL_MAX_DRAPES];
   uint8_t group_chars[PCL_MAX_SPRITES + PCL_MAX_DRAPES];

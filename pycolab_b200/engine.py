@@ -154,14 +154,16 @@ class Engine(object):
     """General-program action row from the fixture conventions
     (tests/test_things.py:219-250): a direction string for everybody, or
     {char: direction}; unknown / missing = stay.  Directive keys '_reward',
-    '_terminate', '_z' stand in for post_update code injection."""
+    '_terminate', '_z' — or '_directives', an ordered list of Plot calls such as
+    ('terminate_episode', 0.5) — stand in for post_update code injection."""
     from pycolab_b200.games import fixtures
     code = lambda d: self._MOTION_NAMES.index(d) if d in self._MOTION_NAMES else 8
     order = ''.join(self._batched.game.groups)
     if isinstance(actions, dict):
       motions = {ch: code(actions.get(ch)) for ch in order}
       return fixtures.action_rows(self._batched.game, motions, actions.get('_reward'),
-                                  bool(actions.get('_terminate')), actions.get('_z'))
+                                  bool(actions.get('_terminate')), actions.get('_z'),
+                                  directives=actions.get('_directives'))
     return fixtures.action_rows(self._batched.game, {ch: code(actions) for ch in order})
 
   def _wrap(self, result):

@@ -40,20 +40,22 @@ class FixtureDrape(plab_things.Drape):
 
 def make_game(art, what_lies_beneath, walkers, scrollys=None, drapes='',
               update_schedule=None, z_order=None, occlusion_in_layers=True):
-  """walkers: {char: dict(impassable, confined, egocentric)}; scrollys:
-  {char: dict(pattern, corner, margins)}; drapes: chars of static drapes."""
+  """walkers: {char: dict(impassable, confined, egocentric, group)}; scrollys:
+  {char: dict(pattern, corner, margins, group)}; drapes: chars of static drapes."""
   scrollys = scrollys or {}
   shape = (len(art), len(art[0]))
   sprites = {
       ch: ascii_art.Partial(FixtureMazeWalker, impassable=kw.get('impassable', ''),
                             confined_to_board=kw.get('confined', False),
-                            egocentric_scroller=kw.get('egocentric', False))
+                            egocentric_scroller=kw.get('egocentric', False),
+                            scrolling_group=kw.get('group', ''))
       for ch, kw in walkers.items()}
   dr = {
       ch: ascii_art.Partial(FixtureScrolly, board_shape=shape,
                             whole_pattern=np.array(kw['pattern'], dtype=bool),
                             board_northwest_corner=tuple(kw['corner']),
-                            scroll_margins=kw.get('margins', (2, 3)))
+                            scroll_margins=kw.get('margins', (2, 3)),
+                            scrolling_group=kw.get('group', ''))
       for ch, kw in scrollys.items()}
   for ch in drapes:
     dr[ch] = FixtureDrape

@@ -199,6 +199,10 @@ class LoweredGame(object):
     self.program_arg = [0] * 8  # pcl_spec.program_arg
     self.reward_type = int      # the reference's reward type (classics pay floats)
     self.backdrop_role = None   # device counterpart of a Backdrop with update() logic
+    self.scroll_groups = ['']   # names of the scrolling groups, index = device group id
+    self.sprite_group = []      # per sprite: index into scroll_groups
+    self.drape_group = []       # per drape
+    self.group_records = None   # i32 [MAX_SCROLL_GROUPS, 4] reset template (groups >= 1)
 
   def signature(self):
     """Everything that must agree between envs sharing one handle."""
@@ -206,7 +210,8 @@ class LoweredGame(object):
             tuple(map(tuple, self.impassable)), tuple(self.confined),
             tuple(self.egocentric), tuple(map(tuple, self.margins)), self.z_order,
             tuple(self.groups), self.pattern_rows, self.pattern_cols,
-            tuple(self.program_arg))
+            tuple(self.program_arg), tuple(self.scroll_groups), tuple(self.sprite_group),
+            tuple(self.drape_group))
 
   def make_spec(self, auto_reset):
     s = _lib.Spec()
@@ -232,6 +237,11 @@ class LoweredGame(object):
       s.z_order[i] = ord(ch)
     for i, v in enumerate(self.program_arg):
       s.program_arg[i] = int(v)
+    s.n_scroll_groups = len(self.scroll_groups)
+    for i, g in enumerate(self.sprite_group):
+      s.sprite_group[i] = g
+    for i, g in enumerate(self.drape_group):
+      s.drape_group[i] = g
     s.n_groups = len(self.groups)
     k = 0
     for g, group in enumerate(self.groups):
@@ -254,11 +264,11 @@ def _sprite_record(sprite, aux0=0, aux1=0, aux2=0):
           flags, int(aux0), int(aux1), int(aux2)]
 
 
-def _walker_meta(sprite):
+def _walker_meta(sprite, named_groups=False):
   if not isinstance(sprite, prefab_sprites.MazeWalker):
     raise NotLoweredError('sprite {!r} is not a MazeWalker'.format(sprite.character))
-  if sprite._scrolling_group != '':
-    raise NotLoweredError('only the default scrolling group is lowered')
+  if sprite._scrolling_group != '' and not named_groups:
+    raise NotLoweredError('named scrolling groups are lowered by the general program only')
   if (type(sprite)._on_board_exit is not prefab_sprites.MazeWalker._on_board_exit or
       type(sprite)._on_board_enter is not prefab_sprites.MazeWalker._on_board_enter):
     raise NotLoweredError('overridden MazeWalker board exit/enter hooks are not lowered')
@@ -307,9 +317,9 @@ def _common(engine, game, program):
                           'entities never consult `layers`')
 
 
-def _set_sprites(game, sprites, records):
+def _set_sprites(game, sprites, records, named_groups=False):
   game.sprite_chars = ''.join(s.character for s in sprites)
-  meta = [_walker_meta(s) for s in sprites]
+  meta = [_walker_meta(s, named_groups) for s in sprites]
   game.impassable = [m[0] for m in meta]
   game.confined = [m[1] for m in meta]
   game.egocentric = [m[2] for m in meta]
@@ -505,15 +515,29 @@ def _lower_fixture(engine, roles):
   if len(sprite_chars) > _lib.MAX_SPRITES or len(drape_chars) > _lib.MAX_DRAPES:
     raise NotLoweredError('too many entities for the general device program')
   sprites = [th[c] for c in sprite_chars]
-  _set_sprites(game, sprites, [_sprite_record(s, aux0=0, aux1=_lib.NEVER) for s in sprites])
+  _set_sprites(game, sprites, [_sprite_record(s, aux0=0, aux1=_lib.NEVER) for s in sprites],
+               named_groups=True)
+  # Scrolling groups (protocols/scrolling.py:198-241): one device record per name.
+  names = []
+  for ch in order:
+    name = getattr(th[ch], '_scrolling_group', None)
+    if name is not None and name not in names:
+      names.append(name)
+  names = names or ['']
+  if len(names) > _lib.MAX_SCROLL_GROUPS:
+    raise NotLoweredError('more than {} scrolling groups'.format(_lib.MAX_SCROLL_GROUPS))
+  game.scroll_groups = names
+  game.sprite_group = [names.index(th[c]._scrolling_group) for c in sprite_chars]
+  game.drape_group = [names.index(getattr(th[c], '_scrolling_group', names[0]))
+                      for c in drape_chars]
+  game.group_records = np.zeros((_lib.MAX_SCROLL_GROUPS, _lib.GROUP_WORDS), dtype=np.int32)
+  game.group_records[:, _lib.G_ORDER_FRAME] = _lib.NEVER
   game.drape_chars = ''.join(drape_chars)
   game.drape_kind, game.margins, recs = [], [], []
   shape = None
   for d, ch in enumerate(drape_chars):
     ent = th[ch]
     if roles[ch] == 'fixture.scrolly':
-      if ent._scrolling_group != '':
-        raise NotLoweredError('only the default scrolling group is lowered')
       if shape not in (None, ent.whole_pattern.shape):
         raise NotLoweredError('Scrolly patterns of different shapes')
       shape = ent.whole_pattern.shape

@@ -173,6 +173,71 @@ def fixture_scrolly(name, seed, margins, second_ego, T=400):
        curtains=np.stack(curtains).astype(np.uint8))
 
 
+def fixture_groups(name, seed, margins, T=400):
+  """Two scrolling groups at once (protocols/scrolling.py:198-241): group 'one' =
+  Scrolly '#' + egocentric walker P, group 'two' = Scrolly '@' + egocentric walker q;
+  every step each group gets its own random motion, so the two windows scroll
+  independently and each walker obeys only its own group's orders."""
+  rs = np.random.RandomState(2000 + seed)
+  PH, PW, H, W = 17, 23, 8, 11
+  pattern = rs.random_sample((PH, PW)) < 0.2
+  pattern2 = rs.random_sample((PH, PW)) < 0.1
+  corner = (int(rs.randint(0, PH - H + 1)), int(rs.randint(0, PW - W + 1)))
+  corner2 = (int(rs.randint(0, PH - H + 1)), int(rs.randint(0, PW - W + 1)))
+  art = np.full((H, W), ord(' '), dtype=np.uint8)
+  art[3, 4] = ord('P')
+  art[5, 7] = ord('q')
+  art_l = tj.u8_to_art(art)
+  walkers = {'P': dict(impassable='#', egocentric=True, group='one'),
+             'q': dict(impassable='@', egocentric=True, group='two')}
+  scrollys = {'#': dict(pattern=pattern, corner=corner, margins=margins, group='one'),
+              '@': dict(pattern=pattern2, corner=corner2, margins=margins, group='two')}
+  schedule = [['#', '@'], ['P', 'q']]
+  motions = rs.randint(0, 9, size=(T, 2)).astype(np.int32)      # (group one, group two)
+  sprites, curtains = [], []
+  rec = sprite_recorder('Pq', sprites)
+
+  def on_frame(env, out):
+    rec(env, out)
+    curtains.append(np.stack([env.things['#'].curtain.copy(),
+                              env.things['@'].curtain.copy()]))
+
+  env = refdriver.ref_fixture(art_l, ' ', walkers, scrollys,
+                              update_schedule=schedule, z_order='@#Pq')
+  out = env.its_showtime()
+  boards = [tj.board_of(out[0]).copy()]
+  on_frame(env, out)
+  used = []
+  for m1, m2 in motions:
+    act = {'#': int(m1), 'P': int(m1), '@': int(m2), 'q': int(m2)}
+    try:
+      out = env.play(refdriver.fixture_actions_to_ref(act))
+    except RuntimeError:
+      break                         # reference rejects a (0,0)-clipped order
+    used.append([int(m1), int(m2)])
+    boards.append(tj.board_of(out[0]).copy())
+    on_frame(env, out)
+  cfg = dict(
+      walkers=walkers,
+      scrollys={'#': dict(corner=list(corner), group='one',
+                          margins=None if margins is None else list(margins)),
+                '@': dict(corner=list(corner2), group='two',
+                          margins=None if margins is None else list(margins))},
+      drapes='', schedule=schedule, z_order='@#Pq', what_lies_beneath=' ',
+      action_chars='', motion_of=dict([('#', 0), ('P', 0), ('@', 1), ('q', 1)]))
+  save(name, art=art, config=np.frombuffer(json.dumps(cfg).encode(), np.uint8),
+       pattern_hash=pattern.astype(np.uint8), pattern_at=pattern2.astype(np.uint8),
+       actions=np.array(used, dtype=np.int32).reshape(-1, 2), boards=np.stack(boards),
+       sprites=np.array(sprites, dtype=np.int32),
+       curtains=np.stack(curtains).astype(np.uint8))
+  print('  %s: %d steps' % (name, len(used)))
+
+
+def groups():
+  for seed, margins in ((0, (2, 3)), (1, None), (2, (1, 2))):
+    fixture_groups('fixture_groups_%d' % seed, seed, margins)
+
+
 def better_scrolly(name, level, T=400):
   """better_scrolly_maze stock level + its three croppers (player view with an
   initial offset and no padding, patroller view padded with (None, 3) margins,
@@ -371,6 +436,8 @@ def main():
     return fluvials()
   if sys.argv[1:] == ['aperture']:
     return apertures()
+  if sys.argv[1:] == ['groups']:
+    return groups()
   # BASELINE.json configs[0]: stock scrolly_maze, 1000 random-action steps.
   for level, T in ((0, 1000), (1, 400), (2, 400)):
     maze, board, beneath = refdriver.ref_stock_scrolly_art(level)
@@ -419,6 +486,7 @@ def main():
   stories()
   fluvials()
   apertures()
+  groups()
 
 
 # Same-shape (4x12) chapters for a list-style story without croppers.

@@ -47,6 +47,8 @@ def fixture_kwargs(g):
                         corner=tuple(kw['corner']),
                         margins=None if kw['margins'] is None
                         else tuple(kw['margins']))
+    if 'group' in kw:                    # named scrolling group (fixture_groups_*)
+      scrollys[ch]['group'] = kw['group']
   return dict(art=tj.u8_to_art(g['art']),
               what_lies_beneath=cfg['what_lies_beneath'],
               walkers=cfg['walkers'], scrollys=scrollys, drapes=cfg['drapes'],
@@ -59,3 +61,22 @@ def oracle_sprite_rows(world, chars):
     w = world.things[ch]
     rows.append([w.row, w.col, int(bool(w.visible)), w.vrow, w.vcol])
   return rows
+
+
+def new_directive_row(row, n):
+  """A stored action row of the `fixture_directives_*` goldens (n motions, reward
+  or INT32_MIN, terminate 0/1, z_move_this or -1, z_in_front_of or 0) in the
+  device's current layout: n motions + (opcode, argument) directive pairs
+  (include/pcl.h PCL_DIR_*), same call order: reward, terminate, z-order."""
+  from pycolab_b200 import _lib
+  row = [int(x) for x in row]
+  out, dirs = row[:n], []
+  reward, term, z_this, z_that = row[n:n + 4]
+  if reward != -(2 ** 31):
+    dirs += [_lib.DIR_ADD_REWARD, reward]
+  if term:
+    dirs += [_lib.DIR_TERMINATE, 0]      # f32 bits of 0.0
+  if z_this >= 0:
+    dirs += [_lib.DIR_Z_ORDER, z_this | (z_that << 8)]
+  dirs += [0] * (2 * _lib.FIXTURE_DIRECTIVES - len(dirs))
+  return out + dirs

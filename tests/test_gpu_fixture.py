@@ -34,12 +34,11 @@ def _rows(eng, motions_by_char, T):
   """[T, B, A] action rows from {char: [T] codes} (same for every env)."""
   order = ''.join(eng.game.groups)
   n = len(order)
-  rows = np.zeros((T, eng.batch, n + 4), dtype=np.int64)
+  from pycolab_b200 import _lib
+  rows = np.zeros((T, eng.batch, n + 2 * _lib.FIXTURE_DIRECTIVES), dtype=np.int64)
   for k, ch in enumerate(order):
     rows[:, :, k] = np.asarray(motions_by_char.get(ch, np.full(T, 8)))[:, None]
-  rows[:, :, n] = -(2 ** 31)
-  rows[:, :, n + 2] = -1
-  return rows.astype(np.int32)
+  return rows.astype(np.int32)            # no Plot directives: opcode 0
 
 
 def _sprite_rows(eng, chars, env=0):
@@ -96,6 +95,33 @@ def test_fixture_scrolly_golden(name):
   assert int(eng.error_codes().abs().max()) == 0
 
 
+@pytest.mark.parametrize('name', gc.names('fixture_groups_'))
+def test_fixture_two_scrolling_groups_golden(name):
+  """Named scrolling groups on the device (protocols/scrolling.py:198-241,
+  `scrolling_group` of sprites.py MazeWalker / drapes.py Scrolly): group 'one' =
+  '#' + P, group 'two' = '@' + q, each driven by its own motion; boards, sprite
+  registers and both curtains must equal the reference's at every step."""
+  torch = _torch()
+  g = gc.load(name)
+  kw, cfg = gc.fixture_kwargs(g)
+  eng = _engine(kw, batch=2)
+  assert eng.game.scroll_groups == ['one', 'two'] and eng.groups is not None
+  T = len(g['actions'])
+  rows = _rows(eng, {ch: g['actions'][:, k] for ch, k in cfg['motion_of'].items()}, T)
+  res = eng.its_showtime()
+  for t in range(T + 1):
+    torch.cuda.synchronize()
+    for e in range(2):
+      np.testing.assert_array_equal(res.board[e].cpu().numpy(), g['boards'][t],
+                                    err_msg='%s t=%d' % (name, t))
+    np.testing.assert_array_equal(_sprite_rows(eng, 'Pq'), g['sprites'][t])
+    cur = np.stack([eng.curtain('#')[0].cpu().numpy(), eng.curtain('@')[0].cpu().numpy()])
+    np.testing.assert_array_equal(cur, g['curtains'][t].astype(bool))
+    if t < T:
+      res = eng.play(torch.from_numpy(rows[t]).cuda())
+  assert int(eng.error_codes().abs().max()) == 0
+
+
 @pytest.mark.parametrize('name', gc.names('fixture_directives_'))
 def test_fixture_directives_golden(name):
   torch = _torch()
@@ -115,7 +141,8 @@ def test_fixture_directives_golden(name):
     assert int(res.done[0]) == int(g['game_over'][t])
     np.testing.assert_array_equal(eng.z_order[0].cpu().numpy(), g['z_orders'][t])
     if t < T:
-      row = g['actions'][t].astype(np.int32)
+      row = np.array(gc.new_directive_row(g['actions'][t], len(cfg['action_chars'])),
+                     dtype=np.int32)
       res = eng.play(torch.from_numpy(np.stack([row, row])).cuda())
   assert int(eng.error_codes().abs().max()) == 0
 

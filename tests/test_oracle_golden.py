@@ -89,6 +89,24 @@ def test_fixture_scrolly(name):
       out = world.play(int(g['actions'][t]))
 
 
+@pytest.mark.parametrize('name', gc.names('fixture_groups_'))
+def test_fixture_two_scrolling_groups(name):
+  """Two named scrolling groups driven by independent motions
+  (protocols/scrolling.py:198-241); golden produced by the reference."""
+  g = gc.load(name)
+  kw, cfg = gc.fixture_kwargs(g)
+  world = games.make_fixture_world(**kw)
+  out = world.its_showtime()
+  for t in range(len(g['actions']) + 1):
+    np.testing.assert_array_equal(g['boards'][t], out[0], err_msg='t=%d' % t)
+    np.testing.assert_array_equal(g['sprites'][t], gc.oracle_sprite_rows(world, 'Pq'))
+    np.testing.assert_array_equal(
+        g['curtains'][t],
+        np.stack([world.things['#'].curtain, world.things['@'].curtain]))
+    if t < len(g['actions']):
+      out = world.play({ch: int(g['actions'][t][k]) for ch, k in cfg['motion_of'].items()})
+
+
 def better_croppers(g, world_or_engine, make_scrolling, make_fixed):
   """The three better_scrolly_maze views (better_scrolly_maze.py:224-251)."""
   views = [
