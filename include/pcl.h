@@ -379,6 +379,9 @@ const char* pcl_status_string(int status);
  * valid until the next failing call on the handle. */
 const char* pcl_last_error(pcl_handle* h);
 int pcl_abi_version(void);
+/* sizeof of the four structs that cross the boundary, for bindings to verify their
+ * own layouts at load time: out[0..3] = pcl_spec, pcl_state, pcl_outputs, pcl_crop_spec. */
+int pcl_struct_sizes(int32_t out[4]);
 
 #ifdef __cplusplus
 }

@@ -130,6 +130,7 @@ class ObserveSpec(C.Structure):
 # name -> (restype, argtypes); every symbol include/pcl.h declares.
 SYMBOLS = {
     'pcl_abi_version': (C.c_int, []),
+    'pcl_struct_sizes': (C.c_int, [C.POINTER(C.c_int32)]),
     'pcl_status_string': (C.c_char_p, [C.c_int]),
     'pcl_create': (C.c_int, [C.POINTER(Spec), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     'pcl_destroy': (C.c_int, [C.c_void_p]),
@@ -194,6 +195,13 @@ def load():
   if lib.pcl_abi_version() != ABI_VERSION:
     raise PclLibraryError('ABI mismatch: library %d, binding %d' % (
         lib.pcl_abi_version(), ABI_VERSION))
+  sizes = (C.c_int32 * 4)()
+  lib.pcl_struct_sizes(sizes)
+  mine = [C.sizeof(Spec), C.sizeof(State), C.sizeof(Outputs), C.sizeof(CropSpec)]
+  if list(sizes) != mine:
+    raise PclLibraryError('struct layout mismatch between include/pcl.h and _lib.py: library '
+                          '%s, binding %s (pcl_spec, pcl_state, pcl_outputs, pcl_crop_spec)' % (
+                              list(sizes), mine))
   _lib = lib
   return lib
 

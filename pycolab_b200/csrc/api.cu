@@ -286,6 +286,13 @@ extern "C" {
 
 int pcl_abi_version(void) { return PCL_ABI_VERSION; }
 
+int pcl_struct_sizes(int32_t out[4]) {
+  if (!out) return PCL_ERR_INVALID;
+  out[0] = (int32_t)sizeof(pcl_spec); out[1] = (int32_t)sizeof(pcl_state);
+  out[2] = (int32_t)sizeof(pcl_outputs); out[3] = (int32_t)sizeof(pcl_crop_spec);
+  return PCL_OK;
+}
+
 const char* pcl_status_string(int status) {
   switch (status) {
     case PCL_OK: return "ok";

@@ -52,12 +52,15 @@ def test_binding_loads_and_reports_abi():
   assert _lib.status_string(_lib.ERR_UNSUPPORTED) == 'game not lowered to a device program'
 
 
-def test_spec_struct_matches_header_size():
-  # pcl_spec: 12 int32 + 16 + 8 bytes + 16*4 u32 + 16 + 16 i32 + 8*2 i32 + 24 bytes
-  # + 1 i32 + 24 i32 + 24 bytes + 8 i32 drape_kind + 8 i32.
-  import ctypes
-  expected = 12 * 4 + 16 + 8 + 16 * 16 + 16 * 4 + 16 * 4 + 16 * 4 + 24 + 4 + 24 * 4 + 24 + 8 * 4 + 8 * 4
-  assert ctypes.sizeof(_lib.Spec) == expected
+def test_binding_structs_match_the_header():
+  """The library reports sizeof() of every struct that crosses the boundary;
+  `_lib.load()` refuses a binding whose ctypes layouts disagree."""
+  import ctypes as C
+  lib = _lib.load()
+  sizes = (C.c_int32 * 4)()
+  assert lib.pcl_struct_sizes(sizes) == _lib.OK
+  assert list(sizes) == [C.sizeof(_lib.Spec), C.sizeof(_lib.State), C.sizeof(_lib.Outputs),
+                         C.sizeof(_lib.CropSpec)]
 
 
 def test_create_rejects_bad_specs_without_gpu():
