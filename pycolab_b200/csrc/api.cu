@@ -101,9 +101,17 @@ int validate(const pcl_spec& s) {
         if (s.sprite_egocentric[i] != (i == 0)) return PCL_ERR_UNSUPPORTED;
       }
       if (s.pattern_rows < s.rows || s.pattern_cols < s.cols) return PCL_ERR_INVALID;
-      if ((s.pattern_words & 1) || s.pattern_words < (((s.pattern_cols - s.cols) >> 5) & ~1) + 4 ||
-          s.pattern_words < (s.pattern_cols + 31) / 32 + 1) return PCL_ERR_INVALID;
-      if (s.cols > 64) return PCL_ERR_UNSUPPORTED;   // window rows are staged as 3 words
+      {
+        // Window rows are staged from the even word at or below corner_c >> 5:
+        // 2 * ceil((63 + W) / 64) words (4 up to 64 columns) must stay inside the row.
+        const int nw = 2 * ((63 + s.cols + 63) / 64);
+        if ((s.pattern_words & 1) || s.pattern_words < (((s.pattern_cols - s.cols) >> 5) & ~1) + nw ||
+            s.pattern_words < (s.pattern_cols + 31) / 32 + 1) return PCL_ERR_INVALID;
+        // one CTA (4 envs) stages tile + windows in shared memory
+        const long per_env = 256L + (long)s.rows * s.pitch + 2L * s.rows * nw * 4 +
+                             (long)s.rows * (s.pitch >> 2) + 64;
+        if (per_env * 4 > 227L * 1024) return PCL_ERR_UNSUPPORTED;
+      }
       for (int d = 0; d < 2; ++d) {
         const int mr = s.margins[d][0], mc = s.margins[d][1];
         if (mr >= 0 && (mc - 1 >= s.cols - mc || mr - 1 >= s.rows - mr)) return PCL_ERR_INVALID;

@@ -78,9 +78,16 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   return d;
 }
 
-__host__ __device__ __forceinline__ size_t warp_smem_bytes(int H, int pitch) {
-  // records, backdrop tile, two 4-word window rows per board row, one word per segment
-  return kRecWords * 4 + (size_t)H * pitch + 2 * ((size_t)H * 16) +
+// Words staged per window row: a W-cell window row starts at bit corner_c of its
+// pattern row; from the even word at or below corner_c >> 5 it spans at most
+// 63 + W bits.  4 words (two 8-byte cp.async, one 16-byte slot) up to W = 64, 6 or 8
+// beyond (drapes.py:293-376 puts no limit on the board width).
+__host__ __device__ __forceinline__ int window_words(int W) { return 2 * ((63 + W + 63) / 64); }
+
+__host__ __device__ __forceinline__ size_t warp_smem_bytes(int H, int pitch, int nw) {
+  // records, backdrop tile, two nw-word window rows per board row, one word per segment
+  const size_t rows = (((size_t)H * nw * 4) + 15) & ~(size_t)15;
+  return kRecWords * 4 + (size_t)H * pitch + 2 * rows +
          (((size_t)H * (pitch >> 2) + 15) & ~(size_t)15);      // keep every warp's slice 16-byte aligned
 }
 
@@ -199,12 +206,13 @@ scrolly_maze_step(const StepParams p) {
   const bool live = env < p.B;
   const int H = p.H, W = p.W, PWW = p.PWW;
   const int pitch = p.pitch;
+  const int nw = window_words(W);            // staged words per window row (4 for W <= 64)
 
-  uint8_t* my = smem_raw + warp * warp_smem_bytes(H, pitch);
+  uint8_t* my = smem_raw + warp * warp_smem_bytes(H, pitch, nw);
   int32_t* rec = reinterpret_cast<int32_t*>(my);
   uint8_t* s_bd = my + kRecWords * 4;
   uint32_t* s_wall = reinterpret_cast<uint32_t*>(s_bd + (size_t)H * pitch);
-  uint32_t* s_coin = s_wall + H * 4;
+  uint32_t* s_coin = s_wall + ((H * nw + 3) & ~3);
   // Everything above ran without touching state earlier kernels may have
   // produced (g_sel is a constant); from here on the kernel reads such state.
   pdl_wait_prior_grids();
@@ -324,10 +332,18 @@ scrolly_maze_step(const StepParams p) {
 
   // ---- 3. one batch of loads ---------------------------------------------
   const int we = (wc >> 5) & ~1, ce = (cc_pred >> 5) & ~1;   // first staged word (even)
-  {
+  const bool narrow = W <= 64;               // the 4-word fast paths (pitch <= 64)
+  if (narrow) {
     const int nhalf = H * 2;                 // two 8-byte halves per window row
     for (int i = lane; i < nhalf; i += 32) {
       const int r = i >> 1, k = (i & 1) * 2;
+      cp_async8(s_wall + i * 2, wall_pat + (int64_t)(wr + r) * PWW + we + k);
+      cp_async8(s_coin + i * 2, coin_pat + (int64_t)(cr_pred + r) * PWW + ce + k);
+    }
+  } else {                                   // boards wider than 64 columns
+    const int hw = nw >> 1, nhalf = H * hw;
+    for (int i = lane; i < nhalf; i += 32) {
+      const int r = i / hw, k = (i - r * hw) * 2;
       cp_async8(s_wall + i * 2, wall_pat + (int64_t)(wr + r) * PWW + we + k);
       cp_async8(s_coin + i * 2, coin_pat + (int64_t)(cr_pred + r) * PWW + ce + k);
     }
@@ -509,8 +525,8 @@ scrolly_maze_step(const StepParams p) {
     // The coin window was staged before the pick-up: clear the bit there too.
     if (picked_r >= 0) {
       const int r2 = picked_r - cr_pred, b = picked_c - (ce << 5);
-      if ((unsigned)r2 < (unsigned)H && (unsigned)b < 128u)
-        s_coin[r2 * 4 + (b >> 5)] &= ~(1u << (b & 31));
+      if ((unsigned)r2 < (unsigned)H && (unsigned)b < (unsigned)(nw * 32))
+        s_coin[r2 * nw + (b >> 5)] &= ~(1u << (b & 31));
     }
   }
   const int cr = coins.corner_r, cc = coins.corner_c;
@@ -518,8 +534,8 @@ scrolly_maze_step(const StepParams p) {
   if (cr != cr_pred || cc != cc_pred) {      // '@' issued its own order: restage
     __syncwarp();
     ce_final = (cc >> 5) & ~1;
-    for (int i = lane; i < H * 4; i += 32)
-      s_coin[i] = coin_pat[(int64_t)(cr + (i >> 2)) * PWW + ce_final + (i & 3)];
+    for (int i = lane; i < H * nw; i += 32)
+      s_coin[i] = coin_pat[(int64_t)(cr + i / nw) * PWW + ce_final + i % nw];
   }
   __syncwarp();
   g_sprites[lane] = rec[lane];
@@ -532,9 +548,9 @@ scrolly_maze_step(const StepParams p) {
   // below does no bit addressing at all.  Cells past W and the stale coin
   // (drapes.py:689 has not refreshed the curtain yet) are folded in here.
   const int spr = pitch >> 4;                // 16-byte segments per row
-  uint32_t* s_seg = s_coin + H * 4;
-  {
-    const int wsh = wc - (we << 5), csh = cc - (ce_final << 5);   // 0..63 into the staged row
+  uint32_t* s_seg = s_coin + ((H * nw + 3) & ~3);
+  const int wsh = wc - (we << 5), csh = cc - (ce_final << 5);     // 0..63 into the staged row
+  if (narrow) {
     const uint32_t m_lo = W >= 32 ? 0xffffffffu : (1u << W) - 1u;
     const uint32_t m_hi = W >= 64 ? 0xffffffffu : W > 32 ? (1u << (W - 32)) - 1u : 0u;
     for (int r = lane; r < H; r += 32) {
@@ -553,6 +569,22 @@ scrolly_maze_step(const StepParams p) {
       if (spr > 1) out[1] = __byte_perm(c_lo, w_lo, 0x7632);
       if (spr > 2) out[2] = __byte_perm(c_hi, w_hi, 0x5410);
       if (spr > 3) out[3] = __byte_perm(c_hi, w_hi, 0x7632);
+    }
+  } else {                                   // general width: one (row, segment) per lane and round
+    for (int i = lane; i < H * spr; i += 32) {
+      const int r = i / spr, j = i - r * spr;
+      const int ncols = min(16, W - 16 * j);
+      if (ncols <= 0) { s_seg[i] = 0; continue; }          // pitch padding past the board
+      const uint32_t keep = (1u << ncols) - 1u;
+      const int wo = wsh + 16 * j, co = csh + 16 * j;
+      const uint32_t* wrow = s_wall + r * nw;
+      const uint32_t* crow = s_coin + r * nw;
+      // the second word is only fetched while inside the staged row
+      const uint32_t w16 = __funnelshift_r(wrow[wo >> 5], (wo >> 5) + 1 < nw ? wrow[(wo >> 5) + 1] : 0u,
+                                           wo & 31) & keep;
+      const uint32_t c16 = __funnelshift_r(crow[co >> 5], (co >> 5) + 1 < nw ? crow[(co >> 5) + 1] : 0u,
+                                           co & 31) & keep;
+      s_seg[i] = (w16 << 16) | c16;
     }
   }
   // a, b, c lie under both drapes, so they are patched into the staged backdrop
@@ -597,9 +629,10 @@ scrolly_maze_step(const StepParams p) {
 }  // namespace
 
 cudaError_t launch_scrolly_maze(const StepParams& p, cudaStream_t s) {
-  if (p.W > 64 || (p.PWW & 1)) return cudaErrorInvalidValue;   // 4-word staged window rows
+  if (p.PWW & 1) return cudaErrorInvalidValue;   // window rows are staged in 8-byte halves
   const int blocks = (p.B + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  const size_t smem = warp_smem_bytes(p.H, p.pitch) * kWarpsPerBlock;
+  const size_t smem = warp_smem_bytes(p.H, p.pitch, window_words(p.W)) * kWarpsPerBlock;
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;         // board too large for one CTA
   if (smem > 48 * 1024) {   // opt in per launch: the attribute is per device, handles are not
     cudaError_t e = cudaFuncSetAttribute(scrolly_maze_step,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

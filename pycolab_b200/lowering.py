@@ -355,7 +355,10 @@ def _lower_scrolly_maze(engine, roles):
   game.margins = [(-1, -1) if d._scroll_margins is None else tuple(d._scroll_margins)
                   for d in (walls, coins)]
   game.pattern_rows, game.pattern_cols = walls.whole_pattern.shape
-  game.pattern_words = round_up((game.pattern_cols + 31) // 32 + 3, 2)
+  # zero-padded row: the kernel stages 2 * ceil((63 + W) / 64) words per window row
+  # starting at an even word (4 words up to 64 columns).
+  slack = 3 if engine.cols <= 64 else 2 * ((63 + engine.cols + 63) // 64) + 1
+  game.pattern_words = round_up((game.pattern_cols + 31) // 32 + slack, 2)
   game.patterns = {0: pack_rows(walls.whole_pattern, game.pattern_words),
                    1: pack_rows(coins.whole_pattern, game.pattern_words)}
   game.pattern_mutable = {0: False, 1: True}

@@ -153,6 +153,23 @@ def test_batched_scrolly_generated_multi_level():
                      actions, n_levels=3)
 
 
+@pytest.mark.parametrize('board_shape,world_shape', [((40, 96), (97, 161)), ((24, 128), (65, 257)),
+                                                     ((20, 65), (41, 131))])
+def test_batched_scrolly_wider_than_64_columns(board_shape, world_shape):
+  """The reference Scrolly has no width limit (drapes.py:293-376): boards of 65, 96
+  and 128 columns stage 4 / 6 words per window row instead of 4."""
+  from pycolab_b200 import levels
+  from pycolab_b200.games import scrolly_maze
+  arts = [levels.scrolly_maze_level(70 + i, world_shape=world_shape, board_shape=board_shape)
+          for i in range(2)]
+  rs = np.random.RandomState(47)
+  actions = rs.choice([0, 1, 2, 3, 4], size=(150, 6), p=[.2, .2, .25, .25, .1])
+  _batched_vs_oracle(lambda i: scrolly_maze.make_game(*arts[i]),
+                     lambda e: ogames.make_scrolly_maze(arts[e % 2][0], arts[e % 2][1],
+                                                        '+', arts[e % 2][2]),
+                     actions, n_levels=2, check_curtains='#@')
+
+
 def test_batched_warehouse():
   from pycolab_b200 import levels
   from pycolab_b200.games import warehouse_manager
