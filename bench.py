@@ -954,62 +954,81 @@ def per_env_level_point(torch, dist, dev, world, rank, lowered, actions, W, K, b
 
 def handoff_bench(torch, dist, dev, rank, world, engines, actions, W, K, barrier):
   """Every rank receives every shard's egocentric 9x9 crop + reward / discount /
-  done each step.  Times step + crop + hand-off and checks the result against a
-  plain NCCL all-gather of the same tensors."""
+  done each step.  Times step + hand-off (ONE kernel after the step: cropper, record
+  packing, stores into every rank's gather buffer over NVLink, flag barrier) as a
+  CUDA graph, and checks the result against a plain NCCL all-gather."""
   from pycolab_b200 import batched
   from pycolab_b200 import dist as pdist
   B, R = engines[0].batch, len(engines)
   spec = batched.scrolling_crop_spec(9, 9, 0, pad_char=' ', scroll_margins=(None, None))
+  fused_err = None
+  try:
+    handoffs = [pdist.FusedHandoff(e, spec, world * B) for e in engines]
+    transport = ('one kernel per step: crop + pack + %s into symmetric memory + in-kernel flag '
+                 'barrier' % handoffs[0].transport)
+    kind = 'fused'
+  except Exception as err:      # noqa: BLE001 - any failure to set peer mapping up
+    fused_err = str(err).splitlines()[0][:120] if str(err) else type(err).__name__
+    kind = 'nccl'
+  agree = torch.tensor([0 if kind == 'fused' else 1], device=dev)
+  dist.all_reduce(agree, op=dist.ReduceOp.MAX)
+  if int(agree.item()):         # some rank cannot map peer memory: all use NCCL
+    kind = 'nccl'
+    handoffs = [pdist.Handoff(e, (9, 9), world * B) for e in engines]
+    transport = 'crop kernel + pack kernel + 1 NCCL all-gather (symmetric memory unavailable: %s)' % (
+        fused_err or 'on a peer')
   states = [e.new_crop_state() for e in engines]
   crops = [torch.empty((B, 9, 9), dtype=torch.uint8, device=dev) for _ in engines]
-  try:
-    handoffs = [pdist.PeerHandoff(e, (9, 9), world * B) for e in engines]
-    transport = 'p2p stores into symmetric memory (fused into the pack kernel) + 1 barrier'
-  except Exception as err:      # noqa: BLE001 - any failure to set peer mapping up
-    handoffs = [pdist.Handoff(e, (9, 9), world * B) for e in engines]
-    transport = 'pack kernel + 1 NCCL all-gather (symmetric memory unavailable: %s)' % (
-        str(err).splitlines()[0][:80] if str(err) else type(err).__name__)
-  agree = torch.tensor([0 if transport.startswith('p2p') else 1], device=dev)
-  dist.all_reduce(agree, op=dist.ReduceOp.MAX)
-  if int(agree.item()) and transport.startswith('p2p'):   # some rank fell back: all do
-    handoffs = [pdist.Handoff(e, (9, 9), world * B) for e in engines]
-    transport = 'pack kernel + 1 NCCL all-gather (a peer could not map symmetric memory)'
 
   def step_and_gather(t):
     e = engines[t % R]
     e.play(actions[W + (t % K)])
-    crop = e.crop(spec, state=states[t % R], out=crops[t % R])
-    return handoffs[t % R].gather(crop)
+    if kind == 'fused':
+      return handoffs[t % R].gather()
+    return handoffs[t % R].gather(e.crop(spec, state=states[t % R], out=crops[t % R]))
+
+  n_h = max(2 * R, (min(K, 120) // (2 * R)) * 2 * R)     # even number of calls per batch
   for t in range(2 * R):
     step_and_gather(t)
   barrier()
-  h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  h0.record()
-  n_h = min(K, 120)
-  for t in range(n_h):
-    gathered = step_and_gather(t)
-  h1.record()
+  timed = Timed(torch, dev, step_and_gather, 0, n_h) if kind == 'fused' else None
+  if timed is not None and timed.graphs:
+    timed.run()                                           # upload + first replay, untimed
+    ms_local = timed.time_ms(barrier) / n_h
+    path = timed.path
+  else:
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    h0.record()
+    for t in range(n_h):
+      step_and_gather(t)
+    h1.record()
+    barrier()
+    ms_local = float(h0.elapsed_time(h1)) / n_h
+    path = 'host loop'
+  ms, per_rank = max_over_ranks(torch, dist, dev, world, ms_local)
+  # correctness of the timed transport: one more step through it, and the same
+  # step's tensors through the stand-alone cropper + plain NCCL all-gathers
   barrier()
-  ms, per_rank = max_over_ranks(torch, dist, dev, world, float(h0.elapsed_time(h1)) / n_h)
-  # correctness of the timed transport: the same step's tensors through plain NCCL
-  e = engines[(n_h - 1) % R]
-  want = pdist.allgather_outputs([crops[(n_h - 1) % R], e.reward, e.discount, e.done,
-                                  e.has_reward], world * B)
-  got_view, got_reward, got_disc, got_done, got_has = gathered
-  ok = (bool((got_view == want[0]).all()) and bool((got_reward == want[1]).all()) and
-        bool((got_disc == want[2]).all()) and bool((got_done == want[3]).all()) and
-        bool((got_has == want[4]).all()))
+  gathered = step_and_gather(0)
+  e = engines[0]
+  mine = e.crop(spec, state=states[0], out=crops[0])
+  want = pdist.allgather_outputs([mine, e.reward, e.discount, e.done, e.has_reward], world * B)
+  ok = all(bool((g == w).all()) for g, w in zip(gathered, want))
+  if kind == 'fused':           # keep every batch at an even number of fused calls
+    step_and_gather(0)
   flag = torch.tensor([1 if ok else 0], device=dev)
   dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-  rec = pdist.handoff_record_bytes(81)
+  rec = handoffs[0].rec if kind == 'fused' else pdist.handoff_record_bytes(81)
   return {'what': 'step + 9x9 crop + hand-off of the packed (crop, reward, discount, done) '
-                  'records to every rank', 'transport': transport, 'ms_per_step': ms,
-          'per_rank_ms_per_step': per_rank,
+                  'records to every rank', 'transport': transport, 'launch_path': path,
+          'ms_per_step': ms, 'per_rank_ms_per_step': per_rank, 'steps': n_h,
           'value': world * B / (ms / 1000.0), 'unit': 'env-steps/s',
           'handoff_checked': bool(int(flag.item())),
-          'checked_against': 'dist.all_gather_into_tensor of crop/reward/discount/done/has_reward '
-                             'of the same step, on every rank',
-          'nvlink_bytes_out_per_rank_per_step': (world - 1) * B * rec}
+          'checked_against': 'stand-alone crop kernel + dist.all_gather_into_tensor of '
+                             'crop/reward/discount/done/has_reward of the same step, every rank',
+          'record_bytes': rec,
+          'nvlink_bytes_in_per_rank_per_step': (world - 1) * B * rec}
 
 
 if __name__ == '__main__':

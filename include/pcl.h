@@ -368,6 +368,36 @@ int pcl_pack_handoff_peers(pcl_handle* h, const uint8_t* d_view, int32_t view_by
                            const pcl_outputs* out, uint8_t* const* d_peer_bases,
                            int32_t n_peers, int64_t first_row, void* stream);
 
+/* ScrollingCropper.crop + pcl_pack_handoff_peers + the cross-GPU barrier in ONE
+ * kernel (cropping.py:393-426 for the view): every env's record —
+ * its crop_rows x crop_cols window, zero padding to a multiple of 4, reward i32,
+ * discount f32, done u8, has_reward u8, then zero padding up to `record_bytes` — is
+ * stored with 16-byte stores into row first_row + env of EVERY rank's gather buffer
+ * over NVLink (or once through `d_multicast`, the NVLS multicast mapping of those
+ * buffers).  The last thread block to finish publishes this rank's step count in
+ * every peer's flag array and waits until every peer has published the same count
+ * here: when the kernel retires, half (step & 1) of the LOCAL gather buffer holds
+ * all ranks' records of this step.  No collective call and no separate barrier
+ * kernel; the step count lives in device memory (`d_local`), so the launch can be
+ * captured in a CUDA graph.  Every rank must make the same sequence of calls.
+ *   gather buffer of a rank: u8 [2, rows, record_bytes]  (two halves alternate)
+ *   flag array of a rank:    u32 [PCL_MAX_PEERS], zero-initialised; word s = steps
+ *                            whose records from rank s have landed here
+ *   d_local:                 u32 [2] zero-initialised device memory of this rank
+ * record_bytes: multiple of 16, >= PCL_HANDOFF_RECORD_BYTES(crop rows * cols), <= 256. */
+typedef struct pcl_handoff {
+  int32_t n_peers, rank;
+  int32_t record_bytes;
+  int64_t rows, first_row;
+  uint8_t* d_peer_base[PCL_MAX_PEERS];   /* peer-mapped: every rank's gather buffer */
+  uint32_t* d_peer_flags[PCL_MAX_PEERS]; /* peer-mapped: every rank's flag array   */
+  uint8_t* d_multicast;                  /* multicast mapping of the gather buffers, or NULL */
+  uint32_t* d_local;
+} pcl_handoff;
+int pcl_crop_handoff(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d_board,
+                     int32_t* d_crop_state, const pcl_outputs* out, const pcl_handoff* x,
+                     void* stream);
+
 /* Copy the per-env latched error words (PCL_ENV_ERR_*) to d_out i32 [B]. */
 int pcl_error_codes(pcl_handle* h, int32_t* d_out, void* stream);
 

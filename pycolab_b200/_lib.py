@@ -122,6 +122,17 @@ class CropSpec(C.Structure):
               ('track', C.c_int32 * 4)]      # MAX_TRACK priority list, 0-terminated
 
 
+MAX_PEERS = 8
+
+
+class HandoffState(C.Structure):
+  """include/pcl.h pcl_handoff."""
+  _fields_ = [('n_peers', C.c_int32), ('rank', C.c_int32), ('record_bytes', C.c_int32),
+              ('rows', C.c_int64), ('first_row', C.c_int64),
+              ('d_peer_base', C.c_void_p * MAX_PEERS), ('d_peer_flags', C.c_void_p * MAX_PEERS),
+              ('d_multicast', C.c_void_p), ('d_local', C.c_void_p)]
+
+
 class ObserveSpec(C.Structure):
   _fields_ = [('depth', C.c_int32), ('dtype', C.c_int32), ('stride_b', C.c_int64),
               ('stride_d', C.c_int64), ('stride_r', C.c_int64), ('stride_c', C.c_int64)]
@@ -162,6 +173,8 @@ SYMBOLS = {
     'pcl_pack_handoff_peers': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(Outputs),
                                          C.POINTER(C.c_void_p), C.c_int32, C.c_int64,
                                          C.c_void_p]),
+    'pcl_crop_handoff': (C.c_int, [C.c_void_p, C.POINTER(CropSpec), C.c_void_p, C.c_void_p,
+                                   C.POINTER(Outputs), C.POINTER(HandoffState), C.c_void_p]),
     'pcl_observe': (C.c_int, [C.c_void_p, C.POINTER(ObserveSpec), C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'pcl_error_codes': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

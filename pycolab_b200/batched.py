@@ -423,6 +423,14 @@ class BatchedEngine(object):
         self._h, view.data_ptr(), int(view[0].numel()), C.byref(self._out), ptrs,
         len(peer_ptrs), int(first_row), self._stream()), 'pcl_pack_handoff_peers', self._h)
 
+  def crop_handoff(self, crop_spec, crop_state, handoff_state):
+    """ScrollingCropper.crop + record packing + the all-gather to every rank + the
+    cross-GPU barrier as ONE kernel (`pcl_crop_handoff`, dist.FusedHandoff)."""
+    _lib.check(self._lib.pcl_crop_handoff(
+        self._h, C.byref(crop_spec), self._board.data_ptr(),
+        None if crop_state is None else crop_state.data_ptr(), C.byref(self._out),
+        C.byref(handoff_state), self._stream()), 'pcl_crop_handoff', self._h)
+
   # --- observation post-processors (rendering.py:304-661) over the whole batch
   def to_feature_array(self, layers, permute=None):
     """ObservationToFeatureArray: float32 one-hot planes, [B, C, rows, cols] (or

@@ -658,6 +658,46 @@ int pcl_crop_tracking(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d
   return launched(h, pcl::launch_crop(p, (cudaStream_t)stream), "launch_crop");
 }
 
+int pcl_crop_handoff(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d_board,
+                     int32_t* d_crop_state, const pcl_outputs* out, const pcl_handoff* x,
+                     void* stream) {
+  if (!h || !crop || !d_board || !out || !x) return PCL_ERR_INVALID;
+  if (!h->bound) return PCL_ERR_UNBOUND;
+  if (!out->d_reward || !out->d_has_reward || !out->d_discount || !out->d_done)
+    return PCL_ERR_INVALID;
+  if (crop->rows <= 0 || crop->cols <= 0 || crop->sprite_index >= h->spec.n_sprites)
+    return PCL_ERR_INVALID;
+  for (int i = 0; i < PCL_MAX_TRACK; ++i)
+    if (crop->track[i] < 0) return PCL_ERR_UNSUPPORTED;      // drape tracking: pcl_crop_tracking
+  if (crop->sprite_index >= 0 &&
+      (2 * crop->margin_rows >= crop->rows || 2 * crop->margin_cols >= crop->cols))
+    return PCL_ERR_INVALID;
+  if (crop->pad_char < 0 && (crop->rows > h->spec.rows || crop->cols > h->spec.cols))
+    return PCL_ERR_INVALID;
+  const int view = crop->rows * crop->cols;
+  if (x->n_peers < 1 || x->n_peers > PCL_MAX_PEERS || x->rank < 0 || x->rank >= x->n_peers)
+    return PCL_ERR_INVALID;
+  if ((x->record_bytes & 15) || x->record_bytes < PCL_HANDOFF_RECORD_BYTES(view) ||
+      x->record_bytes > 256) return PCL_ERR_INVALID;
+  if (!x->d_local || x->first_row < 0 || x->first_row + h->batch > x->rows) return PCL_ERR_INVALID;
+  pcl::CropParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = h->batch; p.H = h->spec.rows; p.W = h->spec.cols; p.pitch = h->spec.pitch;
+  p.S = h->spec.n_sprites; p.crop = *crop;
+  p.sprites = h->st.d_sprites; p.plot = h->st.d_plot; p.board = d_board; p.out = nullptr;
+  p.state = d_crop_state;
+  pcl::HandoffParams q;
+  memset(&q, 0, sizeof(q));
+  q.n_peers = x->n_peers; q.rank = x->rank; q.record_bytes = x->record_bytes;
+  q.rows = x->rows; q.first_row = x->first_row;
+  for (int i = 0; i < x->n_peers; ++i) {
+    if (!x->d_peer_base[i] || !x->d_peer_flags[i]) return PCL_ERR_INVALID;
+    q.peer_base[i] = x->d_peer_base[i]; q.peer_flags[i] = x->d_peer_flags[i];
+  }
+  q.multicast = x->d_multicast; q.local = x->d_local; q.out = *out;
+  return launched(h, pcl::launch_crop_handoff(p, q, (cudaStream_t)stream), "launch_crop_handoff");
+}
+
 int pcl_pack_handoff(pcl_handle* h, const uint8_t* d_view, int32_t view_bytes,
                      const pcl_outputs* out, uint8_t* d_packed, void* stream) {
   if (!h || !d_view || !out || !d_packed || view_bytes <= 0) return PCL_ERR_INVALID;

@@ -112,6 +112,19 @@ struct CropParams {
 };
 cudaError_t launch_crop(const CropParams& p, cudaStream_t s);
 
+// Exchange state of the fused crop + hand-off kernel (pcl_crop_handoff).
+struct HandoffParams {
+  int n_peers, rank, record_bytes;
+  int64_t rows;                  // records per half of a gather buffer
+  int64_t first_row;             // this rank's first row
+  uint8_t* peer_base[PCL_MAX_PEERS];    // peer-mapped bases of every rank's gather buffer (2 halves)
+  uint32_t* peer_flags[PCL_MAX_PEERS];  // peer-mapped flag arrays u32 [PCL_MAX_PEERS] of every rank
+  uint8_t* multicast;            // NVLS multicast mapping of the gather buffers, or NULL
+  uint32_t* local;               // device-local u32 [2]: steps done, block ticket
+  pcl_outputs out;
+};
+cudaError_t launch_crop_handoff(const CropParams& p, const HandoffParams& x, cudaStream_t s);
+
 struct PackParams {
   int B, view_bytes, record_bytes;
   const uint8_t* view;           // u8 [B, view_bytes]

@@ -229,13 +229,11 @@ __device__ bool curtain_centroid(const uint8_t* curtain, int H, int W, int pitch
   return true;
 }
 
-// ScrollingCropper.crop (cropping.py:393-426): follow the first visible entity of
-// the tracking list.
-__global__ void __launch_bounds__(128) crop_kernel(const CropParams p) {
-  __shared__ int s_hist[4][256];
-  const int lane = threadIdx.x & 31;
-  const int env = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (env >= p.B) return;
+// ScrollingCropper.crop (cropping.py:393-426) up to the window corner: follow the
+// first visible entity of the tracking list, pan / saccade, persist the corner.
+// Warp-wide; returns the corner every lane must use for _do_crop.
+__device__ __forceinline__ void crop_corner(const CropParams& p, int env, int lane, int* hist,
+                                            int* out_wr, int* out_wc) {
   const pcl_crop_spec& c = p.crop;
   int32_t* plot = p.plot + (int64_t)env * PCL_PLOT_WORDS;
   const bool fixed = c.sprite_index < 0;                  // FixedCropper :229-310
@@ -251,7 +249,7 @@ __global__ void __launch_bounds__(128) crop_kernel(const CropParams p) {
         if (rec[PCL_S_FLAGS] & 1) { have = true; crow = rec[PCL_S_ROW]; ccol = rec[PCL_S_COL]; }
       } else {
         have = curtain_centroid(p.curtains[e] + (int64_t)env * p.H * p.pitch, p.H, p.W, p.pitch,
-                                lane, s_hist[threadIdx.x >> 5], &crow, &ccol);
+                                lane, hist, &crow, &ccol);
       }
     }
   }
@@ -303,17 +301,136 @@ __global__ void __launch_bounds__(128) crop_kernel(const CropParams p) {
     state[0] = wr; state[1] = wc; state[2] = 1;
     if (p.state) state[3] = episode;
   }
-  // _do_crop :118-227: pad fill + window copy.
-  const uint8_t* board = p.board + (int64_t)env * p.H * p.pitch;
-  uint8_t* out = p.out + (int64_t)env * c.rows * c.cols;
-  const int cells = c.rows * c.cols;
-  for (int i = lane; i < cells; i += 32) {
-    const int r = wr + i / c.cols, cc2 = wc + i % c.cols;
-    uint8_t v = pad ? (uint8_t)c.pad_char : 0;
+  *out_wr = wr; *out_wc = wc;
+}
+
+// Four consecutive cells i .. i + 3 of the crop window (row-major over rows x cols)
+// as one little-endian word, pad character outside the board (_do_crop :118-227).
+__device__ __forceinline__ uint32_t crop_word(const CropParams& p, const uint8_t* board, int wr,
+                                              int wc, int i, int cells) {
+  const pcl_crop_spec& c = p.crop;
+  const uint32_t padv = c.pad_char >= 0 ? (uint32_t)c.pad_char : 0u;
+  uint32_t v = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int j = i + k;
+    if (j >= cells) break;
+    const int r = wr + j / c.cols, cc2 = wc + j % c.cols;
+    uint32_t b = padv;
     if ((unsigned)r < (unsigned)p.H && (unsigned)cc2 < (unsigned)p.W)
-      v = board[(int64_t)r * p.pitch + cc2];
-    out[i] = v;
+      b = board[(int64_t)r * p.pitch + cc2];
+    v |= b << (8 * k);
   }
+  return v;
+}
+
+__global__ void __launch_bounds__(128) crop_kernel(const CropParams p) {
+  __shared__ int s_hist[4][256];
+  const int lane = threadIdx.x & 31;
+  const int env = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (env >= p.B) return;
+  int wr, wc;
+  crop_corner(p, env, lane, s_hist[threadIdx.x >> 5], &wr, &wc);
+  // _do_crop :118-227: pad fill + window copy, 4 cells per lane per round; word
+  // stores wherever the env's output row is word aligned (cells % 4 == 0 or env
+  // aligned), bytes for the ragged rest.
+  const uint8_t* board = p.board + (int64_t)env * p.H * p.pitch;
+  const int cells = p.crop.rows * p.crop.cols;
+  uint8_t* out = p.out + (int64_t)env * cells;
+  const int mis = (int)(reinterpret_cast<uintptr_t>(out) & 3);     // bytes before the first aligned word
+  const int head = mis ? 4 - mis : 0;
+  if (lane < head && lane < cells) {
+    const uint32_t v = crop_word(p, board, wr, wc, lane, cells);
+    out[lane] = (uint8_t)v;
+  }
+  for (int i = head + lane * 4; i < cells; i += 128) {
+    const uint32_t v = crop_word(p, board, wr, wc, i, cells);
+    if (i + 4 <= cells) {
+      *reinterpret_cast<uint32_t*>(out + i) = v;
+    } else {
+      for (int k = 0; i + k < cells; ++k) out[i + k] = (uint8_t)(v >> (8 * k));
+    }
+  }
+}
+
+// ---- crop + pack + all-gather + signal in ONE kernel -------------
+// One warp per env: window corner (as crop_kernel), the crop gathered straight into
+// the env's hand-off record (view bytes, reward, discount, done | has_reward << 8),
+// the record stored with 16-byte stores into row first_row + env of EVERY rank's
+// gather buffer over NVLink (or once through the NVLS multicast address).  The last
+// block to finish publishes this rank's step number in every peer's flag word and
+// then waits until every peer has published the same step here, so when the kernel
+// retires the local gather buffer holds all ranks' records: no collective call, no
+// separate barrier kernel.  Two halves alternate by step parity; the step counter
+// lives in device memory, so the launch is CUDA-graph capturable.
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_v4(void* mc, uint4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+               :: "l"(mc), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)),
+                  "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)) : "memory");
+}
+
+__global__ void __launch_bounds__(128) crop_handoff_kernel(const CropParams p,
+                                                           const HandoffParams x) {
+  __shared__ int s_hist[4][256];
+  __shared__ __align__(16) uint32_t s_rec[4][64];          // record words of this block's envs
+  __shared__ int s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int env = blockIdx.x * 4 + warp;
+  const uint32_t step = x.local[0];                        // steps completed so far
+  const int64_t half = (int64_t)(step & 1u) * x.rows * x.record_bytes;
+  if (env < p.B) {
+    int wr, wc;
+    crop_corner(p, env, lane, s_hist[warp], &wr, &wc);
+    const uint8_t* board = p.board + (int64_t)env * p.H * p.pitch;
+    const int cells = p.crop.rows * p.crop.cols;
+    const int view_words = (cells + 3) >> 2, words = x.record_bytes >> 2;
+    for (int w = lane; w < words; w += 32) {
+      uint32_t v = 0;                                      // padding up to record_bytes
+      if (w < view_words) v = crop_word(p, board, wr, wc, w * 4, cells);
+      else if (w == view_words) v = (uint32_t)x.out.d_reward[env];
+      else if (w == view_words + 1) v = __float_as_uint(x.out.d_discount[env]);
+      else if (w == view_words + 2)
+        v = (uint32_t)x.out.d_done[env] | ((uint32_t)x.out.d_has_reward[env] << 8);
+      s_rec[warp][w] = v;
+    }
+    __syncwarp();
+    const int64_t row_off = half + (x.first_row + env) * x.record_bytes;
+    const int vecs = x.record_bytes >> 4;                  // record_bytes is a multiple of 16 here
+    if (x.multicast) {
+      for (int q = lane; q < vecs; q += 32)
+        multimem_st_v4(x.multicast + row_off + q * 16,
+                       *reinterpret_cast<const uint4*>(&s_rec[warp][q * 4]));
+    } else {
+      for (int q = lane; q < vecs * x.n_peers; q += 32) {
+        const int d = q / vecs, k = q - d * vecs;
+        *reinterpret_cast<uint4*>(x.peer_base[d] + row_off + k * 16) =
+            *reinterpret_cast<const uint4*>(&s_rec[warp][k * 4]);
+      }
+    }
+  }
+  // ---- publish: every block fences its peer stores, the last one signals --------
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&x.local[1], 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  if (threadIdx.x < x.n_peers)                             // my step has landed on peer d
+    st_release_sys(x.peer_flags[threadIdx.x] + x.rank, step + 1);
+  if (threadIdx.x < x.n_peers) {                           // wait for every peer's records
+    const uint32_t* mine = x.peer_flags[x.rank] + threadIdx.x;
+    while ((int32_t)(ld_acquire_sys(mine) - (step + 1)) < 0) { __nanosleep(20); }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { x.local[1] = 0; x.local[0] = step + 1; __threadfence(); }
 }
 
 }  // namespace
@@ -337,6 +454,10 @@ cudaError_t launch_layers(const LayersParams& p, cudaStream_t s) {
 }
 cudaError_t launch_crop(const CropParams& p, cudaStream_t s) {
   crop_kernel<<<(p.B + 3) / 4, 128, 0, s>>>(p);
+  return cudaGetLastError();
+}
+cudaError_t launch_crop_handoff(const CropParams& p, const HandoffParams& x, cudaStream_t s) {
+  crop_handoff_kernel<<<(p.B + 3) / 4, 128, 0, s>>>(p, x);
   return cudaGetLastError();
 }
 

@@ -72,14 +72,16 @@ def handoff_record_bytes(view_bytes):
 def unpack_handoff(records, view_shape):
   """Views into packed hand-off records u8 [N, record_bytes] (no copies):
   (view u8 [N, *view_shape], reward i32 [N], discount f32 [N], done u8 [N],
-  has_reward u8 [N])."""
+  has_reward u8 [N]).  record_bytes may exceed PCL_HANDOFF_RECORD_BYTES (the fused
+  path pads records to a multiple of 16)."""
   import torch
   view_bytes = 1
   for d in view_shape:
     view_bytes *= int(d)
   word = ((view_bytes + 3) & ~3) // 4
   n = records.shape[0]
-  assert records.dtype == torch.uint8 and records.shape[1] == handoff_record_bytes(view_bytes)
+  assert records.dtype == torch.uint8 and records.shape[1] >= handoff_record_bytes(view_bytes)
+  assert records.shape[1] % 4 == 0
   view = records[:, :view_bytes].reshape((n,) + tuple(view_shape))
   return (view, records.view(torch.int32)[:, word], records.view(torch.float32)[:, word + 1],
           records[:, 4 * word + 8], records[:, 4 * word + 9])
@@ -158,6 +160,86 @@ class PeerHandoff(object):
     self.step += 1
     self.engine.pack_handoff_peers(view, self.peer_ptrs[k], self.first_row)
     self.handle.barrier(channel=0)            # all ranks' stores have been issued and finished
+    records = self.halves[k]
+    if any(c != self.biggest for c in self.counts):
+      import torch
+      records = torch.cat([records[r * self.biggest: r * self.biggest + c]
+                           for r, c in enumerate(self.counts)])
+    return unpack_handoff(records, self.view_shape)
+
+
+class FusedHandoff(object):
+  """The per-step hand-off as ONE kernel per rank (`pcl_crop_handoff`): the cropper,
+  the record packing, the stores into every rank's gather buffer over NVLink (or one
+  NVLS multicast store) and the cross-GPU flag barrier.  Gather buffers and flag
+  arrays live in symmetric memory; nothing from a collective library runs per step
+  and the launch can be captured in a CUDA graph (the step counter is on the
+  device).  With a single rank it degenerates to crop + pack into a local buffer."""
+
+  def __init__(self, engine, crop_spec, global_batch, group=None, multicast=True):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from pycolab_b200 import _lib
+    self.engine, self.crop_spec = engine, crop_spec
+    self.view_shape = (int(crop_spec.rows), int(crop_spec.cols))
+    self.view_bytes = self.view_shape[0] * self.view_shape[1]
+    if dist.is_available() and dist.is_initialized():
+      group = group if group is not None else dist.group.WORLD
+      world, rank = dist.get_world_size(group), dist.get_rank(group)
+    else:
+      world, rank = 1, 0
+    self.counts = [shard_range(global_batch, r, world)[1] for r in range(world)]
+    assert self.counts[rank] == engine.batch
+    self.biggest = max(self.counts)
+    self.rows = world * self.biggest
+    self.rec = (handoff_record_bytes(self.view_bytes) + 15) & ~15
+    self.first_row = rank * self.biggest
+    half = self.rows * self.rec
+    flag_bytes = 256
+    total = 2 * half + flag_bytes
+    self.handle = None
+    mc_ptr = 0
+    if world > 1:
+      import torch.distributed._symmetric_memory as symm_mem
+      self.buffer = symm_mem.empty(total, dtype=torch.uint8, device=engine.device)
+      self.buffer.zero_()
+      self.handle = symm_mem.rendezvous(self.buffer, group)
+      bases = [int(p) for p in self.handle.buffer_ptrs]
+      if multicast:
+        try:
+          mc_ptr = int(getattr(self.handle, 'multicast_ptr', 0) or 0)
+        except Exception:           # noqa: BLE001 - no NVLS on this box: unicast stores
+          mc_ptr = 0
+    else:
+      self.buffer = torch.zeros(total, dtype=torch.uint8, device=engine.device)
+      bases = [self.buffer.data_ptr()]
+    self.transport = 'NVLS multicast stores' if mc_ptr else (
+        'peer-to-peer stores' if world > 1 else 'local stores (single rank)')
+    self.local = torch.zeros(2, dtype=torch.int32, device=engine.device)
+    st = _lib.HandoffState()
+    st.n_peers, st.rank, st.record_bytes = world, rank, self.rec
+    st.rows, st.first_row = self.rows, self.first_row
+    for i, b in enumerate(bases):
+      st.d_peer_base[i] = b
+      st.d_peer_flags[i] = b + 2 * half
+    st.d_multicast = mc_ptr or None
+    st.d_local = self.local.data_ptr()
+    self._state = st
+    self.halves = [self.buffer[k * half:(k + 1) * half].view(self.rows, self.rec)
+                   for k in (0, 1)]
+    self.crop_state = engine.new_crop_state()
+    self.step = 0
+    torch.cuda.synchronize(engine.device)
+    if self.handle is not None:
+      self.handle.barrier(channel=0)          # everyone's buffers exist and are zeroed
+
+  def gather(self):
+    """Crop the engine's last boards and exchange: (view u8 [N, rows, cols], reward,
+    discount, done, has_reward) of ALL ranks' envs, views into this rank's buffer."""
+    k = self.step & 1
+    self.step += 1
+    self.engine.crop_handoff(self.crop_spec, self.crop_state, self._state)
     records = self.halves[k]
     if any(c != self.biggest for c in self.counts):
       import torch

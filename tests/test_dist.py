@@ -134,6 +134,9 @@ def _peer_worker(rank, world, port, ok):
   eng.its_showtime()
   spec = batched.scrolling_crop_spec(9, 9, 0, pad_char=' ', scroll_margins=(None, None))
   nccl, peer = pdist.Handoff(eng, (9, 9), total), pdist.PeerHandoff(eng, (9, 9), total)
+  # the one-kernel path (crop + pack + stores + flag barrier), unicast and multicast
+  fused = [pdist.FusedHandoff(eng, spec, total, multicast=False),
+           pdist.FusedHandoff(eng, spec, total, multicast=True)]
   rs = np.random.RandomState(rank)
   for _ in range(25):
     eng.play(torch.from_numpy(rs.randint(0, 5, size=eng.batch).astype(np.int32)).cuda())
@@ -143,6 +146,10 @@ def _peer_worker(rank, world, port, ok):
     torch.cuda.synchronize()
     good = good and all(bool((g == w).all()) for g, w in zip(got, want))
     good = good and got[0].shape == (total, 9, 9)
+    for f in fused:                            # each owns its cropper state: same windows
+      got = f.gather()
+      torch.cuda.synchronize()
+      good = good and all(bool((g == w).all()) for g, w in zip(got, want))
   ok[rank] = 1 if good else 0
   dist.destroy_process_group()
 
@@ -181,6 +188,46 @@ def test_pack_handoff_kernel_matches_the_record_layout():
                         res.done.cpu().numpy(), res.has_reward.cpu().numpy())
     np.testing.assert_array_equal(packed[:37].cpu().numpy(), want)
     assert not packed[37:].any()
+
+
+@pytest.mark.gpu
+def test_fused_crop_handoff_kernel_single_rank():
+  """`pcl_crop_handoff` with one rank = crop_kernel + pack_handoff_kernel: same
+  windows (own cropper state), same records, alternating halves, CUDA-graph
+  replayable because the step counter lives on the device."""
+  import torch
+  from pycolab_b200 import batched, levels
+  from pycolab_b200.games import scrolly_maze
+  arts = [levels.scrolly_maze_level(70 + i, world_shape=(65, 65), board_shape=(30, 45))
+          for i in range(2)]
+  eng = batched.BatchedEngine([scrolly_maze.make_game(*a) for a in arts], batch=37)
+  eng.its_showtime()
+  rs = np.random.RandomState(1)
+  spec = batched.scrolling_crop_spec(9, 9, 0, pad_char=' ', scroll_margins=(None, None))
+  state = eng.new_crop_state()
+  fused = pdist.FusedHandoff(eng, spec, 37)
+  assert fused.rec == 96 and fused.transport.startswith('local')
+  for t in range(41):
+    res = eng.play(torch.from_numpy(rs.randint(0, 5, size=37).astype(np.int32)).cuda())
+    crop = eng.crop(spec, state=state)
+    view, reward, discount, done, has = fused.gather()
+    torch.cuda.synchronize()
+    assert bool((view == crop).all()), t
+    assert bool((reward == res.reward).all()) and bool((discount == res.discount).all())
+    assert bool((done == res.done).all()) and bool((has == res.has_reward).all())
+    assert int(fused.local[0]) == t + 1 and int(fused.local[1]) == 0
+  # an odd view size whose record needs zero padding up to a multiple of 16
+  spec2 = batched.scrolling_crop_spec(5, 7, 0, pad_char='.', scroll_margins=(1, 2))
+  fused2 = pdist.FusedHandoff(eng, spec2, 37)
+  state2 = eng.new_crop_state()
+  assert fused2.rec == 48
+  for t in range(6):
+    eng.play(torch.from_numpy(rs.randint(0, 5, size=37).astype(np.int32)).cuda())
+    crop = eng.crop(spec2, state=state2)
+    view = fused2.gather()[0]
+    torch.cuda.synchronize()
+    assert bool((view == crop).all()), t
+    assert not fused2.halves[t & 1][:, 35 + 1 + 12:].any()    # padding stays zero
 
 
 @pytest.mark.gpu
