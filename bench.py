@@ -334,10 +334,11 @@ class Timed(object):
     self.path = 'host loop of pcl_step calls (CUDA graph capture unavailable)'
     try:
       torch.cuda.synchronize(dev)
-      gw, gt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-      with torch.cuda.graph(gw):
-        for t in range(n_warm):
-          step_fn(t)
+      gw, gt = (torch.cuda.CUDAGraph() if n_warm > 0 else None), torch.cuda.CUDAGraph()
+      if gw is not None:
+        with torch.cuda.graph(gw):
+          for t in range(n_warm):
+            step_fn(t)
       with torch.cuda.graph(gt):
         for t in range(n_steps):
           step_fn(n_warm + t)
@@ -352,7 +353,8 @@ class Timed(object):
 
   def warm(self):
     if self.graphs:
-      self.graphs[0].replay()
+      if self.graphs[0] is not None:
+        self.graphs[0].replay()
     else:
       for t in range(self.n_warm):
         self.step_fn(t)
