@@ -5,6 +5,8 @@
 
 #include <new>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges show up in nsys / ncu timelines
+
 #include "pcl_device.cuh"
 #include "pcl_kernels.cuh"
 
@@ -30,6 +32,13 @@ struct pcl_handle {
 namespace {
 
 using pcl::StepParams;
+
+// One NVTX range per boundary call (a no-op costing a pointer test when no tool
+// is attached); the ranges name the reference call each entry point stands for.
+struct Range {
+  explicit Range(const char* name) { nvtxRangePushA(name); }
+  ~Range() { nvtxRangePop(); }
+};
 
 // Remember what failed: PCL_ERR_CUDA alone says nothing (pcl_last_error).
 int cuda_failed(pcl_handle* h, cudaError_t e, const char* what) {
@@ -378,6 +387,7 @@ int pcl_bind_state(pcl_handle* h, const pcl_state* st) {
 }
 
 int pcl_reset(pcl_handle* h, const uint8_t* d_env_mask, const pcl_outputs* out, void* stream) {
+  Range nvtx_range("pcl_reset (Engine.its_showtime)");
   const int r = check_ready(h, out);
   if (r != PCL_OK) return r;
   StepParams p = h->base;
@@ -388,6 +398,7 @@ int pcl_reset(pcl_handle* h, const uint8_t* d_env_mask, const pcl_outputs* out, 
 }
 
 int pcl_step(pcl_handle* h, const int32_t* d_actions, const pcl_outputs* out, void* stream) {
+  Range nvtx_range("pcl_step (Engine.play)");
   const int r = check_ready(h, out);
   if (r != PCL_OK) return r;
   if (!d_actions) return PCL_ERR_INVALID;
@@ -400,6 +411,7 @@ int pcl_step(pcl_handle* h, const int32_t* d_actions, const pcl_outputs* out, vo
 
 int pcl_run(pcl_handle* h, const int32_t* d_actions, int steps, const pcl_outputs* out,
             void* stream) {
+  Range nvtx_range("pcl_run");
   const int r = check_ready(h, out);
   if (r != PCL_OK) return r;
   if (!d_actions || steps < 0) return PCL_ERR_INVALID;
@@ -416,6 +428,7 @@ int pcl_run(pcl_handle* h, const int32_t* d_actions, int steps, const pcl_output
 
 int pcl_run_many(pcl_handle* const* handles, int n_handles, const int32_t* const* d_actions,
                  const pcl_outputs* const* outs, int steps, void* stream) {
+  Range nvtx_range("pcl_run_many");
   if (!handles || !d_actions || !outs || n_handles < 1 || steps < 0) return PCL_ERR_INVALID;
   for (int i = 0; i < n_handles; ++i) {
     const int r = check_ready(handles[i], outs[i]);
@@ -475,6 +488,7 @@ int host_pipeline_ready(pcl_handle* h) {
 int pcl_step_host(pcl_handle* h, const int32_t* h_actions, int32_t* d_actions,
                   const pcl_outputs* out, uint8_t* h_board, int32_t* h_reward,
                   uint8_t* h_has_reward, float* h_discount, uint8_t* h_done, void* stream) {
+  Range nvtx_range("pcl_step_host");
   const int r = check_ready(h, out);
   if (r != PCL_OK) return r;
   if (!h_actions || !d_actions) return PCL_ERR_INVALID;
@@ -494,6 +508,7 @@ int pcl_step_host_async(pcl_handle* h, const int32_t* h_actions, int32_t* d_acti
                         int32_t* d_crop_state, uint8_t* h_view, int32_t* h_reward,
                         uint8_t* h_has_reward, float* h_discount, uint8_t* h_done, int slot,
                         void* stream) {
+  Range nvtx_range("pcl_step_host_async");
   const int r = check_ready(h, out);
   if (r != PCL_OK) return r;
   if (!h_actions || !d_actions || slot < 0 || slot >= PCL_HOST_SLOTS) return PCL_ERR_INVALID;
@@ -533,6 +548,7 @@ int pcl_host_wait(pcl_handle* h, int slot) {
 int pcl_render(pcl_handle* h, const uint8_t* d_backdrop, int64_t backdrop_bstride,
                const uint8_t* d_curtains, const int32_t* d_sprites, const uint8_t* d_z_order,
                uint8_t* d_board, void* stream) {
+  Range nvtx_range("pcl_render (Engine._render)");
   if (!h || !d_backdrop || !d_z_order || !d_board) return PCL_ERR_INVALID;
   if (h->spec.n_drapes > 0 && !d_curtains) return PCL_ERR_INVALID;
   if (h->spec.n_sprites > 0 && !d_sprites) return PCL_ERR_INVALID;
@@ -581,6 +597,7 @@ int pcl_export_curtain(pcl_handle* h, int drape_index, uint8_t* d_out, void* str
 
 int pcl_layers(pcl_handle* h, const uint8_t* chars, int32_t n_chars, uint8_t* d_out,
                void* stream) {
+  Range nvtx_range("pcl_layers");
   if (!h || !chars || !d_out || n_chars < 1 || n_chars > PCL_MAX_LAYER_CHARS)
     return PCL_ERR_INVALID;
   if (!h->bound) return PCL_ERR_UNBOUND;
@@ -628,6 +645,7 @@ int pcl_crop(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d_board, u
 int pcl_crop_tracking(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d_board,
                       uint8_t* d_crop, int32_t* d_crop_state,
                       const uint8_t* const* d_curtains, void* stream) {
+  Range nvtx_range("pcl_crop (ScrollingCropper.crop)");
   if (!h || !crop || !d_board || !d_crop) return PCL_ERR_INVALID;
   if (!h->bound) return PCL_ERR_UNBOUND;
   if (crop->rows <= 0 || crop->cols <= 0 || crop->sprite_index >= h->spec.n_sprites)
@@ -661,6 +679,7 @@ int pcl_crop_tracking(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d
 int pcl_crop_handoff(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d_board,
                      int32_t* d_crop_state, const pcl_outputs* out, const pcl_handoff* x,
                      void* stream) {
+  Range nvtx_range("pcl_crop_handoff");
   if (!h || !crop || !d_board || !out || !x) return PCL_ERR_INVALID;
   if (!h->bound) return PCL_ERR_UNBOUND;
   if (!out->d_reward || !out->d_has_reward || !out->d_discount || !out->d_done)
@@ -735,6 +754,7 @@ int pcl_pack_handoff_peers(pcl_handle* h, const uint8_t* d_view, int32_t view_by
 int pcl_observe(pcl_handle* h, const pcl_observe_spec* spec, const void* d_table,
                 const uint8_t* d_valid, const uint8_t* d_board, void* d_out,
                 int32_t* d_unknown, void* stream) {
+  Range nvtx_range("pcl_observe");
   if (!h || !spec || !d_table || !d_board || !d_out) return PCL_ERR_INVALID;
   if (spec->depth < 1 || spec->depth > 32 || spec->dtype < 0 || spec->dtype > 4)
     return PCL_ERR_INVALID;

@@ -7,6 +7,8 @@
 // occlusion flatten down the z-order is done per 16-byte segment with byte-SIMD
 // rank compares so that all (1 + D) loads of a segment are issued up front and
 // no register array is indexed dynamically.
+#include <stdlib.h>
+
 #include "pcl_device.cuh"
 #include "pcl_kernels.cuh"
 
@@ -112,6 +114,118 @@ render_kernel(const RenderParams p) {
 #pragma unroll
       for (int d = 0; d < MAXD; ++d)
         if (d < p.D) cur[d] = __ldg(reinterpret_cast<const uint4*>(curtains + d * plane + off));
+    }
+  }
+}
+
+// ---- persistent, warp-granular variant ----------------------------------------
+// One-env CTAs leave a 4096-env launch with 3.46 waves of 256-thread blocks (ramp +
+// a half-empty last wave).  Here the grid is sized to the machine (148 SMs x 4 CTAs
+// x 8 warps) and every WARP walks quarter-env items (H/4 rows) with a static
+// stride: 16 384 items over 4 736 warps keeps every SM busy until the end, and the
+// per-env header (z-order ranks, sprite cells) is decoded with shuffles/ballots
+// instead of shared memory + __syncthreads.
+constexpr int kRenderCtasPerSm = 4;
+
+template <int MAXD, int MAXS>
+__global__ void __launch_bounds__(kRenderThreads)
+render_kernel_warp(const RenderParams p, const int parts) {
+  const int lane = threadIdx.x & 31;
+  const int warps_total = (gridDim.x * kRenderThreads) >> 5;
+  const int warp_id = (blockIdx.x * kRenderThreads + threadIdx.x) >> 5;
+  const int n = p.S + p.D;
+  const int segs_per_row = p.pitch >> 4;
+  const int rows_per_part = (p.H + parts - 1) / parts;
+  const int64_t plane = (int64_t)p.H * p.pitch;
+  const int64_t items = (int64_t)p.B * parts;
+  for (int64_t item = warp_id; item < items; item += warps_total) {
+    const int env = (int)(item / parts), part = (int)(item - (int64_t)env * parts);
+    const int r0 = part * rows_per_part, r1 = min(p.H, r0 + rows_per_part);
+    const int seg0 = r0 * segs_per_row, seg1 = r1 * segs_per_row;
+    const uint8_t* backdrop = p.backdrop + (int64_t)env * p.backdrop_bstride;
+    const uint8_t* curtains = p.curtains + (int64_t)env * p.D * plane;
+    uint8_t* board = p.board + (int64_t)env * plane;
+    // Tile loads of the first round go out before the header decode.
+    int seg = seg0 + lane;
+    uint4 px = make_uint4(0, 0, 0, 0);
+    uint4 cur[MAXD];
+    if (seg < seg1) {
+      const int64_t off = (int64_t)seg << 4;
+      px = __ldg(reinterpret_cast<const uint4*>(backdrop + off));
+#pragma unroll
+      for (int d = 0; d < MAXD; ++d)
+        if (d < p.D) cur[d] = __ldg(reinterpret_cast<const uint4*>(curtains + d * plane + off));
+    }
+    // Header: lane k < n holds z-order entry k; an entity's rank is the position of
+    // its character in the env's z-order (engine.py:751), found with one ballot.
+    const uint8_t zch = lane < n ? p.z_order[(int64_t)env * n + lane] : 0;
+    uint32_t rank_d[MAXD];
+#pragma unroll
+    for (int d = 0; d < MAXD; ++d) {
+      const unsigned hit = __ballot_sync(0xffffffffu, d < p.D && lane < n && zch == p.drape_char[d]);
+      rank_d[d] = (uint32_t)__ffs(hit) * 0x01010101u;
+    }
+    // Lane s < S holds sprite s: its segment (or -1), word, byte cover and rank.
+    int my_seg = -1, my_word = 0;
+    uint32_t my_cover = 0, my_rank = 0, my_ch4 = 0;
+    {
+      int sidx = lane < p.S ? lane : 0;
+      const int32_t* rec = p.sprites + ((int64_t)env * p.S + sidx) * PCL_SPRITE_WORDS;
+      int row = 0, col = 0, flags = 0;
+      if (lane < p.S) { row = rec[PCL_S_ROW]; col = rec[PCL_S_COL]; flags = rec[PCL_S_FLAGS]; }
+#pragma unroll
+      for (int s2 = 0; s2 < MAXS; ++s2) {
+        const unsigned hit = __ballot_sync(0xffffffffu, s2 < p.S && lane < n && zch == p.sprite_char[s2]);
+        if (lane == s2) {                   // static index: no local copy of the param block
+          my_rank = (uint32_t)__ffs(hit) * 0x01010101u;
+          my_ch4 = p.sprite_char[s2] * 0x01010101u;
+        }
+      }
+      if (lane < p.S) {
+        my_seg = (flags & 1) ? row * segs_per_row + (col >> 4) : -1;     // engine.py:754
+        my_word = (col & 15) >> 2;
+        my_cover = 0xffu << ((col & 3) * 8);
+      }
+    }
+    while (true) {
+      const bool live = seg < seg1;
+      uint4 rk = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int d = 0; d < MAXD; ++d) {
+        if (d < p.D) {
+          const uint32_t ch4 = p.drape_char[d] * 0x01010101u;
+          overlay(px.x, rk.x, __vcmpne4(cur[d].x, 0), ch4, rank_d[d]);   // rendering.py:160
+          overlay(px.y, rk.y, __vcmpne4(cur[d].y, 0), ch4, rank_d[d]);
+          overlay(px.z, rk.z, __vcmpne4(cur[d].z, 0), ch4, rank_d[d]);
+          overlay(px.w, rk.w, __vcmpne4(cur[d].w, 0), ch4, rank_d[d]);
+        }
+      }
+#pragma unroll
+      for (int s2 = 0; s2 < MAXS; ++s2) {
+        if (s2 < p.S) {                                                   // rendering.py:139
+          const int sseg = __shfl_sync(0xffffffffu, my_seg, s2);
+          const int w = __shfl_sync(0xffffffffu, my_word, s2);
+          const uint32_t cover = __shfl_sync(0xffffffffu, my_cover, s2);
+          const uint32_t r4 = __shfl_sync(0xffffffffu, my_rank, s2);
+          const uint32_t ch4 = __shfl_sync(0xffffffffu, my_ch4, s2);
+          if (live && sseg == seg) {
+            if (w == 0) overlay(px.x, rk.x, cover, ch4, r4);
+            else if (w == 1) overlay(px.y, rk.y, cover, ch4, r4);
+            else if (w == 2) overlay(px.z, rk.z, cover, ch4, r4);
+            else overlay(px.w, rk.w, cover, ch4, r4);
+          }
+        }
+      }
+      if (live) *reinterpret_cast<uint4*>(board + ((int64_t)seg << 4)) = px;
+      seg += 32;
+      if (__all_sync(0xffffffffu, seg >= seg1)) break;
+      if (seg < seg1) {
+        const int64_t off = (int64_t)seg << 4;
+        px = __ldg(reinterpret_cast<const uint4*>(backdrop + off));
+#pragma unroll
+        for (int d = 0; d < MAXD; ++d)
+          if (d < p.D) cur[d] = __ldg(reinterpret_cast<const uint4*>(curtains + d * plane + off));
+      }
     }
   }
 }
@@ -437,6 +551,25 @@ __global__ void __launch_bounds__(128) crop_handoff_kernel(const CropParams p,
 
 cudaError_t launch_render(const RenderParams& p, cudaStream_t s) {
   // Loop bounds are compile-time so the per-segment code stays small.
+  static const bool block_per_env = getenv("PCL_RENDER_BLOCK_PER_ENV") != nullptr;   // A/B switch
+  if (!block_per_env && p.S + p.D <= 32 && p.S <= 16) {
+    // Persistent warp-granular kernel: part = the largest power of two <= 8 that
+    // leaves every part at least one 32-segment round.
+    const int segs = p.H * (p.pitch >> 4);
+    int parts = 1;
+    while (parts < 8 && segs / (parts * 2) >= 32) parts *= 2;
+    const int64_t items = (int64_t)p.B * parts;
+    int64_t ctas = (items * 32 + kRenderThreads - 1) / kRenderThreads;
+    const int64_t cap = 148 * kRenderCtasPerSm;
+    if (ctas > cap) ctas = cap;
+    const int grid = (int)ctas;
+    if (p.D <= 2 && p.S <= 4) render_kernel_warp<2, 4><<<grid, kRenderThreads, 0, s>>>(p, parts);
+    else if (p.D <= 2 && p.S <= 8) render_kernel_warp<2, 8><<<grid, kRenderThreads, 0, s>>>(p, parts);
+    else if (p.D <= 2) render_kernel_warp<2, 16><<<grid, kRenderThreads, 0, s>>>(p, parts);
+    else if (p.S <= 4) render_kernel_warp<8, 4><<<grid, kRenderThreads, 0, s>>>(p, parts);
+    else render_kernel_warp<8, 16><<<grid, kRenderThreads, 0, s>>>(p, parts);
+    return cudaGetLastError();
+  }
   if (p.D <= 2 && p.S <= 4) render_kernel<2, 4><<<p.B, kRenderThreads, 0, s>>>(p);
   else if (p.D <= 2 && p.S <= 8) render_kernel<2, 8><<<p.B, kRenderThreads, 0, s>>>(p);
   else if (p.D <= 2) render_kernel<2, 16><<<p.B, kRenderThreads, 0, s>>>(p);
