@@ -71,9 +71,18 @@ typedef enum pcl_program {
   PCL_PROG_BETTER_SCROLLY = 5, /* examples/better_scrolly_maze.py:209-324       */
   PCL_PROG_CLASSICS = 6,     /* one-walker games: examples/classics/{four_rooms,cliff_walk,
                                 chain_walk}.py, examples/fluvial_natation.py */
-  PCL_PROG_APERTURE = 7      /* examples/aperture.py:118-196; the drape record's AUX0 / AUX1 hold
+  PCL_PROG_APERTURE = 7,     /* examples/aperture.py:118-196; the drape record's AUX0 / AUX1 hold
                                 the two aperture cells (row << 16 | col, -1 = none) */
+  PCL_PROG_ORDEAL = 8        /* examples/ordeal.py:74-266: program_arg[0] = PCL_ORDEAL_* chapter;
+                                plot words AUX0 has_sword, AUX1 last_position (row << 16 | col,
+                                -1 unset), AUX2 next_chapter chosen on the device, AUX3 prior chapter */
 } pcl_program;
+
+/* PCL_PROG_ORDEAL chapters (storytelling.Story keys of ordeal.py:94-97); AUX2 holds
+ * PCL_ORDEAL_NEXT_UNSET until an entity names the next chapter, PCL_ORDEAL_NEXT_NONE for
+ * `next_chapter = None`. */
+enum { PCL_ORDEAL_NEXT_UNSET = -1, PCL_ORDEAL_NEXT_NONE = 0,
+       PCL_ORDEAL_CASTLE = 1, PCL_ORDEAL_CAVERN = 2, PCL_ORDEAL_KANSAS = 3 };
 
 /* PCL_PROG_CLASSICS: pcl_spec.program_arg[0] selects the rule set; the games
  * pay float rewards (1.0, -1.0, -100.0, 100.0) which d_reward carries as the

@@ -568,3 +568,115 @@ def fixture_program(world, ch, actions):
       world.plot.terminate_episode()
     if actions.get('_z') is not None:
       world.plot.change_z_order(*actions['_z'])
+
+
+# ==========================================================================
+# ordeal: three sub-games chained by storytelling.Story; the
+# one real user of Plot.change_z_order (examples/ordeal.py:182-185).
+# ==========================================================================
+
+ORDEAL_CHAPTERS = ('castle', 'cavern', 'kansas')
+
+
+def make_ordeal(chapter, art, story_plot=None):
+  """One chapter of examples/ordeal.py:74-97.  `story_plot`: what Story hands the
+  new Engine's Plot (storytelling.py:449-457): dict(has_sword, last_position,
+  prior_chapter); None for the first chapter."""
+  assert chapter in ORDEAL_CHAPTERS
+  story_plot = dict(story_plot or {})
+  beneath = '~' if chapter == 'kansas' else ' '
+  chars = {'castle': 'PD', 'cavern': 'PS', 'kansas': 'P'}[chapter]
+  backdrop, masks = split_art(art, list(chars), beneath)
+  shape = backdrop.shape
+  things = {'P': em.Walker('P', shape, mask_position(masks['P']), impassable='@#w',
+                           confined=True)}                       # ordeal.py:199-202
+  if chapter == 'castle':                                        # :137-140
+    things['D'] = em.Walker('D', shape, mask_position(masks['D']), impassable='#',
+                            confined=True)
+    z_order, groups = ['D', 'P'], [['P', 'D']]                   # :80-82
+  elif chapter == 'cavern':                                      # :85-89; default z = sorted
+    things['S'] = em.PlainDrape('S', masks['S'])
+    z_order, groups = ['P', 'S'], [['P', 'S']]
+  else:                                                          # :91-93
+    z_order, groups = ['P'], [['P']]
+  world = em.World(shape[0], shape[1], backdrop, things, z_order=z_order, groups=groups,
+                   program=ordeal_program)
+  world.plot.store.update(
+      has_sword=bool(story_plot.get('has_sword')),
+      last_position=story_plot.get('last_position'),
+      this_chapter=chapter, prior_chapter=story_plot.get('prior_chapter'),
+      next_chapter=None)                                         # dict stories: storytelling.py:455
+  return world
+
+
+def ordeal_program(world, ch, actions):
+  plot, store, ent, board = world.plot, world.plot.store, world.things[ch], world.board
+  if ch == 'P':                                                  # PlayerSprite.update :206-266
+    limit_r, limit_c = ent.rows - 1, ent.cols - 1                # self._limits :204
+    this, prior = store['this_chapter'], store['prior_chapter']
+
+    def leave(to):
+      store['next_chapter'] = to
+      plot.terminate_episode()
+    if actions == 0:
+      if this == 'kansas' and ent.row <= 0:
+        leave('castle')
+      else:
+        em.walker_move(ent, board, plot, em.M_N)
+    elif actions == 1:
+      if this == 'castle' and ent.row >= limit_r:
+        leave('kansas')
+      else:
+        em.walker_move(ent, board, plot, em.M_S)
+    elif actions == 2:
+      if this == 'cavern' and ent.col <= 0:
+        leave('kansas')
+      else:
+        em.walker_move(ent, board, plot, em.M_W)
+    elif actions == 3:
+      if this == 'kansas' and ent.col >= limit_c:
+        leave('cavern')
+      else:
+        em.walker_move(ent, board, plot, em.M_E)
+    elif actions == 4:
+      leave(None)
+    elif plot.frame == 0:                                        # line up with the last game
+      last = store['last_position']
+      if (prior, this) == ('kansas', 'castle'):
+        em.walker_teleport(ent, limit_r, last[1])
+      elif (prior, this) == ('castle', 'kansas'):
+        em.walker_teleport(ent, 0, last[1])
+      elif (prior, this) == ('kansas', 'cavern'):
+        em.walker_teleport(ent, last[0], 0)
+      elif (prior, this) == ('cavern', 'kansas'):
+        em.walker_teleport(ent, last[0], limit_c)
+    store['last_position'] = ent.position                        # :266
+  elif ch == 'D':                                                # DragonduckSprite.update :142-185
+    if plot.frame == 0:
+      return
+    player = world.things['P']
+    rel = (ent.row > player.row, ent.col < player.col, ent.row < player.row,
+           ent.col > player.col)
+    motion = {(True, False, False, False): em.M_N, (True, True, False, False): em.M_NE,
+              (False, True, False, False): em.M_E, (False, True, True, False): em.M_SE,
+              (False, False, True, False): em.M_S, (False, False, True, True): em.M_SW,
+              (False, False, False, True): em.M_W, (True, False, False, True): em.M_NW}.get(rel)
+    if motion is not None:
+      em.walker_move(ent, board, plot, motion)
+    # layers['P'] of the board as last rendered (occluded layers, rendering.py:177)
+    if board[ent.row, ent.col] == ord('P'):
+      store['next_chapter'] = None
+      plot.terminate_episode()
+      if store.get('has_sword'):
+        plot.add_reward(1.0)
+        plot.change_z_order('D', 'P')
+      else:
+        plot.add_reward(-1.0)
+        plot.change_z_order('P', 'D')
+  else:                                                          # SwordDrape.update :120-124
+    player = world.things['P']
+    if ent.curtain[player.row, player.col]:
+      store['has_sword'] = True
+      plot.add_reward(1.0)
+    if store.get('has_sword'):
+      ent.curtain[:] = False

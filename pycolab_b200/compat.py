@@ -17,7 +17,7 @@ import os
 import sys
 import types
 
-_ALIASED = ('things', 'plot', 'engine', 'ascii_art', 'rendering', 'cropping',
+_ALIASED = ('things', 'plot', 'engine', 'ascii_art', 'rendering', 'cropping', 'storytelling',
             'prefab_parts', 'prefab_parts.sprites', 'prefab_parts.drapes',
             'protocols', 'protocols.scrolling', 'protocols.logging')
 

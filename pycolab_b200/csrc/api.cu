@@ -202,6 +202,19 @@ int validate(const pcl_spec& s) {
       if (s.rows >= 32768 || s.cols >= 32768 || s.rows * s.pitch > 8192) return PCL_ERR_UNSUPPORTED;
       return PCL_OK;
     }
+    case PCL_PROG_ORDEAL: {
+      const int chapter = s.program_arg[0];
+      const int want_s = chapter == PCL_ORDEAL_CASTLE ? 2 : 1, want_d = chapter == PCL_ORDEAL_CAVERN ? 1 : 0;
+      if (chapter != PCL_ORDEAL_CASTLE && chapter != PCL_ORDEAL_CAVERN && chapter != PCL_ORDEAL_KANSAS)
+        return PCL_ERR_INVALID;
+      if (s.n_sprites != want_s || s.n_drapes != want_d) return PCL_ERR_UNSUPPORTED;
+      if (s.n_groups != 1 || s.group_len[0] != want_s + want_d) return PCL_ERR_UNSUPPORTED;
+      if (s.group_chars[0] != s.sprite_char[0]) return PCL_ERR_UNSUPPORTED;     // the player moves first
+      for (int i = 0; i < want_s; ++i) if (s.sprite_egocentric[i]) return PCL_ERR_UNSUPPORTED;
+      if (s.rows >= 32768 || s.cols >= 32768 || s.rows * s.pitch > 8192) return PCL_ERR_UNSUPPORTED;
+      if (want_d && s.bits_words < (s.cols + 31) / 32 + 1) return PCL_ERR_INVALID;
+      return PCL_OK;
+    }
     case PCL_PROG_FIXTURE: {
       // Any MazeWalker / Scrolly / plain-drape mix; entities and z-order must
       // be consistent permutations of each other.
@@ -270,6 +283,7 @@ int launch(pcl_handle* h, const StepParams& p, cudaStream_t stream) {
     case PCL_PROG_BETTER_SCROLLY: e = pcl::launch_better_scrolly(p, stream); break;
     case PCL_PROG_CLASSICS: e = pcl::launch_classics(p, stream); break;
     case PCL_PROG_APERTURE: e = pcl::launch_aperture(p, stream); break;
+    case PCL_PROG_ORDEAL: e = pcl::launch_ordeal(p, stream); break;
     default: return PCL_ERR_UNSUPPORTED;
   }
   if (e != cudaSuccess) return cuda_failed(h, e, "step kernel launch");
@@ -369,6 +383,12 @@ int pcl_bind_state(pcl_handle* h, const pcl_state* st) {
     for (int d = 0; d < 2; ++d)
       if (!st->d_bits[d] || !st->d_bits_init[d] || st->bits_bstride[d] == 0) return PCL_ERR_INVALID;
     if (!st->d_rng) return PCL_ERR_INVALID;
+  }
+  if (h->spec.program == PCL_PROG_ORDEAL) {
+    if (h->spec.n_drapes && (!st->d_bits[0] || !st->d_bits_init[0] || st->bits_bstride[0] == 0))
+      return PCL_ERR_INVALID;
+    if (h->spec.n_sprites + h->spec.n_drapes == 2 && (!st->d_z_order || !st->d_z_order_init))
+      return PCL_ERR_INVALID;                   // the kernel reads the z-order of two entities
   }
   if (h->spec.program == PCL_PROG_BETTER_SCROLLY) {
     if (!st->d_bits[0] || !st->d_bits_init[0] || st->bits_bstride[0] == 0) return PCL_ERR_INVALID;
@@ -579,7 +599,7 @@ int pcl_export_curtain(pcl_handle* h, int drape_index, uint8_t* d_out, void* str
     if (drape_index == 1) p.stale_slot = 0;
     else p.level = h->st.d_level;            // the wall pattern is read-only: per level
   } else if (h->spec.program == PCL_PROG_MARAUDERS ||
-             h->spec.program == PCL_PROG_BETTER_SCROLLY ||
+             h->spec.program == PCL_PROG_BETTER_SCROLLY || h->spec.program == PCL_PROG_ORDEAL ||
              (h->spec.program == PCL_PROG_FIXTURE && !h->spec.drape_kind[drape_index])) {
     p.scrolly = 0;
     p.bits = h->st.d_bits[drape_index];
@@ -620,7 +640,7 @@ int pcl_layers(pcl_handle* h, const uint8_t* chars, int32_t n_chars, uint8_t* d_
       p.stale_slot[d] = coins;
       p.per_level[d] = !coins && h->st.d_level != nullptr;   // read-only patterns: per level
     } else if (sp.program == PCL_PROG_MARAUDERS || sp.program == PCL_PROG_BETTER_SCROLLY ||
-               sp.program == PCL_PROG_FIXTURE) {
+               sp.program == PCL_PROG_FIXTURE || sp.program == PCL_PROG_ORDEAL) {
       p.bits[d] = h->st.d_bits[d]; p.bits_bstride[d] = h->st.bits_bstride[d];
       p.row_words[d] = sp.bits_words;
     } else {

@@ -209,6 +209,8 @@ class Engine(object):
     sprites = b.sprites[0].cpu().numpy()
     drapes = b.drapes[0].cpu().numpy()
     self._the_plot._frame = int(b.plot[0, _lib.P_FRAME])
+    if b.game.sync_plot is not None:       # dict entries the game keeps on the device
+      b.game.sync_plot(self, b.plot[0].cpu().numpy())
     if b.game.backdrop_role == 'river':    # RiverBackdrop.update as a rotation count
       if self._backdrop_template is None:
         self._backdrop_template = self._backdrop.curtain.copy()

@@ -50,6 +50,9 @@ LOWERED_CLASSES = {
     ('fluvial_natation', 'PlayerSprite'): 'classics.fluvial',
     ('aperture', 'PlayerSprite'): 'aperture.player',
     ('aperture', 'ApertureDrape'): 'aperture.drape',
+    ('ordeal', 'PlayerSprite'): 'ordeal.player',
+    ('ordeal', 'DragonduckSprite'): 'ordeal.dragonduck',
+    ('ordeal', 'SwordDrape'): 'ordeal.sword',
     # General entities: the reference's test fixtures and this package's twins.
     ('test_things', 'TestMazeWalker'): 'fixture.walker',
     ('test_things', 'TestScrolly'): 'fixture.scrolly',
@@ -203,6 +206,8 @@ class LoweredGame(object):
     self.sprite_group = []      # per sprite: index into scroll_groups
     self.drape_group = []       # per drape
     self.group_records = None   # i32 [MAX_SCROLL_GROUPS, 4] reset template (groups >= 1)
+    self.sync_plot = None       # callable(engine, plot words): mirror device plot state into
+                                # the Python Plot after a step (games that keep dict entries)
 
   def signature(self):
     """Everything that must agree between envs sharing one handle."""
@@ -479,6 +484,72 @@ def _lower_classics(engine, roles):
   return game
 
 
+_ORDEAL_CHAPTERS = {'castle': _lib.ORDEAL_CASTLE, 'cavern': _lib.ORDEAL_CAVERN,
+                    'kansas': _lib.ORDEAL_KANSAS}
+
+
+def _lower_ordeal(engine, roles):
+  """examples/ordeal.py:74-266: one chapter of the Story.  Which chapter this Engine
+  is comes from its entities (castle: P + D, cavern: P + S, kansas: P) and must agree
+  with `the_plot.this_chapter`, which Story set before its_showtime()
+  (storytelling.py:453-454).  The Plot entries the game code keeps in dict slots —
+  `has_sword`, `last_position` — and the chapter bookkeeping enter the device plot
+  record here and are mirrored back after every step (`sync_plot`)."""
+  th, plot = engine.things, engine.the_plot
+  by_role = sorted(roles.values())
+  chapter = {('ordeal.dragonduck', 'ordeal.player'): 'castle',
+             ('ordeal.player', 'ordeal.sword'): 'cavern',
+             ('ordeal.player',): 'kansas'}.get(tuple(by_role))
+  if chapter is None:
+    raise NotLoweredError('ordeal program: unknown chapter with entities {}'.format(roles))
+  if plot.this_chapter is not None and plot.this_chapter != chapter:
+    raise NotLoweredError('ordeal chapter {!r} is running under the Story key {!r}'.format(
+        chapter, plot.this_chapter))
+  if plot.prior_chapter is not None and plot.prior_chapter not in _ORDEAL_CHAPTERS:
+    raise NotLoweredError('ordeal chapter entered from an unknown chapter {!r}'.format(
+        plot.prior_chapter))
+  game = LoweredGame()
+  _common(engine, game, _lib.PROG_ORDEAL)
+  if len(game.groups) != 1:
+    raise NotLoweredError('ordeal chapters have one update group')
+  player = [c for c, r in roles.items() if r == 'ordeal.player'][0]
+  sprites = [th[player]] + [th[c] for c, r in roles.items() if r == 'ordeal.dragonduck']
+  if game.groups[0][0] != player:
+    raise NotLoweredError('the ordeal player must update first')
+  if game.rows * game.pitch > 8192:
+    raise NotLoweredError('ordeal boards are staged whole in shared memory (<= 8 KiB)')
+  _set_sprites(game, sprites, [_sprite_record(s) for s in sprites])
+  game.program_arg[0] = _ORDEAL_CHAPTERS[chapter]
+  drapes = [c for c, r in roles.items() if r == 'ordeal.sword']
+  game.drape_chars = ''.join(drapes)
+  game.margins = [(-1, -1)] * len(drapes)
+  game.drapes = np.zeros((len(drapes), _lib.DRAPE_WORDS), dtype=np.int32)
+  for d, ch in enumerate(drapes):
+    game.drapes[d, _lib.D_LAST_FRAME] = _lib.NEVER
+    game.bits[d] = pack_rows(th[ch].curtain, game.bits_words)
+  last = plot.get('last_position')
+  game.plot = np.array(_plot_record(
+      aux0=1 if plot.get('has_sword') else 0,
+      aux1=-1 if last is None else (int(last[0]) << 16) | int(last[1]),
+      aux2=_lib.ORDEAL_NEXT_UNSET,
+      aux3=_ORDEAL_CHAPTERS.get(plot.prior_chapter, 0)), dtype=np.int32)
+  game.dynamic_z = len(sprites) + len(drapes) == 2      # the kernel reads (castle: rewrites) it
+  game.reward_type = float                              # ordeal.py pays 1.0 / -1.0
+  names = {v: k for k, v in _ORDEAL_CHAPTERS.items()}
+
+  def sync_plot(eng, words):
+    p = eng.the_plot
+    if words[_lib.P_AUX0]:
+      p['has_sword'] = True
+    if words[_lib.P_AUX1] >= 0:
+      p['last_position'] = things.Sprite.Position(int(words[_lib.P_AUX1]) >> 16,
+                                                  int(words[_lib.P_AUX1]) & 0xffff)
+    if words[_lib.P_AUX2] != _lib.ORDEAL_NEXT_UNSET:
+      p.next_chapter = names.get(int(words[_lib.P_AUX2]))   # 0 -> None: the story ends
+  game.sync_plot = sync_plot
+  return game
+
+
 def _lower_aperture(engine, roles):
   """examples/aperture.py:188-196: sprite 'A' + the aperture drape.  The drape's
   state is its `_apertures` list (at most two cells) in the record's AUX words."""
@@ -578,7 +649,7 @@ def lower(engine):
   lowerers = {'scrolly': _lower_scrolly_maze, 'warehouse': _lower_warehouse,
               'marauders': _lower_marauders, 'fixture': _lower_fixture,
               'classics': _lower_classics, 'better': _lower_better_scrolly,
-              'aperture': _lower_aperture}
+              'aperture': _lower_aperture, 'ordeal': _lower_ordeal}
   if family not in lowerers:
     raise NotLoweredError(family)
   game = lowerers[family](engine, roles)

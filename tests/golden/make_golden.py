@@ -233,6 +233,25 @@ def fixture_groups(name, seed, margins, T=400):
   print('  %s: %d steps' % (name, len(used)))
 
 
+def ordeals():
+  """examples/ordeal.py through the reference's own Story (cropped observations,
+  summed rewards across chapter crossings, discounts, chapter names, has_sword)."""
+  import ordeal_cases
+  mods = refdriver.ref_storytelling()
+  from pycolab.examples import ordeal as ref_ordeal
+  for name, actions in sorted(ordeal_cases.scripts().items()):
+    chapters, swords = [], []
+
+    def on_frame(env, out):
+      chapters.append(str(env.the_plot.this_chapter))
+      swords.append(1 if env.the_plot.get('has_sword') else 0)
+    traj = tj.run_trajectory(ref_ordeal.make_game, actions, on_frame=on_frame)
+    save(name, actions=np.array(actions, dtype=np.int32),
+         chapters=np.array(chapters), has_sword=np.array(swords, dtype=np.uint8), **traj)
+    print('  %s: %d steps, chapters %s, reward sum %s' % (
+        name, len(traj['boards']) - 1, sorted(set(chapters)), traj['reward'].sum()))
+
+
 def groups():
   for seed, margins in ((0, (2, 3)), (1, None), (2, (1, 2))):
     fixture_groups('fixture_groups_%d' % seed, seed, margins)
@@ -438,6 +457,8 @@ def main():
     return apertures()
   if sys.argv[1:] == ['groups']:
     return groups()
+  if sys.argv[1:] == ['ordeal']:
+    return ordeals()
   # BASELINE.json configs[0]: stock scrolly_maze, 1000 random-action steps.
   for level, T in ((0, 1000), (1, 400), (2, 400)):
     maze, board, beneath = refdriver.ref_stock_scrolly_art(level)
@@ -487,6 +508,7 @@ def main():
   fluvials()
   apertures()
   groups()
+  ordeals()
 
 
 # Same-shape (4x12) chapters for a list-style story without croppers.

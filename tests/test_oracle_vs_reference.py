@@ -301,3 +301,26 @@ def test_scrolling_cropper(pad, margins):
       break
     a = int(rs.randint(0, 5))
     r_out, o_out = ref.play(a), ora.play(a)
+
+
+@pytest.mark.parametrize('seed', range(6))
+def test_ordeal_story_random_walks(seed):
+  """examples/ordeal.py live: the reference's Story vs the chained oracle worlds,
+  every step (current chapter's un-cropped board, summed reward, discount,
+  chapter name, game over), random walks across all three sub-games."""
+  refdriver.ref_storytelling()
+  from pycolab.examples import ordeal as ref_ordeal
+  from test_ordeal import OracleOrdeal
+  rs = np.random.RandomState(500 + seed)
+  story, mine = ref_ordeal.make_game(), OracleOrdeal()
+  story.its_showtime()
+  mine.its_showtime()
+  for t, a in enumerate(rs.choice([0, 1, 2, 3], size=700, p=[.3, .2, .2, .3]).tolist()):
+    if story.game_over:
+      break
+    obs, reward, discount = story.play(a)
+    view, my_reward, my_discount = mine.play(a)
+    assert story.the_plot.this_chapter == mine.chapter, t
+    np.testing.assert_array_equal(obs.board, view, err_msg='t=%d' % t)
+    assert reward == my_reward and discount == my_discount, t
+    assert story.game_over == mine.game_over, t
