@@ -202,7 +202,10 @@ typedef struct pcl_state {
 /* Per-step outputs = the (observation, reward, discount) triple of
  * Engine.play() (engine.py:639) plus Engine.game_over (engine.py:657). */
 typedef struct pcl_outputs {
-  uint8_t* d_board;       /* u8 [B, rows, pitch]; Observation.board */
+  uint8_t* d_board;       /* u8 [B, rows, pitch]; Observation.board.  PCL_PROG_FIXTURE reads the
+                             board of the LAST render back from here at the next step (its
+                             entities may test any character, engine.py:725-735): pass the same
+                             d_board to consecutive steps of a handle running that program. */
   int32_t* d_reward;      /* i32 [B]; summed reward (plot.py:201-214), 0 if none */
   uint8_t* d_has_reward;  /* u8 [B]; 0 = reference returned reward None */
   float*   d_discount;    /* f32 [B]; 1.0 running / 0.0 terminated unless a directive said otherwise

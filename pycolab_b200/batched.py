@@ -375,13 +375,20 @@ class BatchedEngine(object):
   def crop(self, crop_spec, state=None, out=None):
     """ScrollingCropper / FixedCropper .crop over the last boards: u8 [B, rows,
     cols].  `state` (from new_crop_state) keeps this cropper's window corners;
-    None uses the single built-in slot in the plot record."""
+    None uses the single built-in slot in the plot record.  Without `out` the
+    result lives in an engine-owned buffer of THIS cropper (one per `state`), valid
+    until its next crop — copy to keep, as upstream (cropping.py:148-149)."""
     torch = _torch()
     shape = (self.batch, crop_spec.rows, crop_spec.cols)
     if out is None:
-      if self._crop_out is None or tuple(self._crop_out.shape) != shape:
-        self._crop_out = torch.empty(shape, dtype=torch.uint8, device=self.device)
-      out = self._crop_out
+      # one engine-owned buffer per cropper (keyed by its corner state): two croppers
+      # with the same window shape must not overwrite each other's view
+      key = (shape, None if state is None else state.data_ptr())
+      if self._crop_out is None:
+        self._crop_out = {}
+      if key not in self._crop_out:
+        self._crop_out[key] = torch.empty(shape, dtype=torch.uint8, device=self.device)
+      out = self._crop_out[key]
     state_ptr = None if state is None else state.data_ptr()
     if any(code < 0 for code in crop_spec.track):
       # A tracked drape's position is the median of its curtain cells: hand the

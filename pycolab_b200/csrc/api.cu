@@ -668,8 +668,10 @@ int pcl_crop_tracking(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d
   Range nvtx_range("pcl_crop (ScrollingCropper.crop)");
   if (!h || !crop || !d_board || !d_crop) return PCL_ERR_INVALID;
   if (!h->bound) return PCL_ERR_UNBOUND;
-  if (crop->rows <= 0 || crop->cols <= 0 || crop->sprite_index >= h->spec.n_sprites)
-    return PCL_ERR_INVALID;
+  if (crop->rows <= 0 || crop->cols <= 0) return PCL_ERR_INVALID;
+  // sprite_index names the tracked sprite only when no priority list is given (a
+  // cropper may track a drape in a game without sprites).
+  if (crop->track[0] == 0 && crop->sprite_index >= h->spec.n_sprites) return PCL_ERR_INVALID;
   if (crop->sprite_index >= 0 &&
       (2 * crop->margin_rows >= crop->rows || 2 * crop->margin_cols >= crop->cols))
     return PCL_ERR_INVALID;                                  // cropping.py:374-380

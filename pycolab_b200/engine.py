@@ -232,6 +232,15 @@ class Engine(object):
       if isinstance(ent, prefab_drapes.Scrolly):
         ent._northwest_corner = things.Sprite.Position(int(rec[_lib.D_CORNER_R]),
                                                        int(rec[_lib.D_CORNER_C]))
+        # registers behind pattern_position_prescroll / _postscroll (drapes.py:378-441)
+        ent._prescroll_northwest_corner = things.Sprite.Position(int(rec[_lib.D_PRE_R]),
+                                                                 int(rec[_lib.D_PRE_C]))
+        last = int(rec[_lib.D_LAST_FRAME])
+        ent._last_maybe_move_frame = -float('inf') if last == _lib.NEVER else last
+        if b.game.pattern_mutable.get(i):      # e.g. coins picked up on the device
+          from pycolab_b200 import lowering
+          packed = b.patterns[i][0].cpu().numpy().view(np.uint32)
+          np.copyto(ent.whole_pattern, lowering.unpack_rows(packed, ent.whole_pattern.shape[1]))
       np.copyto(ent.curtain, b.curtain(ch)[0].cpu().numpy())
       if b.game.program == _lib.PROG_APERTURE:       # ApertureDrape._apertures
         cells = [int(rec[_lib.D_AUX0]), int(rec[_lib.D_AUX1])]
