@@ -73,6 +73,9 @@ typedef enum pcl_program {
                                 chain_walk}.py, examples/fluvial_natation.py */
   PCL_PROG_APERTURE = 7,     /* examples/aperture.py:118-196; the drape record's AUX0 / AUX1 hold
                                 the two aperture cells (row << 16 | col, -1 = none) */
+  PCL_PROG_HELLO = 9,        /* examples/hello_world.py:58-118: plain Sprites (aux0 = direction set)
+                                + one rolling Drape (record AUX0 / AUX1 = row / column shift of the
+                                reset curtain); program_arg[0..n) = the z-order chars */
   PCL_PROG_ORDEAL = 8        /* examples/ordeal.py:74-266: program_arg[0] = PCL_ORDEAL_* chapter;
                                 plot words AUX0 has_sword, AUX1 last_position (row << 16 | col,
                                 -1 unset), AUX2 next_chapter chosen on the device, AUX3 prior chapter */

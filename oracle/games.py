@@ -680,3 +680,55 @@ def ordeal_program(world, ch, actions):
       plot.add_reward(1.0)
     if store.get('has_sword'):
       ent.curtain[:] = False
+
+
+# ==========================================================================
+# hello_world: plain Sprites that wrap around the board and a
+# Drape that rolls its curtain — no MazeWalker, no board look-ups at all.
+# ==========================================================================
+
+class PlainSprite(object):
+  """A `things.Sprite` (things.py:339-391): a position and a visibility flag."""
+  is_sprite = True
+
+  def __init__(self, char, shape, position):
+    self.char = char
+    self.rows, self.cols = shape
+    self.row, self.col = position
+    self.visible = True
+
+  @property
+  def position(self):
+    return (self.row, self.col)
+
+
+HELLO_DX = ([-1, 1, -1, 1], [-1, 1, -1, 1], [1, -1, 1, -1], [1, -1, 1, -1])   # hello_world.py:96
+HELLO_DY = ([-1, 1, 1, -1], [1, -1, -1, 1], [1, -1, -1, 1], [-1, 1, 1, -1])   # :97
+
+
+def make_hello(art):
+  """examples/hello_world.py:58-68."""
+  backdrop, masks = split_art(art, list('1234@'), ' ')
+  shape = backdrop.shape
+  things = {ch: PlainSprite(ch, shape, mask_position(masks[ch])) for ch in '1234'}
+  things['@'] = em.PlainDrape('@', masks['@'])
+  return em.World(shape[0], shape[1], backdrop, things, z_order=list('12@34'),
+                  groups=[list('1234@')], program=hello_program)
+
+
+def hello_program(world, ch, actions):
+  ent = world.things[ch]
+  if ch == '@':                                   # RollingDrape.update :77-87
+    if actions is None:
+      return
+    if actions == 4:
+      world.plot.terminate_episode()
+    if actions < 4:
+      ent.curtain[:] = np.roll(ent.curtain, [-1, 1, -1, 1][actions], [0, 0, 1, 1][actions])
+      world.plot.add_reward(1)
+  else:                                           # SlidingSprite.update :113-118
+    if actions is None or actions > 3:
+      return
+    k = int(ch) - 1                               # direction_set :62-65
+    ent.col = (ent.col + HELLO_DX[k][actions]) % ent.cols
+    ent.row = (ent.row + HELLO_DY[k][actions]) % ent.rows

@@ -99,6 +99,7 @@ class BatchedEngine(object):
     self.backdrop = tiled([g.backdrop for g in games], np.uint8)
     st.d_backdrop, st.backdrop_bstride = self.backdrop.data_ptr(), bstride(self.backdrop)
     self.patterns, self.bits = {}, {}
+    self._keep_bits_init = {}
     for d in sorted(g0.patterns):
       arrays = [g.patterns[d].view(np.int32) for g in games]
       if g0.pattern_mutable[d]:
@@ -117,6 +118,7 @@ class BatchedEngine(object):
       live = per_env(arrays, np.int32)
       self.bits[d] = live
       self._keep.append(init)
+      self._keep_bits_init[d] = init
       st.d_bits[d], st.bits_bstride[d] = live.data_ptr(), live[0].numel()
       st.d_bits_init[d], st.bits_init_bstride[d] = init.data_ptr(), bstride(init)
     self.sprites = per_env([g.sprites for g in games], np.int32)
@@ -330,6 +332,23 @@ class BatchedEngine(object):
       on = rec[:, :, _lib.S_AUX0] != 0
       b, s = torch.nonzero(on, as_tuple=True)
       out[b, rec[b, s, _lib.S_ROW].long(), rec[b, s, _lib.S_COL].long()] = 1
+    elif self.game.program == _lib.PROG_HELLO:
+      # RollingDrape: the reset curtain shifted by the record's (AUX0, AUX1) counters.
+      from pycolab_b200 import lowering
+      if getattr(self, '_roll_base', None) is None:
+        init = self._keep_bits_init[d].cpu().numpy().view(np.uint32)
+        base = np.stack([lowering.unpack_rows(lvl, self.cols) for lvl in init])
+        self._roll_base = torch.from_numpy(base.astype(np.uint8)).to(self.device)
+      lvl = (self.level.long() if self.level is not None
+             else torch.zeros(self.batch, dtype=torch.long, device=self.device))
+      if self._roll_base.shape[0] == self.batch and self.level is None and self.batch > 1:
+        lvl = torch.arange(self.batch, device=self.device)
+      rr = (torch.arange(self.rows, device=self.device)[None, :] -
+            self.drapes[:, d, _lib.D_AUX0].long()[:, None]) % self.rows
+      cc = (torch.arange(self.cols, device=self.device)[None, :] -
+            self.drapes[:, d, _lib.D_AUX1].long()[:, None]) % self.cols
+      out.zero_()
+      out[:, :, :self.cols] = self._roll_base[lvl[:, None, None], rr[:, :, None], cc[:, None, :]]
     elif self.game.program == _lib.PROG_APERTURE:
       # ApertureDrape curtain = the (at most two) cells of its `_apertures` list.
       out.zero_()

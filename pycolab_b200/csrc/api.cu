@@ -202,6 +202,14 @@ int validate(const pcl_spec& s) {
       if (s.rows >= 32768 || s.cols >= 32768 || s.rows * s.pitch > 8192) return PCL_ERR_UNSUPPORTED;
       return PCL_OK;
     }
+    case PCL_PROG_HELLO: {
+      if (s.n_sprites < 1 || s.n_sprites > 4 || s.n_drapes != 1) return PCL_ERR_UNSUPPORTED;
+      if (s.n_groups != 1 || s.group_len[0] != s.n_sprites + 1) return PCL_ERR_UNSUPPORTED;
+      if (s.bits_words < (s.cols + 31) / 32 + 1) return PCL_ERR_INVALID;
+      for (int k = 0; k < s.n_sprites + 1; ++k)      // program_arg = the z-order
+        if (s.program_arg[k] != s.z_order[k]) return PCL_ERR_INVALID;
+      return PCL_OK;
+    }
     case PCL_PROG_ORDEAL: {
       const int chapter = s.program_arg[0];
       const int want_s = chapter == PCL_ORDEAL_CASTLE ? 2 : 1, want_d = chapter == PCL_ORDEAL_CAVERN ? 1 : 0;
@@ -284,6 +292,7 @@ int launch(pcl_handle* h, const StepParams& p, cudaStream_t stream) {
     case PCL_PROG_CLASSICS: e = pcl::launch_classics(p, stream); break;
     case PCL_PROG_APERTURE: e = pcl::launch_aperture(p, stream); break;
     case PCL_PROG_ORDEAL: e = pcl::launch_ordeal(p, stream); break;
+    case PCL_PROG_HELLO: e = pcl::launch_hello(p, stream); break;
     default: return PCL_ERR_UNSUPPORTED;
   }
   if (e != cudaSuccess) return cuda_failed(h, e, "step kernel launch");
@@ -384,6 +393,7 @@ int pcl_bind_state(pcl_handle* h, const pcl_state* st) {
       if (!st->d_bits[d] || !st->d_bits_init[d] || st->bits_bstride[d] == 0) return PCL_ERR_INVALID;
     if (!st->d_rng) return PCL_ERR_INVALID;
   }
+  if (h->spec.program == PCL_PROG_HELLO && !st->d_bits_init[0]) return PCL_ERR_INVALID;
   if (h->spec.program == PCL_PROG_ORDEAL) {
     if (h->spec.n_drapes && (!st->d_bits[0] || !st->d_bits_init[0] || st->bits_bstride[0] == 0))
       return PCL_ERR_INVALID;

@@ -50,6 +50,8 @@ LOWERED_CLASSES = {
     ('fluvial_natation', 'PlayerSprite'): 'classics.fluvial',
     ('aperture', 'PlayerSprite'): 'aperture.player',
     ('aperture', 'ApertureDrape'): 'aperture.drape',
+    ('hello_world', 'SlidingSprite'): 'hello.slider',
+    ('hello_world', 'RollingDrape'): 'hello.roller',
     ('ordeal', 'PlayerSprite'): 'ordeal.player',
     ('ordeal', 'DragonduckSprite'): 'ordeal.dragonduck',
     ('ordeal', 'SwordDrape'): 'ordeal.sword',
@@ -484,6 +486,48 @@ def _lower_classics(engine, roles):
   return game
 
 
+def _lower_hello(engine, roles):
+  """examples/hello_world.py:58-118: up to four SlidingSprites (plain Sprites, each
+  with one of four diagonal direction sets) and one RollingDrape, one update group."""
+  th = engine.things
+  sliders = [c for c in ''.join(_update_order(engine)) if roles[c] == 'hello.slider']
+  rollers = [c for c, r in roles.items() if r == 'hello.roller']
+  if not 1 <= len(sliders) <= 4 or len(rollers) != 1:
+    raise NotLoweredError('hello_world program needs 1-4 SlidingSprites and one RollingDrape')
+  game = LoweredGame()
+  _common(engine, game, _lib.PROG_HELLO)
+  if len(game.groups) != 1:
+    raise NotLoweredError('hello_world entities share one update group')
+  records = []
+  for ch in sliders:
+    sp = th[ch]
+    sets = list(zip(type(sp)._DX, type(sp)._DY))
+    try:
+      k = sets.index((sp._dx, sp._dy))
+    except ValueError:
+      raise NotLoweredError('SlidingSprite {!r} uses an unknown direction set'.format(ch))
+    records.append(_sprite_record(sp, aux0=k))
+  game.sprite_chars = ''.join(sliders)
+  game.impassable = [[0, 0, 0, 0]] * len(sliders)
+  game.confined = [False] * len(sliders)
+  game.egocentric = [False] * len(sliders)
+  game.sprites = np.array(records, dtype=np.int32).reshape(len(sliders), _lib.SPRITE_WORDS)
+  game.drape_chars = rollers[0]
+  game.margins = [(-1, -1)]
+  rec = [0] * _lib.DRAPE_WORDS
+  rec[_lib.D_LAST_FRAME] = _lib.NEVER
+  game.drapes = np.array([rec], dtype=np.int32)
+  game.bits[0] = pack_rows(th[rollers[0]].curtain, game.bits_words)   # the un-rolled curtain
+  game.plot = np.array(_plot_record(), dtype=np.int32)
+  for k, ch in enumerate(game.z_order):          # the kernel paints in this order
+    game.program_arg[k] = ord(ch)
+  return game
+
+
+def _update_order(engine):
+  return [e.character for _, ents in sorted(engine._update_groups.items()) for e in ents]
+
+
 _ORDEAL_CHAPTERS = {'castle': _lib.ORDEAL_CASTLE, 'cavern': _lib.ORDEAL_CAVERN,
                     'kansas': _lib.ORDEAL_KANSAS}
 
@@ -649,7 +693,8 @@ def lower(engine):
   lowerers = {'scrolly': _lower_scrolly_maze, 'warehouse': _lower_warehouse,
               'marauders': _lower_marauders, 'fixture': _lower_fixture,
               'classics': _lower_classics, 'better': _lower_better_scrolly,
-              'aperture': _lower_aperture, 'ordeal': _lower_ordeal}
+              'aperture': _lower_aperture, 'ordeal': _lower_ordeal,
+              'hello': _lower_hello}
   if family not in lowerers:
     raise NotLoweredError(family)
   game = lowerers[family](engine, roles)

@@ -252,6 +252,25 @@ def ordeals():
         name, len(traj['boards']) - 1, sorted(set(chapters)), traj['reward'].sum()))
 
 
+def hellos():
+  """examples/hello_world.py: stock art, random actions 0-5 (4 quits, 5 is a no-op)."""
+  refdriver._import()
+  from pycolab.examples import hello_world as ref_hello
+  for seed in range(2):
+    rs = np.random.RandomState(600 + seed)
+    actions = rs.choice([0, 1, 2, 3, 4, 5], size=400, p=[.22, .22, .22, .22, .02, .10]).tolist()
+    sprites, curtains = [], []
+    rec = sprite_recorder('1234', sprites)
+
+    def on_frame(env, out):
+      rec(env, out)
+      curtains.append(env.things['@'].curtain.copy())
+    traj = tj.run_trajectory(ref_hello.make_game, actions, on_frame=on_frame)
+    save('hello_stock_s%d' % seed, art=tj.art_to_u8(ref_hello.HELLO_ART),
+         actions=np.array(actions, dtype=np.int32), sprites=np.array(sprites, dtype=np.int32),
+         curtains=np.stack(curtains).astype(np.uint8), **traj)
+
+
 def groups():
   for seed, margins in ((0, (2, 3)), (1, None), (2, (1, 2))):
     fixture_groups('fixture_groups_%d' % seed, seed, margins)
@@ -459,6 +478,8 @@ def main():
     return groups()
   if sys.argv[1:] == ['ordeal']:
     return ordeals()
+  if sys.argv[1:] == ['hello']:
+    return hellos()
   # BASELINE.json configs[0]: stock scrolly_maze, 1000 random-action steps.
   for level, T in ((0, 1000), (1, 400), (2, 400)):
     maze, board, beneath = refdriver.ref_stock_scrolly_art(level)
@@ -509,6 +530,7 @@ def main():
   apertures()
   groups()
   ordeals()
+  hellos()
 
 
 # Same-shape (4x12) chapters for a list-style story without croppers.
