@@ -603,9 +603,9 @@ def other_config(name, torch, dist, dev, rank, world, barrier, peak, K):
   base = rank * R * B
   engines = [batched.BatchedEngine(games, batch=B, device=local, env_offset=base + r * B,
                                    rng_seed=7) for r in range(R)]
+  rng0 = [None if e.rng is None else e.rng.clone() for e in engines]   # before any draw
   for e in engines:
     e.its_showtime()
-  rng0 = [None if e.rng is None else e.rng.clone() for e in engines]
   rs = np.random.RandomState(4321 + rank)
   acts_np = rs.randint(0, n_act, size=(W + K, B)).astype(np.int32)
   acts = torch.from_numpy(acts_np).to(dev)

@@ -45,7 +45,8 @@ def device_game(snap):
         # A plain things.Sprite whose update does nothing (test_things.TestSprite):
         # a walker that is always told to stay.
         w = snap['sprites'][ch]
-        sprite = eng.add_sprite(ch, tuple(w['position']), fixtures.FixtureMazeWalker)
+        sprite = eng.add_sprite(ch, tuple(w['position']), fixtures.FixtureMazeWalker,
+                                impassable='')
         sprite._visible = w['visible']
       elif ch in snap.get('scrollys', {}):
         s = snap['scrollys'][ch]
