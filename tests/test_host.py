@@ -402,7 +402,7 @@ def test_reference_marauders_example_loads_and_lowers(compat_examples):
 def test_reference_example_outside_the_lowered_set_is_refused(compat_examples):
   mod = compat_examples('shockwave')
   with pytest.raises(NotLoweredError):
-    lowering.lower(mod.make_game())
+    lowering.lower(mod.make_game(0))
 
 
 @needs_ref
