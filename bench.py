@@ -332,6 +332,9 @@ class Timed(object):
     self.step_fn, self.n_warm, self.n_steps = step_fn, n_warm, n_steps
     self.graphs = None
     self.path = 'host loop of pcl_step calls (CUDA graph capture unavailable)'
+    if os.environ.get('PCL_BENCH_NO_GRAPH') == '1':   # e.g. under a profiler
+      self.path = 'host loop of pcl_step calls (PCL_BENCH_NO_GRAPH=1)'
+      return
     try:
       torch.cuda.synchronize(dev)
       gw, gt = (torch.cuda.CUDAGraph() if n_warm > 0 else None), torch.cuda.CUDAGraph()
