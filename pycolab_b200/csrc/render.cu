@@ -230,6 +230,131 @@ render_kernel_warp(const RenderParams p, const int parts) {
   }
 }
 
+// ---- persistent, software-pipelined variant --------------------------------------
+// Persistent CTAs (one resident set, grid = SMs x CTAs/SM) walk envs with a static
+// stride; the (1 + D) byte planes of the NEXT env travel into the other half of a
+// shared-memory double buffer with cp.async while the current env is flattened, so
+// every SM keeps loads in flight from its first to its last env and no register is
+// held by a load in flight.  The z-order / sprite header is decoded per env as in
+// render_kernel.
+__device__ __forceinline__ void cp16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::
+               "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() {
+  asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory");
+}
+
+template <int MAXD, int MAXS>
+__global__ void __launch_bounds__(kRenderThreads)
+render_kernel_pipe(const RenderParams p) {
+  extern __shared__ __align__(16) uint8_t stage_mem[];
+  __shared__ RenderShared<MAXD, MAXS> sh;
+  const int n = p.S + p.D;
+  const int segs_per_row = p.pitch >> 4;
+  const int total = p.H * segs_per_row;                  // 16-byte segments per plane
+  const int64_t plane = (int64_t)p.H * p.pitch;
+  const int planes = 1 + p.D;
+  const int stage_segs = planes * total;
+  uint4* stages = reinterpret_cast<uint4*>(stage_mem);
+
+  auto prefetch = [&](int stage, int env) {
+    const uint8_t* backdrop = p.backdrop + (int64_t)env * p.backdrop_bstride;
+    const uint8_t* curtains = p.curtains + (int64_t)env * p.D * plane;
+    uint4* dst = stages + (int64_t)stage * stage_segs;
+    for (int i = threadIdx.x; i < stage_segs; i += kRenderThreads) {
+      const int pl = i / total, seg = i - pl * total;
+      const uint8_t* src = pl == 0 ? backdrop + ((int64_t)seg << 4)
+                                   : curtains + (pl - 1) * plane + ((int64_t)seg << 4);
+      cp16(dst + i, src);
+    }
+    cp_commit();
+  };
+
+  int env = blockIdx.x;
+  if (env >= p.B) return;
+  prefetch(0, env);
+  for (int it = 0; env < p.B; env += gridDim.x, ++it) {
+    const int next = env + gridDim.x;
+    if (next < p.B) prefetch((it + 1) & 1, next);
+    // Decode this env's z-order and sprite cells once per block.
+    if (threadIdx.x < n) {
+      const uint8_t ch = p.z_order[(int64_t)env * n + threadIdx.x];
+      const uint32_t rank4 = (threadIdx.x + 1) * 0x01010101u;
+#pragma unroll
+      for (int s2 = 0; s2 < MAXS; ++s2) if (s2 < p.S && p.sprite_char[s2] == ch) sh.rank_s[s2] = rank4;
+#pragma unroll
+      for (int d = 0; d < MAXD; ++d) if (d < p.D && p.drape_char[d] == ch) sh.rank_d[d] = rank4;
+    }
+    if (threadIdx.x < p.S) {
+      const int32_t* rec = p.sprites + ((int64_t)env * p.S + threadIdx.x) * PCL_SPRITE_WORDS;
+      const int row = rec[PCL_S_ROW], col = rec[PCL_S_COL];
+      const bool vis = rec[PCL_S_FLAGS] & 1;                     // engine.py:754
+      sh.seg[threadIdx.x] = vis ? row * segs_per_row + (col >> 4) : -1;
+      sh.word[threadIdx.x] = (col & 15) >> 2;
+      sh.cover[threadIdx.x] = 0xffu << ((col & 3) * 8);
+    }
+    if (next < p.B) cp_wait<1>(); else cp_wait<0>();
+    __syncthreads();
+    const uint4* st = stages + (int64_t)(it & 1) * stage_segs;
+    uint8_t* board = p.board + (int64_t)env * plane;
+    for (int seg = threadIdx.x; seg < total; seg += kRenderThreads) {
+      uint4 px = st[seg];
+      uint4 rk = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int d = 0; d < MAXD; ++d) {
+        if (d < p.D) {
+          const uint4 cur = st[(d + 1) * total + seg];
+          const uint32_t ch4 = p.drape_char[d] * 0x01010101u;
+          const uint32_t r4 = sh.rank_d[d];
+          overlay(px.x, rk.x, __vcmpne4(cur.x, 0), ch4, r4);   // rendering.py:160
+          overlay(px.y, rk.y, __vcmpne4(cur.y, 0), ch4, r4);
+          overlay(px.z, rk.z, __vcmpne4(cur.z, 0), ch4, r4);
+          overlay(px.w, rk.w, __vcmpne4(cur.w, 0), ch4, r4);
+        }
+      }
+#pragma unroll
+      for (int s2 = 0; s2 < MAXS; ++s2) {
+        if (s2 < p.S && sh.seg[s2] == seg) {                         // rendering.py:139
+          const uint32_t ch4 = p.sprite_char[s2] * 0x01010101u;
+          const uint32_t r4 = sh.rank_s[s2], cover = sh.cover[s2];
+          const int w = sh.word[s2];
+          if (w == 0) overlay(px.x, rk.x, cover, ch4, r4);
+          else if (w == 1) overlay(px.y, rk.y, cover, ch4, r4);
+          else if (w == 2) overlay(px.z, rk.z, cover, ch4, r4);
+          else overlay(px.w, rk.w, cover, ch4, r4);
+        }
+      }
+      *reinterpret_cast<uint4*>(board + ((int64_t)seg << 4)) = px;
+    }
+    __syncthreads();                       // the stage and the header are free again
+  }
+}
+
+template <int MAXD, int MAXS>
+cudaError_t launch_render_pipe(const RenderParams& p, cudaStream_t s, bool* launched) {
+  const size_t smem = 2 * (size_t)(1 + p.D) * p.H * p.pitch;
+  *launched = false;
+  if (smem > 96 * 1024) return cudaSuccess;              // big boards: the plain kernel
+  auto kern = render_kernel_pipe<MAXD, MAXS>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRenderThreads, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaSuccess;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = sms * per_sm;
+  if (grid > p.B) grid = p.B;
+  kern<<<grid, kRenderThreads, smem, s>>>(p);
+  *launched = true;
+  return cudaGetLastError();
+}
+
 // Drape.curtain as bytes (things.py:213-217) from the packed device state.
 __global__ void export_curtain_kernel(const ExportParams p) {
   const int env = blockIdx.x;
@@ -551,8 +676,19 @@ __global__ void __launch_bounds__(128) crop_handoff_kernel(const CropParams p,
 
 cudaError_t launch_render(const RenderParams& p, cudaStream_t s) {
   // Loop bounds are compile-time so the per-segment code stays small.
-  static const bool block_per_env = getenv("PCL_RENDER_BLOCK_PER_ENV") != nullptr;   // A/B switch
-  if (!block_per_env && p.S + p.D <= 32 && p.S <= 16) {
+  // A/B switch: 1 = one CTA per env, 2 = persistent warps, 3 = persistent pipelined CTAs
+  static const int variant = getenv("PCL_RENDER_VARIANT") ? atoi(getenv("PCL_RENDER_VARIANT")) : 3;
+  if (variant == 3) {
+    bool done = false;
+    cudaError_t e;
+    if (p.D <= 2 && p.S <= 4) e = launch_render_pipe<2, 4>(p, s, &done);
+    else if (p.D <= 2 && p.S <= 8) e = launch_render_pipe<2, 8>(p, s, &done);
+    else if (p.D <= 2) e = launch_render_pipe<2, 16>(p, s, &done);
+    else if (p.S <= 4) e = launch_render_pipe<8, 4>(p, s, &done);
+    else e = launch_render_pipe<8, 16>(p, s, &done);
+    if (e != cudaSuccess || done) return e;
+  }
+  if (variant == 2 && p.S + p.D <= 32 && p.S <= 16) {
     // Persistent warp-granular kernel: part = the largest power of two <= 8 that
     // leaves every part at least one 32-segment round.
     const int segs = p.H * (p.pitch >> 4);
