@@ -394,7 +394,7 @@ def ramp_clocks(torch, dev, timed, seconds=0.5):
 
 
 def e2e_pipelined(torch, dev, engines, actions_np, n_steps, barrier, crop_spec=None,
-                  crop_states=None):
+                  crop_states=None, warm_seconds=0.3):
   """End to end through `pcl_step_host_async`: every step copies its actions from
   pinned host memory, steps, and copies its outputs back to pinned host memory;
   step t's copies overlap step t + 1's kernel (another batch); the host collects
@@ -406,9 +406,24 @@ def e2e_pipelined(torch, dev, engines, actions_np, n_steps, barrier, crop_spec=N
                       crop_state=None if crop_states is None else crop_states[t % R])
   def collect(t):
     return engines[t % R].host_wait((t // R) % 2)
-  for t in range(2 * R):                    # warm the pinned buffers / copy streams
+  # Warm the pinned buffers / copy streams, then keep the pipeline busy for
+  # `warm_seconds`: after an idle stretch (the CPU oracle check runs just before)
+  # the SM clocks and the PCIe link take tens of milliseconds to leave their idle
+  # state, and a 30 ms timed window straight after it measured 3x low
+  # (profiles/r02a_e2e_probe.txt has the steady-state figures).
+  for t in range(2 * R):
     submit(t)
     collect(t)
+  until = time.perf_counter() + warm_seconds
+  t = 0
+  while time.perf_counter() < until:
+    submit(t)
+    if t >= 1:
+      collect(t - 1)
+    t += 1
+  if t:
+    collect(t - 1)
+  torch.cuda.synchronize(dev)
   barrier()
   t0 = time.perf_counter()
   for t in range(n_steps):
@@ -471,25 +486,41 @@ def render_microbench(engines, n=60):
     z = z[None].repeat(B, 1).contiguous()
     out = torch.zeros((B, H, pitch), dtype=torch.uint8, device=dev)
     sets.append((eng, backdrop, curtains, z, out))
-  stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+  cur_stream = lambda: C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+  stream = cur_stream()
 
   def launch(i):
     eng, backdrop, curtains, z, out = sets[i % len(sets)]
     _lib.check(lib.pcl_render(eng._h, backdrop.data_ptr(), eng.rows * eng.pitch,
                               curtains.data_ptr(), eng.sprites.data_ptr(), z.data_ptr(),
-                              out.data_ptr(), stream), 'pcl_render')
+                              out.data_ptr(), cur_stream()), 'pcl_render')   # the capture stream
   for i in range(2 * len(sets)):
     launch(i)
   torch.cuda.synchronize(dev)
+  # n launches as one CUDA graph (like the step kernel's timed region): the host
+  # cannot feed 15 us kernels one ctypes call at a time without gaps.
+  timed = Timed(torch, dev, launch, 0, n)
+  timed.run()
+  ms = timed.time_ms(lambda: torch.cuda.synchronize(dev)) / n
   a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  a.record()
-  for i in range(n):
-    launch(i)
-  b.record()
-  torch.cuda.synchronize(dev)
   for eng, _, _, _, out in sets:
     assert bool((out[:, :, :eng.cols] == eng.board).all()), 'pcl_render != step kernel board'
-  ms = float(a.elapsed_time(b)) / n
+  # What a plain device copy reaches at THIS launch size: torch copy_ of 2 planes per
+  # env to 2 planes (the renderer reads 3 and writes 1: the same 4 planes of DRAM
+  # traffic per launch), rotating buffers, same graph timing.  MEASURED_PEAKS'
+  # figure is a 4 GB copy; a 67 MB launch does not get there.
+  copy_ms = None
+  try:
+    srcs = [s_[2].view(-1) for s_ in sets]              # the curtains: 2 planes per env
+    dsts = [torch.empty_like(x) for x in srcs]          # 2 planes read + 2 written = 4 planes
+    def copy(i):
+      dsts[i % len(sets)].copy_(srcs[i % len(sets)])
+    tc = Timed(torch, dev, copy, 0, n)
+    tc.run()
+    copy_ms = tc.time_ms(lambda: torch.cuda.synchronize(dev)) / n
+    del dsts
+  except Exception:                 # noqa: BLE001 - a reference figure only
+    copy_ms = None
 
   # The same kernel over all R batches in ONE launch (R x 4096 envs): how much of
   # the 4096-env figure is launch ramp/tail rather than bandwidth.
@@ -527,6 +558,8 @@ def render_microbench(engines, n=60):
     lib.pcl_destroy(handle)
   except Exception as e:            # the headline numbers do not depend on this
     big = {'error': str(e)}
+  if big is not None:
+    big['copy_ms_same_bytes_4096'] = copy_ms
   return ms, big
 
 
@@ -812,7 +845,7 @@ def main():
   del flush
 
   # ---- end to end through the host-buffer C-ABI calls ---------------------
-  e2e_steps = max(2 * R, min(K, 100))
+  e2e_steps = max(2 * R, min(K, 300))
   e2e_s, _ = e2e_pipelined(torch, dev, engines, actions_np[W:], e2e_steps, barrier)
   e2e_s, e2e_per_rank = max_over_ranks(torch, dist, dev, world, e2e_s)
   e2e_value = world * B * e2e_steps / e2e_s

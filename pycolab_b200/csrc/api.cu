@@ -381,8 +381,9 @@ const char* pcl_last_error(pcl_handle* h) { return h ? h->last_error : ""; }
 
 int pcl_bind_state(pcl_handle* h, const pcl_state* st) {
   if (!h || !st) return PCL_ERR_INVALID;
-  if (!st->d_backdrop || !st->d_sprites || !st->d_sprites_init || !st->d_plot || !st->d_plot_init)
-    return PCL_ERR_INVALID;
+  if (!st->d_backdrop || !st->d_plot || !st->d_plot_init) return PCL_ERR_INVALID;
+  // A game may have no sprites at all (engine_test.py:578-640 renders one drape).
+  if (h->spec.n_sprites > 0 && (!st->d_sprites || !st->d_sprites_init)) return PCL_ERR_INVALID;
   if (h->spec.n_drapes > 0 && (!st->d_drapes || !st->d_drapes_init)) return PCL_ERR_INVALID;
   if (h->spec.program == PCL_PROG_SCROLLY_MAZE) {
     for (int d = 0; d < 2; ++d) if (!st->d_pattern[d]) return PCL_ERR_INVALID;

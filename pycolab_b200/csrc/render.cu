@@ -118,125 +118,7 @@ render_kernel(const RenderParams p) {
   }
 }
 
-// ---- persistent, warp-granular variant ----------------------------------------
-// One-env CTAs leave a 4096-env launch with 3.46 waves of 256-thread blocks (ramp +
-// a half-empty last wave).  Here the grid is sized to the machine (148 SMs x 4 CTAs
-// x 8 warps) and every WARP walks quarter-env items (H/4 rows) with a static
-// stride: 16 384 items over 4 736 warps keeps every SM busy until the end, and the
-// per-env header (z-order ranks, sprite cells) is decoded with shuffles/ballots
-// instead of shared memory + __syncthreads.
-constexpr int kRenderCtasPerSm = 4;
-
-template <int MAXD, int MAXS>
-__global__ void __launch_bounds__(kRenderThreads)
-render_kernel_warp(const RenderParams p, const int parts) {
-  const int lane = threadIdx.x & 31;
-  const int warps_total = (gridDim.x * kRenderThreads) >> 5;
-  const int warp_id = (blockIdx.x * kRenderThreads + threadIdx.x) >> 5;
-  const int n = p.S + p.D;
-  const int segs_per_row = p.pitch >> 4;
-  const int rows_per_part = (p.H + parts - 1) / parts;
-  const int64_t plane = (int64_t)p.H * p.pitch;
-  const int64_t items = (int64_t)p.B * parts;
-  for (int64_t item = warp_id; item < items; item += warps_total) {
-    const int env = (int)(item / parts), part = (int)(item - (int64_t)env * parts);
-    const int r0 = part * rows_per_part, r1 = min(p.H, r0 + rows_per_part);
-    const int seg0 = r0 * segs_per_row, seg1 = r1 * segs_per_row;
-    const uint8_t* backdrop = p.backdrop + (int64_t)env * p.backdrop_bstride;
-    const uint8_t* curtains = p.curtains + (int64_t)env * p.D * plane;
-    uint8_t* board = p.board + (int64_t)env * plane;
-    // Tile loads of the first round go out before the header decode.
-    int seg = seg0 + lane;
-    uint4 px = make_uint4(0, 0, 0, 0);
-    uint4 cur[MAXD];
-    if (seg < seg1) {
-      const int64_t off = (int64_t)seg << 4;
-      px = __ldg(reinterpret_cast<const uint4*>(backdrop + off));
-#pragma unroll
-      for (int d = 0; d < MAXD; ++d)
-        if (d < p.D) cur[d] = __ldg(reinterpret_cast<const uint4*>(curtains + d * plane + off));
-    }
-    // Header: lane k < n holds z-order entry k; an entity's rank is the position of
-    // its character in the env's z-order (engine.py:751), found with one ballot.
-    const uint8_t zch = lane < n ? p.z_order[(int64_t)env * n + lane] : 0;
-    uint32_t rank_d[MAXD];
-#pragma unroll
-    for (int d = 0; d < MAXD; ++d) {
-      const unsigned hit = __ballot_sync(0xffffffffu, d < p.D && lane < n && zch == p.drape_char[d]);
-      rank_d[d] = (uint32_t)__ffs(hit) * 0x01010101u;
-    }
-    // Lane s < S holds sprite s: its segment (or -1), word, byte cover and rank.
-    int my_seg = -1, my_word = 0;
-    uint32_t my_cover = 0, my_rank = 0, my_ch4 = 0;
-    {
-      int sidx = lane < p.S ? lane : 0;
-      const int32_t* rec = p.sprites + ((int64_t)env * p.S + sidx) * PCL_SPRITE_WORDS;
-      int row = 0, col = 0, flags = 0;
-      if (lane < p.S) { row = rec[PCL_S_ROW]; col = rec[PCL_S_COL]; flags = rec[PCL_S_FLAGS]; }
-#pragma unroll
-      for (int s2 = 0; s2 < MAXS; ++s2) {
-        const unsigned hit = __ballot_sync(0xffffffffu, s2 < p.S && lane < n && zch == p.sprite_char[s2]);
-        if (lane == s2) {                   // static index: no local copy of the param block
-          my_rank = (uint32_t)__ffs(hit) * 0x01010101u;
-          my_ch4 = p.sprite_char[s2] * 0x01010101u;
-        }
-      }
-      if (lane < p.S) {
-        my_seg = (flags & 1) ? row * segs_per_row + (col >> 4) : -1;     // engine.py:754
-        my_word = (col & 15) >> 2;
-        my_cover = 0xffu << ((col & 3) * 8);
-      }
-    }
-    while (true) {
-      const bool live = seg < seg1;
-      uint4 rk = make_uint4(0, 0, 0, 0);
-#pragma unroll
-      for (int d = 0; d < MAXD; ++d) {
-        if (d < p.D) {
-          const uint32_t ch4 = p.drape_char[d] * 0x01010101u;
-          overlay(px.x, rk.x, __vcmpne4(cur[d].x, 0), ch4, rank_d[d]);   // rendering.py:160
-          overlay(px.y, rk.y, __vcmpne4(cur[d].y, 0), ch4, rank_d[d]);
-          overlay(px.z, rk.z, __vcmpne4(cur[d].z, 0), ch4, rank_d[d]);
-          overlay(px.w, rk.w, __vcmpne4(cur[d].w, 0), ch4, rank_d[d]);
-        }
-      }
-#pragma unroll
-      for (int s2 = 0; s2 < MAXS; ++s2) {
-        if (s2 < p.S) {                                                   // rendering.py:139
-          const int sseg = __shfl_sync(0xffffffffu, my_seg, s2);
-          const int w = __shfl_sync(0xffffffffu, my_word, s2);
-          const uint32_t cover = __shfl_sync(0xffffffffu, my_cover, s2);
-          const uint32_t r4 = __shfl_sync(0xffffffffu, my_rank, s2);
-          const uint32_t ch4 = __shfl_sync(0xffffffffu, my_ch4, s2);
-          if (live && sseg == seg) {
-            if (w == 0) overlay(px.x, rk.x, cover, ch4, r4);
-            else if (w == 1) overlay(px.y, rk.y, cover, ch4, r4);
-            else if (w == 2) overlay(px.z, rk.z, cover, ch4, r4);
-            else overlay(px.w, rk.w, cover, ch4, r4);
-          }
-        }
-      }
-      if (live) *reinterpret_cast<uint4*>(board + ((int64_t)seg << 4)) = px;
-      seg += 32;
-      if (__all_sync(0xffffffffu, seg >= seg1)) break;
-      if (seg < seg1) {
-        const int64_t off = (int64_t)seg << 4;
-        px = __ldg(reinterpret_cast<const uint4*>(backdrop + off));
-#pragma unroll
-        for (int d = 0; d < MAXD; ++d)
-          if (d < p.D) cur[d] = __ldg(reinterpret_cast<const uint4*>(curtains + d * plane + off));
-      }
-    }
-  }
-}
-
-// ---- persistent, software-pipelined variant --------------------------------------
-// Persistent CTAs (one resident set, grid = SMs x CTAs/SM) walk envs with a static
-// stride; the (1 + D) byte planes of the NEXT env travel into the other half of a
-// shared-memory double buffer with cp.async while the current env is flattened, so
-// every SM keeps loads in flight from its first to its last env and no register is
-// held by a load in flight.  The z-order / sprite header is decoded per env as in
-// render_kernel.
+// cp.async helpers (LDGSTS): 16-byte global -> shared copies, per-thread commit groups.
 __device__ __forceinline__ void cp16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::
                "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
@@ -246,113 +128,177 @@ template <int N> __device__ __forceinline__ void cp_wait() {
   asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory");
 }
 
+// ---- balanced chunks + per-thread cp.async ring (the default renderer) -------------------
+// The launch is ONE flat list of T = B * H * pitch / 16 segments.  The grid is sized to
+// the machine (SMs x resident CTAs) and CTA c owns the contiguous chunk
+// [c * chunk, (c + 1) * chunk): every SM moves the same number of bytes whatever B and
+// the board shape are (one-env CTAs waste most of a 256-thread block on a 16x39 board
+// and leave a 4096-env launch of 64x64 boards with 3.46 waves).  A chunk spans at most
+// kFlatEnvs envs; their headers (z-order ranks, sprite cells) are decoded ONCE into shared
+// memory while the first loads are already in flight, after which the streaming loop has
+// no block barrier: the (1 + D) 16-byte loads of a segment land in a PRIVATE shared-memory
+// slot of the issuing thread (cp.async: no register held while in flight; a thread only
+// ever reads slots it filled itself) and each thread keeps U segments in flight, so an SM
+// carries U x (1 + D) x 16 B x resident threads of loads from its first cycle to its last
+// (192 KB at U = 4, D = 2, 4 CTAs).  Programmatic dependent launch lets the next launch's
+// CTAs become resident while this one drains (they touch memory after griddepcontrol.wait).
+//
+// Measured (profiles/r02_render_ab.txt): 14.4 us per 4096-env launch of 64x64 boards
+// (0.71 of the 4 GB-copy peak; the one-env-CTA kernel, a register-staged flat kernel and
+// this one with an L2 prefetch ahead of griddepcontrol.wait all land on the same figure,
+// and a plain torch copy of the same bytes at this launch size is no faster), 0.89-0.90 when
+// one launch covers 24 576 envs.
+constexpr int kFlatEnvs = 12;
+
 template <int MAXD, int MAXS>
+struct FlatShared {
+  uint32_t rank_d[kFlatEnvs][MAXD];     // z rank of each drape, replicated in 4 bytes
+  uint32_t rank_s[kFlatEnvs][MAXS];
+  int seg[kFlatEnvs][MAXS];             // segment (within the env) of each visible sprite, or -1
+  uint32_t word_cover[kFlatEnvs][MAXS]; // the sprite's column & 15: word in bits 2-3, byte in 0-1
+};
+
+template <int MAXD, int MAXS, int U>
 __global__ void __launch_bounds__(kRenderThreads)
-render_kernel_pipe(const RenderParams p) {
+render_kernel_ring(const RenderParams p, const int64_t chunk, const int total_shift) {
   extern __shared__ __align__(16) uint8_t stage_mem[];
-  __shared__ RenderShared<MAXD, MAXS> sh;
+  __shared__ FlatShared<MAXD, MAXS> sh;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int n = p.S + p.D;
   const int segs_per_row = p.pitch >> 4;
-  const int total = p.H * segs_per_row;                  // 16-byte segments per plane
-  const int64_t plane = (int64_t)p.H * p.pitch;
+  const int total = p.H * segs_per_row;                 // segments per plane
+  const int64_t plane = (int64_t)total << 4;
+  const int64_t T = (int64_t)p.B * total;
+  const int64_t lo = (int64_t)blockIdx.x * chunk;
+  const int64_t hi = min(T, lo + chunk);
+  if (lo >= hi) return;
+  const int env0 = total_shift >= 0 ? (int)(lo >> total_shift) : (int)(lo / total);
+  const int env1 = total_shift >= 0 ? (int)((hi - 1) >> total_shift) : (int)((hi - 1) / total);
   const int planes = 1 + p.D;
-  const int stage_segs = planes * total;
-  uint4* stages = reinterpret_cast<uint4*>(stage_mem);
+  // slot (u, plane) of this thread: conflict-free 16-byte accesses
+  uint4* slots = reinterpret_cast<uint4*>(stage_mem) + threadIdx.x;
+  auto slot = [&](int u, int pl) { return slots + (u * planes + pl) * kRenderThreads; };
 
-  auto prefetch = [&](int stage, int env) {
-    const uint8_t* backdrop = p.backdrop + (int64_t)env * p.backdrop_bstride;
-    const uint8_t* curtains = p.curtains + (int64_t)env * p.D * plane;
-    uint4* dst = stages + (int64_t)stage * stage_segs;
-    for (int i = threadIdx.x; i < stage_segs; i += kRenderThreads) {
-      const int pl = i / total, seg = i - pl * total;
-      const uint8_t* src = pl == 0 ? backdrop + ((int64_t)seg << 4)
-                                   : curtains + (pl - 1) * plane + ((int64_t)seg << 4);
-      cp16(dst + i, src);
+  auto issue = [&](int u, int64_t g) {     // one commit group per segment, empty past the end
+    if (g < hi) {
+      const int env = total_shift >= 0 ? (int)(g >> total_shift) : (int)(g / total);
+      const int64_t off = (g - (int64_t)env * total) << 4;
+      cp16(slot(u, 0), p.backdrop + (int64_t)env * p.backdrop_bstride + off);
+      const uint8_t* curtains = p.curtains + (int64_t)env * p.D * plane + off;
+#pragma unroll
+      for (int d = 0; d < MAXD; ++d)
+        if (d < p.D) cp16(slot(u, d + 1), curtains + d * plane);
     }
     cp_commit();
   };
 
-  int env = blockIdx.x;
-  if (env >= p.B) return;
-  prefetch(0, env);
-  for (int it = 0; env < p.B; env += gridDim.x, ++it) {
-    const int next = env + gridDim.x;
-    if (next < p.B) prefetch((it + 1) & 1, next);
-    // Decode this env's z-order and sprite cells once per block.
-    if (threadIdx.x < n) {
-      const uint8_t ch = p.z_order[(int64_t)env * n + threadIdx.x];
-      const uint32_t rank4 = (threadIdx.x + 1) * 0x01010101u;
+  const int64_t first = lo + threadIdx.x;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 #pragma unroll
-      for (int s2 = 0; s2 < MAXS; ++s2) if (s2 < p.S && p.sprite_char[s2] == ch) sh.rank_s[s2] = rank4;
+  for (int u = 0; u < U; ++u) issue(u, first + (int64_t)u * kRenderThreads);
+
+  // Headers of the envs this chunk touches (overlaps the first DRAM round trip).
+  for (int i = threadIdx.x; i < (env1 - env0 + 1) * n; i += kRenderThreads) {
+    const int e = i / n, k = i - e * n;
+    const uint8_t ch = p.z_order[(int64_t)(env0 + e) * n + k];
+    const uint32_t rank4 = (k + 1) * 0x01010101u;
 #pragma unroll
-      for (int d = 0; d < MAXD; ++d) if (d < p.D && p.drape_char[d] == ch) sh.rank_d[d] = rank4;
-    }
-    if (threadIdx.x < p.S) {
-      const int32_t* rec = p.sprites + ((int64_t)env * p.S + threadIdx.x) * PCL_SPRITE_WORDS;
-      const int row = rec[PCL_S_ROW], col = rec[PCL_S_COL];
-      const bool vis = rec[PCL_S_FLAGS] & 1;                     // engine.py:754
-      sh.seg[threadIdx.x] = vis ? row * segs_per_row + (col >> 4) : -1;
-      sh.word[threadIdx.x] = (col & 15) >> 2;
-      sh.cover[threadIdx.x] = 0xffu << ((col & 3) * 8);
-    }
-    if (next < p.B) cp_wait<1>(); else cp_wait<0>();
-    __syncthreads();
-    const uint4* st = stages + (int64_t)(it & 1) * stage_segs;
-    uint8_t* board = p.board + (int64_t)env * plane;
-    for (int seg = threadIdx.x; seg < total; seg += kRenderThreads) {
-      uint4 px = st[seg];
-      uint4 rk = make_uint4(0, 0, 0, 0);
+    for (int s2 = 0; s2 < MAXS; ++s2) if (s2 < p.S && p.sprite_char[s2] == ch) sh.rank_s[e][s2] = rank4;
 #pragma unroll
-      for (int d = 0; d < MAXD; ++d) {
-        if (d < p.D) {
-          const uint4 cur = st[(d + 1) * total + seg];
-          const uint32_t ch4 = p.drape_char[d] * 0x01010101u;
-          const uint32_t r4 = sh.rank_d[d];
-          overlay(px.x, rk.x, __vcmpne4(cur.x, 0), ch4, r4);   // rendering.py:160
-          overlay(px.y, rk.y, __vcmpne4(cur.y, 0), ch4, r4);
-          overlay(px.z, rk.z, __vcmpne4(cur.z, 0), ch4, r4);
-          overlay(px.w, rk.w, __vcmpne4(cur.w, 0), ch4, r4);
-        }
-      }
-#pragma unroll
-      for (int s2 = 0; s2 < MAXS; ++s2) {
-        if (s2 < p.S && sh.seg[s2] == seg) {                         // rendering.py:139
-          const uint32_t ch4 = p.sprite_char[s2] * 0x01010101u;
-          const uint32_t r4 = sh.rank_s[s2], cover = sh.cover[s2];
-          const int w = sh.word[s2];
-          if (w == 0) overlay(px.x, rk.x, cover, ch4, r4);
-          else if (w == 1) overlay(px.y, rk.y, cover, ch4, r4);
-          else if (w == 2) overlay(px.z, rk.z, cover, ch4, r4);
-          else overlay(px.w, rk.w, cover, ch4, r4);
-        }
-      }
-      *reinterpret_cast<uint4*>(board + ((int64_t)seg << 4)) = px;
-    }
-    __syncthreads();                       // the stage and the header are free again
+    for (int d = 0; d < MAXD; ++d) if (d < p.D && p.drape_char[d] == ch) sh.rank_d[e][d] = rank4;
   }
+  for (int i = threadIdx.x; i < (env1 - env0 + 1) * p.S; i += kRenderThreads) {
+    const int e = i / p.S, s2 = i - e * p.S;
+    const int32_t* rec = p.sprites + ((int64_t)(env0 + e) * p.S + s2) * PCL_SPRITE_WORDS;
+    const int row = rec[PCL_S_ROW], col = rec[PCL_S_COL];
+    const bool vis = rec[PCL_S_FLAGS] & 1;                       // engine.py:754
+    sh.seg[e][s2] = vis ? row * segs_per_row + (col >> 4) : -1;
+    sh.word_cover[e][s2] = (uint32_t)(col & 15);
+  }
+  __syncthreads();
+
+  int u = 0;
+  for (int64_t g = first; g < hi; g += kRenderThreads) {
+    cp_wait<U - 1>();                        // the oldest group of this thread has landed
+    const int env = total_shift >= 0 ? (int)(g >> total_shift) : (int)(g / total);
+    const int seg = (int)(g - (int64_t)env * total);
+    const int e = env - env0;
+    uint4 px = *slot(u, 0);
+    uint4 rk = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int d = 0; d < MAXD; ++d) {
+      if (d < p.D) {
+        const uint4 cur = *slot(u, d + 1);
+        const uint32_t ch4 = p.drape_char[d] * 0x01010101u;
+        const uint32_t r4 = sh.rank_d[e][d];
+        overlay(px.x, rk.x, __vcmpne4(cur.x, 0), ch4, r4);   // rendering.py:160
+        overlay(px.y, rk.y, __vcmpne4(cur.y, 0), ch4, r4);
+        overlay(px.z, rk.z, __vcmpne4(cur.z, 0), ch4, r4);
+        overlay(px.w, rk.w, __vcmpne4(cur.w, 0), ch4, r4);
+      }
+    }
+    // the slot is free again: refill it before the (register-only) sprite pass
+    issue(u, g + (int64_t)U * kRenderThreads);
+#pragma unroll
+    for (int s2 = 0; s2 < MAXS; ++s2) {
+      if (s2 < p.S && sh.seg[e][s2] == seg) {                      // rendering.py:139
+        const uint32_t ch4 = p.sprite_char[s2] * 0x01010101u;
+        const uint32_t r4 = sh.rank_s[e][s2];
+        const uint32_t c = sh.word_cover[e][s2];
+        const uint32_t cover = 0xffu << ((c & 3) * 8);
+        const int w = c >> 2;
+        if (w == 0) overlay(px.x, rk.x, cover, ch4, r4);
+        else if (w == 1) overlay(px.y, rk.y, cover, ch4, r4);
+        else if (w == 2) overlay(px.z, rk.z, cover, ch4, r4);
+        else overlay(px.w, rk.w, cover, ch4, r4);
+      }
+    }
+    *reinterpret_cast<uint4*>(p.board + (int64_t)env * plane + ((int64_t)seg << 4)) = px;
+    u = (u + 1 == U) ? 0 : u + 1;
+  }
+  cp_wait<0>();
 }
 
-template <int MAXD, int MAXS>
-cudaError_t launch_render_pipe(const RenderParams& p, cudaStream_t s, bool* launched) {
-  const size_t smem = 2 * (size_t)(1 + p.D) * p.H * p.pitch;
+template <int MAXD, int MAXS, int U>
+cudaError_t launch_render_ring(const RenderParams& p, cudaStream_t s, bool* launched) {
   *launched = false;
-  if (smem > 96 * 1024) return cudaSuccess;              // big boards: the plain kernel
-  auto kern = render_kernel_pipe<MAXD, MAXS>;
+  const int total = p.H * (p.pitch >> 4);
+  const int64_t T = (int64_t)p.B * total;
+  const size_t smem = (size_t)U * (1 + p.D) * kRenderThreads * 16;
+  auto kern = render_kernel_ring<MAXD, MAXS, U>;
+  if (smem > 200 * 1024) return cudaSuccess;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  int per_sm = 0;
+  int dev = 0, sms = 148, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRenderThreads, smem);
   if (e != cudaSuccess) return e;
+  static const int cap = getenv("PCL_RENDER_CTAS_PER_SM") ? atoi(getenv("PCL_RENDER_CTAS_PER_SM")) : 0;
+  if (cap > 0 && per_sm > cap) per_sm = cap;
   if (per_sm < 1) return cudaSuccess;
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int grid = sms * per_sm;
-  if (grid > p.B) grid = p.B;
-  kern<<<grid, kRenderThreads, smem, s>>>(p);
+  int64_t grid = (int64_t)sms * per_sm;
+  int64_t chunk = (T + grid - 1) / grid;
+  if (chunk < kRenderThreads) chunk = kRenderThreads;
+  // A chunk may touch at most kFlatEnvs envs (the header table): big batches run
+  // several waves of capped chunks instead; boards under 256 / (kFlatEnvs - 2)
+  // segments take the plain kernel.
+  if (chunk > (int64_t)(kFlatEnvs - 2) * total) chunk = (int64_t)(kFlatEnvs - 2) * total;
+  if (chunk < kRenderThreads) return cudaSuccess;
+  grid = (T + chunk - 1) / chunk;
+  int shift = -1;
+  if ((total & (total - 1)) == 0) { shift = 0; while ((1 << shift) < total) ++shift; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kRenderThreads); cfg.stream = s;
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
   *launched = true;
-  return cudaGetLastError();
+  return cudaLaunchKernelEx(&cfg, kern, p, chunk, shift);
 }
 
 // Drape.curtain as bytes (things.py:213-217) from the packed device state.
@@ -676,36 +622,19 @@ __global__ void __launch_bounds__(128) crop_handoff_kernel(const CropParams p,
 
 cudaError_t launch_render(const RenderParams& p, cudaStream_t s) {
   // Loop bounds are compile-time so the per-segment code stays small.
-  // A/B switch: 1 = one CTA per env, 2 = persistent warps, 3 = persistent pipelined CTAs
-  static const int variant = getenv("PCL_RENDER_VARIANT") ? atoi(getenv("PCL_RENDER_VARIANT")) : 3;
-  if (variant == 3) {
+  // PCL_RENDER_VARIANT=1 forces the one-CTA-per-env kernel (A/B runs, tools/render_ab.py).
+  static const int variant = getenv("PCL_RENDER_VARIANT") ? atoi(getenv("PCL_RENDER_VARIANT")) : 5;
+  if (variant != 1) {
     bool done = false;
     cudaError_t e;
-    if (p.D <= 2 && p.S <= 4) e = launch_render_pipe<2, 4>(p, s, &done);
-    else if (p.D <= 2 && p.S <= 8) e = launch_render_pipe<2, 8>(p, s, &done);
-    else if (p.D <= 2) e = launch_render_pipe<2, 16>(p, s, &done);
-    else if (p.S <= 4) e = launch_render_pipe<8, 4>(p, s, &done);
-    else e = launch_render_pipe<8, 16>(p, s, &done);
+    if (p.D <= 2 && p.S <= 4) e = launch_render_ring<2, 4, 4>(p, s, &done);
+    else if (p.D <= 2 && p.S <= 8) e = launch_render_ring<2, 8, 4>(p, s, &done);
+    else if (p.D <= 2) e = launch_render_ring<2, 16, 4>(p, s, &done);
+    else if (p.S <= 4) e = launch_render_ring<8, 4, 2>(p, s, &done);
+    else e = launch_render_ring<8, 16, 2>(p, s, &done);
     if (e != cudaSuccess || done) return e;
   }
-  if (variant == 2 && p.S + p.D <= 32 && p.S <= 16) {
-    // Persistent warp-granular kernel: part = the largest power of two <= 8 that
-    // leaves every part at least one 32-segment round.
-    const int segs = p.H * (p.pitch >> 4);
-    int parts = 1;
-    while (parts < 8 && segs / (parts * 2) >= 32) parts *= 2;
-    const int64_t items = (int64_t)p.B * parts;
-    int64_t ctas = (items * 32 + kRenderThreads - 1) / kRenderThreads;
-    const int64_t cap = 148 * kRenderCtasPerSm;
-    if (ctas > cap) ctas = cap;
-    const int grid = (int)ctas;
-    if (p.D <= 2 && p.S <= 4) render_kernel_warp<2, 4><<<grid, kRenderThreads, 0, s>>>(p, parts);
-    else if (p.D <= 2 && p.S <= 8) render_kernel_warp<2, 8><<<grid, kRenderThreads, 0, s>>>(p, parts);
-    else if (p.D <= 2) render_kernel_warp<2, 16><<<grid, kRenderThreads, 0, s>>>(p, parts);
-    else if (p.S <= 4) render_kernel_warp<8, 4><<<grid, kRenderThreads, 0, s>>>(p, parts);
-    else render_kernel_warp<8, 16><<<grid, kRenderThreads, 0, s>>>(p, parts);
-    return cudaGetLastError();
-  }
+  // Boards under 256 / (kFlatEnvs - 2) segments: one CTA per env.
   if (p.D <= 2 && p.S <= 4) render_kernel<2, 4><<<p.B, kRenderThreads, 0, s>>>(p);
   else if (p.D <= 2 && p.S <= 8) render_kernel<2, 8><<<p.B, kRenderThreads, 0, s>>>(p);
   else if (p.D <= 2) render_kernel<2, 16><<<p.B, kRenderThreads, 0, s>>>(p);
