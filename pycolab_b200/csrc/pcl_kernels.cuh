@@ -111,6 +111,7 @@ struct CropParams {
   const uint8_t* board;
   uint8_t* out;
   const uint8_t* curtains[PCL_MAX_TRACK];   // byte curtains of tracked drapes (or NULL)
+  uint32_t cols_recip;           // floor(2^32 / crop.cols) + 1, set by the launcher
 };
 cudaError_t launch_crop(const CropParams& p, cudaStream_t s);
 

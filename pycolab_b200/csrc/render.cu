@@ -491,20 +491,24 @@ __device__ __forceinline__ void crop_corner(const CropParams& p, int env, int la
 
 // Four consecutive cells i .. i + 3 of the crop window (row-major over rows x cols)
 // as one little-endian word, pad character outside the board (_do_crop :118-227).
+// One division per word (by a runtime width, as a multiply-high with the reciprocal the
+// launcher put in CropParams: exact for i < 65536), then the cell walks along the row.
 __device__ __forceinline__ uint32_t crop_word(const CropParams& p, const uint8_t* board, int wr,
                                               int wc, int i, int cells) {
   const pcl_crop_spec& c = p.crop;
   const uint32_t padv = c.pad_char >= 0 ? (uint32_t)c.pad_char : 0u;
+  int jr = c.cols == 1 ? i : (int)__umulhi((uint32_t)i, p.cols_recip);   // i / cols
+  int jc = i - jr * c.cols;                                // i % cols
   uint32_t v = 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int j = i + k;
-    if (j >= cells) break;
-    const int r = wr + j / c.cols, cc2 = wc + j % c.cols;
+    if (i + k >= cells) break;
+    const int r = wr + jr, cc2 = wc + jc;
     uint32_t b = padv;
     if ((unsigned)r < (unsigned)p.H && (unsigned)cc2 < (unsigned)p.W)
       b = board[(int64_t)r * p.pitch + cc2];
     v |= b << (8 * k);
+    if (++jc == c.cols) { jc = 0; ++jr; }
   }
   return v;
 }
@@ -513,6 +517,8 @@ __global__ void __launch_bounds__(128) crop_kernel(const CropParams p) {
   __shared__ int s_hist[4][256];
   const int lane = threadIdx.x & 31;
   const int env = blockIdx.x * 4 + (threadIdx.x >> 5);
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");     // the step kernel's board and records
   if (env >= p.B) return;
   int wr, wc;
   crop_corner(p, env, lane, s_hist[threadIdx.x >> 5], &wr, &wc);
@@ -569,6 +575,10 @@ __global__ void __launch_bounds__(128) crop_handoff_kernel(const CropParams p,
   __shared__ int s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int env = blockIdx.x * 4 + warp;
+  // Programmatic dependent launch: resident while the step kernel drains, reads
+  // nothing before it (and the previous hand-off, which bumps the counter) is done.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t step = x.local[0];                        // steps completed so far
   const int64_t half = (int64_t)(step & 1u) * x.rows * x.record_bytes;
   if (env < p.B) {
@@ -650,13 +660,33 @@ cudaError_t launch_layers(const LayersParams& p, cudaStream_t s) {
   layers_kernel<<<p.B, 256, 0, s>>>(p);
   return cudaGetLastError();
 }
+namespace {
+// Launch with the programmatic-stream-serialisation attribute (the kernel calls
+// griddepcontrol.wait before its first global access).
+template <typename... Params, typename... Args>
+cudaError_t launch_pdl(void (*kern)(Params...), int grid, int block, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+}  // namespace
+// floor(2^32 / cols) + 1: __umulhi(i, recip) == i / cols for every i < 65536 (cols >= 1).
+static CropParams with_recip(const CropParams& p) {
+  CropParams q = p;
+  q.cols_recip = p.crop.cols > 1 ? (uint32_t)(0x100000000ull / (uint32_t)p.crop.cols) + 1u : 0u;
+  return q;
+}
 cudaError_t launch_crop(const CropParams& p, cudaStream_t s) {
-  crop_kernel<<<(p.B + 3) / 4, 128, 0, s>>>(p);
-  return cudaGetLastError();
+  if (p.crop.cols < 1 || (int64_t)p.crop.rows * p.crop.cols >= 65536) return cudaErrorInvalidValue;
+  return launch_pdl(crop_kernel, (p.B + 3) / 4, 128, s, with_recip(p));
 }
 cudaError_t launch_crop_handoff(const CropParams& p, const HandoffParams& x, cudaStream_t s) {
-  crop_handoff_kernel<<<(p.B + 3) / 4, 128, 0, s>>>(p, x);
-  return cudaGetLastError();
+  if (p.crop.cols < 1 || (int64_t)p.crop.rows * p.crop.cols >= 65536) return cudaErrorInvalidValue;
+  return launch_pdl(crop_handoff_kernel, (p.B + 3) / 4, 128, s, with_recip(p), x);
 }
 
 }  // namespace pcl

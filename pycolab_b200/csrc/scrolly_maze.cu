@@ -32,6 +32,14 @@
 //      out with uint4 stores; records go back with two coalesced stores.
 // So a step costs ~two dependent DRAM round trips (records, then everything).
 //
+// Tried and rejected (round 2, A/B on one B200, profiles/r02_step_variants.txt): HALF a
+// warp per env (two envs per warp, every warp primitive on the half's 16-lane mask; the
+// ~760 warp instructions of game logic per env issued once per two envs).  Bit-exact on
+// the whole GPU suite, but 14.2 us per 4096-env step against 11.96 us for this kernel:
+// the step is bound by the length of ONE warp's dependent chain, not by issue slots, and
+// halving the lanes doubles every staging / paint loop on that chain while 14 instead of
+// 28 warps per SM hide less of it.
+//
 // Sprite order P,a,b,c (indices 0..3); drape order '#','@' (0, 1).
 // Registers: patroller aux0 = moving_east; P aux0/aux1 = scroll permit mask /
 // permit frame; '@' aux0/aux1 = board cell of a coin already removed from the
@@ -195,13 +203,15 @@ scrolly_maze_step(const StepParams p) {
   // Byte-permute selectors for 4 cells at once: index = wall nibble << 4 | coin
   // nibble; selector nibble k picks byte 5 ('#') if wall_k, else byte 4 ('@') if
   // coin_k, else byte k of the backdrop word (z-order ... '@' '#' ...).
-  __shared__ __align__(16) uint16_t s_sel[256];
-  if (threadIdx.x < 32)
-    cp_async16(reinterpret_cast<uint8_t*>(s_sel) + threadIdx.x * 16,
-               reinterpret_cast<const uint8_t*>(g_sel.v) + threadIdx.x * 16);
-  pdl_launch_dependents();
+  // One copy per WARP: a warp then needs no block barrier before it paints (warps of a
+  // block leave at different points: ragged tail, frozen envs).
+  __shared__ __align__(16) uint16_t s_sel_all[kWarpsPerBlock][256];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  uint16_t* s_sel = s_sel_all[warp];
+  cp_async16(reinterpret_cast<uint8_t*>(s_sel) + lane * 16,
+             reinterpret_cast<const uint8_t*>(g_sel.v) + lane * 16);
+  pdl_launch_dependents();
   const int env = blockIdx.x * kWarpsPerBlock + warp;
   const bool live = env < p.B;
   const int H = p.H, W = p.W, PWW = p.PWW;
@@ -218,7 +228,6 @@ scrolly_maze_step(const StepParams p) {
   pdl_wait_prior_grids();
   if (!live) {                 // ragged last block: only the selector copy to drain
     cp_async_wait_all();
-    __syncthreads();
     return;
   }
   const int64_t lvl = p.st.d_level ? p.st.d_level[env] : env;   // index of static level data
@@ -253,7 +262,6 @@ scrolly_maze_step(const StepParams p) {
   }
   if (frozen) {                              // warp-uniform
     cp_async_wait_all();
-    __syncthreads();                         // the block barrier below is taken by all warps
     return;
   }
   int action;
@@ -454,6 +462,7 @@ scrolly_maze_step(const StepParams p) {
       hit = mine.vrow == p_vrow && mine.vcol == p_vcol;     // PatrollerSprite :303-305
     }
   }
+  __syncwarp();                              // every lane has read the records it needs (racecheck)
   if (lane < 4) {                            // write my walker back
     int32_t* r = rec + me * PCL_SPRITE_WORDS;
     r[PCL_S_ROW] = mine.row; r[PCL_S_COL] = mine.col;
@@ -598,7 +607,7 @@ scrolly_maze_step(const StepParams p) {
     if (lane == i && visible(mine)) s_bd[mine.row * pitch + mine.col] = p.sprite_char[i];
     __syncwarp();
   }
-  __syncthreads();                           // s_sel has landed for every warp of the block
+  __syncwarp();                              // this warp's s_sel copy has landed (waited above)
   // 5b. The streaming loop: 16 cells per lane per iteration, segment index ==
   // 16-byte index into both the staged tile and the board (pitch = 16 * spr).
   const int total = H * spr;

@@ -38,33 +38,57 @@ def main(path):
     for m in RAW:
       if m in hdr:
         print('  %-62s %s %s' % (m, r[hdr.index(m)], units[hdr.index(m)]))
+  # The correlated page comes as one section per source FILE of the first kernel
+  # (header, then a "File Path" row); aggregate them all.
   text = ncu('-i', path, '--page', 'source', '--print-source', 'cuda,sass', '--csv')
-  hdr, agg, cur, kern = None, {}, None, 0
+  hdr, agg, cur, fname, first_kernel = None, {}, None, '?', None
+  ops = {}
   for r in csv.reader(io.StringIO(text)):
-    if r and r[0] == 'Function Name':
-      kern += 1
+    if not r:
       continue
-    if r and r[0] == 'Line No' and len(r) > 5:
+    if r[0] == 'File Path':
+      fname = r[1].split('/')[-1]
+      continue
+    if r[0] == 'Function Name':
+      if first_kernel is None:
+        first_kernel = r[1]
+      cur = None
+      continue
+    if r[0] == 'Line No' and len(r) > 5:
       hdr = r
       continue
-    if hdr is None or len(r) != len(hdr) or kern != 1:
+    if hdr is None or len(r) != len(hdr):
       continue
     if r[0]:
-      cur = (r[0], r[1].strip()[:96])
+      cur = (fname, r[0], r[1].strip()[:92])
       agg.setdefault(cur, [0, 0])
       continue
+    if cur is None:
+      continue
     try:
-      agg[cur][0] += int(r[hdr.index('# Samples')])
-      agg[cur][1] += int(r[hdr.index('Instructions Executed')])
+      n_s, n_i = int(r[hdr.index('# Samples')]), int(r[hdr.index('Instructions Executed')])
     except (ValueError, TypeError, KeyError):
-      pass
+      continue
+    agg[cur][0] += n_s
+    agg[cur][1] += n_i
+    sass = r[3].split()
+    if sass:
+      op = (sass[1] if sass[0].startswith('@') and len(sass) > 1 else sass[0]).split('.')[0]
+      ops[op] = ops.get(op, 0) + n_i
   tot = sum(v[0] for v in agg.values()) or 1
-  print('\n## warp-stall samples by CUDA source line (launch 1): %d samples, %d warp '
-        'instructions' % (tot, sum(v[1] for v in agg.values())))
-  print('  line samples   share   warp-instr  source')
+  tot_i = sum(v[1] for v in agg.values()) or 1
+  print('\n## warp-stall samples by CUDA source line (launch 1, all source files): %d samples, '
+        '%d warp instructions' % (tot, tot_i))
+  print('  file:line                samples   share   warp-instr  source')
   for k in sorted(agg, key=lambda k: -agg[k][0])[:25]:
-    print('  %4s %7d  %5.1f%%  %10d  %s' % (k[0], agg[k][0], 100.0 * agg[k][0] / tot,
-                                           agg[k][1], k[1]))
+    print('  %-22s %7d  %5.1f%%  %10d  %s' % ('%s:%s' % (k[0], k[1]), agg[k][0],
+                                              100.0 * agg[k][0] / tot, agg[k][1], k[2]))
+  print('\n## executed warp instructions by CUDA source line (top 25)')
+  for k in sorted(agg, key=lambda k: -agg[k][1])[:25]:
+    print('  %-22s %10d  %5.1f%%  %s' % ('%s:%s' % (k[0], k[1]), agg[k][1],
+                                         100.0 * agg[k][1] / tot_i, k[2]))
+  print('\n## executed warp instructions by SASS opcode')
+  print('  ' + '  '.join('%s %d' % (o, ops[o]) for o in sorted(ops, key=lambda o: -ops[o])[:24]))
 
 
 if __name__ == '__main__':
