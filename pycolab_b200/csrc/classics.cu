@@ -145,6 +145,7 @@ classics_step(const StepParams p) {
   }
 
   // ---- _apply_and_clear_plot (engine.py:761-847) + records back
+  __syncwarp();                 // every lane has read the staged records (racecheck: WAR)
   if (lane == 0) {
     rec[PCL_S_ROW] = sp.row; rec[PCL_S_COL] = sp.col;
     rec[PCL_S_VROW] = sp.vrow; rec[PCL_S_VCOL] = sp.vcol; rec[PCL_S_FLAGS] = sp.flags;

@@ -7,8 +7,6 @@
 // occlusion flatten down the z-order is done per 16-byte segment with byte-SIMD
 // rank compares so that all (1 + D) loads of a segment are issued up front and
 // no register array is indexed dynamically.
-#include <stdlib.h>
-
 #include "pcl_device.cuh"
 #include "pcl_kernels.cuh"
 
@@ -116,189 +114,6 @@ render_kernel(const RenderParams p) {
         if (d < p.D) cur[d] = __ldg(reinterpret_cast<const uint4*>(curtains + d * plane + off));
     }
   }
-}
-
-// cp.async helpers (LDGSTS): 16-byte global -> shared copies, per-thread commit groups.
-__device__ __forceinline__ void cp16(void* smem, const void* gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::
-               "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
-}
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_wait() {
-  asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory");
-}
-
-// ---- balanced chunks + per-thread cp.async ring (the default renderer) -------------------
-// The launch is ONE flat list of T = B * H * pitch / 16 segments.  The grid is sized to
-// the machine (SMs x resident CTAs) and CTA c owns the contiguous chunk
-// [c * chunk, (c + 1) * chunk): every SM moves the same number of bytes whatever B and
-// the board shape are (one-env CTAs waste most of a 256-thread block on a 16x39 board
-// and leave a 4096-env launch of 64x64 boards with 3.46 waves).  A chunk spans at most
-// kFlatEnvs envs; their headers (z-order ranks, sprite cells) are decoded ONCE into shared
-// memory while the first loads are already in flight, after which the streaming loop has
-// no block barrier: the (1 + D) 16-byte loads of a segment land in a PRIVATE shared-memory
-// slot of the issuing thread (cp.async: no register held while in flight; a thread only
-// ever reads slots it filled itself) and each thread keeps U segments in flight, so an SM
-// carries U x (1 + D) x 16 B x resident threads of loads from its first cycle to its last
-// (192 KB at U = 4, D = 2, 4 CTAs).  Programmatic dependent launch lets the next launch's
-// CTAs become resident while this one drains (they touch memory after griddepcontrol.wait).
-//
-// Measured (profiles/r02_render_ab.txt): 14.4 us per 4096-env launch of 64x64 boards
-// (0.71 of the 4 GB-copy peak; the one-env-CTA kernel, a register-staged flat kernel and
-// this one with an L2 prefetch ahead of griddepcontrol.wait all land on the same figure,
-// and a plain torch copy of the same bytes at this launch size is no faster), 0.89-0.90 when
-// one launch covers 24 576 envs.
-constexpr int kFlatEnvs = 12;
-
-template <int MAXD, int MAXS>
-struct FlatShared {
-  uint32_t rank_d[kFlatEnvs][MAXD];     // z rank of each drape, replicated in 4 bytes
-  uint32_t rank_s[kFlatEnvs][MAXS];
-  int seg[kFlatEnvs][MAXS];             // segment (within the env) of each visible sprite, or -1
-  uint32_t word_cover[kFlatEnvs][MAXS]; // the sprite's column & 15: word in bits 2-3, byte in 0-1
-};
-
-template <int MAXD, int MAXS, int U>
-__global__ void __launch_bounds__(kRenderThreads)
-render_kernel_ring(const RenderParams p, const int64_t chunk, const int total_shift) {
-  extern __shared__ __align__(16) uint8_t stage_mem[];
-  __shared__ FlatShared<MAXD, MAXS> sh;
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  const int n = p.S + p.D;
-  const int segs_per_row = p.pitch >> 4;
-  const int total = p.H * segs_per_row;                 // segments per plane
-  const int64_t plane = (int64_t)total << 4;
-  const int64_t T = (int64_t)p.B * total;
-  const int64_t lo = (int64_t)blockIdx.x * chunk;
-  const int64_t hi = min(T, lo + chunk);
-  if (lo >= hi) return;
-  const int env0 = total_shift >= 0 ? (int)(lo >> total_shift) : (int)(lo / total);
-  const int env1 = total_shift >= 0 ? (int)((hi - 1) >> total_shift) : (int)((hi - 1) / total);
-  const int planes = 1 + p.D;
-  // slot (u, plane) of this thread: conflict-free 16-byte accesses
-  uint4* slots = reinterpret_cast<uint4*>(stage_mem) + threadIdx.x;
-  auto slot = [&](int u, int pl) { return slots + (u * planes + pl) * kRenderThreads; };
-
-  auto issue = [&](int u, int64_t g) {     // one commit group per segment, empty past the end
-    if (g < hi) {
-      const int env = total_shift >= 0 ? (int)(g >> total_shift) : (int)(g / total);
-      const int64_t off = (g - (int64_t)env * total) << 4;
-      cp16(slot(u, 0), p.backdrop + (int64_t)env * p.backdrop_bstride + off);
-      const uint8_t* curtains = p.curtains + (int64_t)env * p.D * plane + off;
-#pragma unroll
-      for (int d = 0; d < MAXD; ++d)
-        if (d < p.D) cp16(slot(u, d + 1), curtains + d * plane);
-    }
-    cp_commit();
-  };
-
-  const int64_t first = lo + threadIdx.x;
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-#pragma unroll
-  for (int u = 0; u < U; ++u) issue(u, first + (int64_t)u * kRenderThreads);
-
-  // Headers of the envs this chunk touches (overlaps the first DRAM round trip).
-  for (int i = threadIdx.x; i < (env1 - env0 + 1) * n; i += kRenderThreads) {
-    const int e = i / n, k = i - e * n;
-    const uint8_t ch = p.z_order[(int64_t)(env0 + e) * n + k];
-    const uint32_t rank4 = (k + 1) * 0x01010101u;
-#pragma unroll
-    for (int s2 = 0; s2 < MAXS; ++s2) if (s2 < p.S && p.sprite_char[s2] == ch) sh.rank_s[e][s2] = rank4;
-#pragma unroll
-    for (int d = 0; d < MAXD; ++d) if (d < p.D && p.drape_char[d] == ch) sh.rank_d[e][d] = rank4;
-  }
-  for (int i = threadIdx.x; i < (env1 - env0 + 1) * p.S; i += kRenderThreads) {
-    const int e = i / p.S, s2 = i - e * p.S;
-    const int32_t* rec = p.sprites + ((int64_t)(env0 + e) * p.S + s2) * PCL_SPRITE_WORDS;
-    const int row = rec[PCL_S_ROW], col = rec[PCL_S_COL];
-    const bool vis = rec[PCL_S_FLAGS] & 1;                       // engine.py:754
-    sh.seg[e][s2] = vis ? row * segs_per_row + (col >> 4) : -1;
-    sh.word_cover[e][s2] = (uint32_t)(col & 15);
-  }
-  __syncthreads();
-
-  int u = 0;
-  for (int64_t g = first; g < hi; g += kRenderThreads) {
-    cp_wait<U - 1>();                        // the oldest group of this thread has landed
-    const int env = total_shift >= 0 ? (int)(g >> total_shift) : (int)(g / total);
-    const int seg = (int)(g - (int64_t)env * total);
-    const int e = env - env0;
-    uint4 px = *slot(u, 0);
-    uint4 rk = make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int d = 0; d < MAXD; ++d) {
-      if (d < p.D) {
-        const uint4 cur = *slot(u, d + 1);
-        const uint32_t ch4 = p.drape_char[d] * 0x01010101u;
-        const uint32_t r4 = sh.rank_d[e][d];
-        overlay(px.x, rk.x, __vcmpne4(cur.x, 0), ch4, r4);   // rendering.py:160
-        overlay(px.y, rk.y, __vcmpne4(cur.y, 0), ch4, r4);
-        overlay(px.z, rk.z, __vcmpne4(cur.z, 0), ch4, r4);
-        overlay(px.w, rk.w, __vcmpne4(cur.w, 0), ch4, r4);
-      }
-    }
-    // the slot is free again: refill it before the (register-only) sprite pass
-    issue(u, g + (int64_t)U * kRenderThreads);
-#pragma unroll
-    for (int s2 = 0; s2 < MAXS; ++s2) {
-      if (s2 < p.S && sh.seg[e][s2] == seg) {                      // rendering.py:139
-        const uint32_t ch4 = p.sprite_char[s2] * 0x01010101u;
-        const uint32_t r4 = sh.rank_s[e][s2];
-        const uint32_t c = sh.word_cover[e][s2];
-        const uint32_t cover = 0xffu << ((c & 3) * 8);
-        const int w = c >> 2;
-        if (w == 0) overlay(px.x, rk.x, cover, ch4, r4);
-        else if (w == 1) overlay(px.y, rk.y, cover, ch4, r4);
-        else if (w == 2) overlay(px.z, rk.z, cover, ch4, r4);
-        else overlay(px.w, rk.w, cover, ch4, r4);
-      }
-    }
-    *reinterpret_cast<uint4*>(p.board + (int64_t)env * plane + ((int64_t)seg << 4)) = px;
-    u = (u + 1 == U) ? 0 : u + 1;
-  }
-  cp_wait<0>();
-}
-
-template <int MAXD, int MAXS, int U>
-cudaError_t launch_render_ring(const RenderParams& p, cudaStream_t s, bool* launched) {
-  *launched = false;
-  const int total = p.H * (p.pitch >> 4);
-  const int64_t T = (int64_t)p.B * total;
-  const size_t smem = (size_t)U * (1 + p.D) * kRenderThreads * 16;
-  auto kern = render_kernel_ring<MAXD, MAXS, U>;
-  if (smem > 200 * 1024) return cudaSuccess;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-  }
-  int dev = 0, sms = 148, per_sm = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRenderThreads, smem);
-  if (e != cudaSuccess) return e;
-  static const int cap = getenv("PCL_RENDER_CTAS_PER_SM") ? atoi(getenv("PCL_RENDER_CTAS_PER_SM")) : 0;
-  if (cap > 0 && per_sm > cap) per_sm = cap;
-  if (per_sm < 1) return cudaSuccess;
-  int64_t grid = (int64_t)sms * per_sm;
-  int64_t chunk = (T + grid - 1) / grid;
-  if (chunk < kRenderThreads) chunk = kRenderThreads;
-  // A chunk may touch at most kFlatEnvs envs (the header table): big batches run
-  // several waves of capped chunks instead; boards under 256 / (kFlatEnvs - 2)
-  // segments take the plain kernel.
-  if (chunk > (int64_t)(kFlatEnvs - 2) * total) chunk = (int64_t)(kFlatEnvs - 2) * total;
-  if (chunk < kRenderThreads) return cudaSuccess;
-  grid = (T + chunk - 1) / chunk;
-  int shift = -1;
-  if ((total & (total - 1)) == 0) { shift = 0; while ((1 << shift) < total) ++shift; }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kRenderThreads); cfg.stream = s;
-  cfg.dynamicSmemBytes = smem;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  *launched = true;
-  return cudaLaunchKernelEx(&cfg, kern, p, chunk, shift);
 }
 
 // Drape.curtain as bytes (things.py:213-217) from the packed device state.
@@ -631,20 +446,11 @@ __global__ void __launch_bounds__(128) crop_handoff_kernel(const CropParams p,
 }  // namespace
 
 cudaError_t launch_render(const RenderParams& p, cudaStream_t s) {
-  // Loop bounds are compile-time so the per-segment code stays small.
-  // PCL_RENDER_VARIANT=1 forces the one-CTA-per-env kernel (A/B runs, tools/render_ab.py).
-  static const int variant = getenv("PCL_RENDER_VARIANT") ? atoi(getenv("PCL_RENDER_VARIANT")) : 5;
-  if (variant != 1) {
-    bool done = false;
-    cudaError_t e;
-    if (p.D <= 2 && p.S <= 4) e = launch_render_ring<2, 4, 4>(p, s, &done);
-    else if (p.D <= 2 && p.S <= 8) e = launch_render_ring<2, 8, 4>(p, s, &done);
-    else if (p.D <= 2) e = launch_render_ring<2, 16, 4>(p, s, &done);
-    else if (p.S <= 4) e = launch_render_ring<8, 4, 2>(p, s, &done);
-    else e = launch_render_ring<8, 16, 2>(p, s, &done);
-    if (e != cudaSuccess || done) return e;
-  }
-  // Boards under 256 / (kFlatEnvs - 2) segments: one CTA per env.
+  // Loop bounds are compile-time so the per-segment code stays small.  One CTA per env
+  // is the measured best at every launch size that matters (profiles/r02_render_ab.txt:
+  // persistent warps, a 2-stage cp.async CTA pipeline, balanced flat chunks with register
+  // staging and with a per-thread cp.async ring were all slower at 4096 envs; only the ring
+  // gained anything, 2 % at 24 576 envs per launch).
   if (p.D <= 2 && p.S <= 4) render_kernel<2, 4><<<p.B, kRenderThreads, 0, s>>>(p);
   else if (p.D <= 2 && p.S <= 8) render_kernel<2, 8><<<p.B, kRenderThreads, 0, s>>>(p);
   else if (p.D <= 2) render_kernel<2, 16><<<p.B, kRenderThreads, 0, s>>>(p);
