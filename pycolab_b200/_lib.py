@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libpcl.so')
+# PCL_LIB_PATH: development switch for A/B runs of two builds in one process series.
+LIB_PATH = os.environ.get('PCL_LIB_PATH') or os.path.join(_HERE, 'libpcl.so')
 
 ABI_VERSION = 2
 MAX_SPRITES = 16

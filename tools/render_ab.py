@@ -1,10 +1,12 @@
 #!/usr/bin/env python
-"""A/B of the stand-alone renderer variants (PCL_RENDER_VARIANT) on the C2 shape:
-4096-env launches rotating over 6 batches (working set > L2) and one 24576-env
-launch.  Each variant runs in its own process (the switch is read once).
+"""Stand-alone renderer microbenchmarks on the C2 shape: 4096-env launches rotating
+over 6 batches (working set > L2), one 24576-env launch, and (`sweep`) a launch-size
+sweep.  Round 2 used it to A/B seven kernel variants through a PCL_RENDER_VARIANT
+switch in csrc/render.cu (results: profiles/r02_render_ab.txt); only the winner (one
+CTA per env) is left in the library, so the variant argument is now just a label.
 
-    python tools/render_ab.py            # variants 1 2 3 4
-    python tools/render_ab.py 4 1        # chosen variants
+    python tools/render_ab.py 1          # the renderer as built
+    python tools/render_ab.py sweep 1    # us per launch by batch size
 """
 import json
 import os
