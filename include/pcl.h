@@ -76,6 +76,11 @@ typedef enum pcl_program {
   PCL_PROG_HELLO = 9,        /* examples/hello_world.py:58-118: plain Sprites (aux0 = direction set)
                                 + one rolling Drape (record AUX0 / AUX1 = row / column shift of the
                                 reset curtain); program_arg[0..n) = the z-order chars */
+  PCL_PROG_APPREHEND = 10,   /* examples/apprehend.py:56-131: sprites 'P' (confined catcher) and 'b' (falling
+                                ball); the ball's AUX0 / AUX1 hold its float64 slope (bits lo / hi), plot
+                                AUX0 / AUX1 its x accumulator; with pcl_state.d_rng bound (the words of
+                                Python's random.Random(seed).getstate()) the slope is drawn on the device at
+                                every (re)start as random.uniform does, else taken from the reset template */
   PCL_PROG_ORDEAL = 8        /* examples/ordeal.py:74-266: program_arg[0] = PCL_ORDEAL_* chapter;
                                 plot words AUX0 has_sword, AUX1 last_position (row << 16 | col,
                                 -1 unset), AUX2 next_chapter chosen on the device, AUX3 prior chapter */

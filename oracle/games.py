@@ -732,3 +732,48 @@ def hello_program(world, ch, actions):
     k = int(ch) - 1                               # direction_set :62-65
     ent.col = (ent.col + HELLO_DX[k][actions]) % ent.cols
     ent.row = (ent.row + HELLO_DY[k][actions]) % ent.rows
+
+
+# ==========================================================================
+# apprehend: a ball falling along a random straight line and a
+# catcher; the ball's slope is a float64 drawn from Python's `random` when the
+# sprite is BUILT (apprehend.py:95-106), so every episode draws once.
+# ==========================================================================
+
+def make_apprehend(art, rng):
+  """examples/apprehend.py:56-60; `rng` stands for the `random` module
+  (`random.Random(seed)` reproduces `random.seed(seed)` + the module functions)."""
+  backdrop, masks = split_art(art, ['P', 'b'], ' ')
+  shape = backdrop.shape
+  player = em.Walker('P', shape, mask_position(masks['P']), impassable='',
+                     confined=True)                                   # :71-74
+  ball = em.Walker('b', shape, mask_position(masks['b']), impassable='')   # :98-100
+  ball.aux['dx'] = rng.uniform(-2.499, 2.499) / (shape[0] - 1.0)       # :103
+  ball.aux['acc'] = 0.0                                                # :107
+  return em.World(shape[0], shape[1], backdrop, {'P': player, 'b': ball},
+                  z_order=['b', 'P'],              # ascii_art.py:184: the flat update schedule
+                  groups=[['b', 'P']], program=apprehend_program)
+
+
+def apprehend_program(world, ch, actions):
+  plot, ent, board = world.plot, world.things[ch], world.board
+  if ch == 'P':                                   # PlayerSprite.update :76-87
+    if actions == 0:
+      em.walker_move(ent, board, plot, em.M_W)
+    elif actions == 1:
+      em.walker_move(ent, board, plot, em.M_E)
+    if ent.virtual_position == world.things['b'].virtual_position:
+      plot.add_reward(1)
+      plot.terminate_episode()
+  else:                                           # BallSprite.update :109-131
+    em.walker_move(ent, board, plot, em.M_S)
+    ent.aux['acc'] += ent.aux['dx']
+    if ent.aux['acc'] < -0.5:
+      em.walker_move(ent, board, plot, em.M_W)
+      ent.aux['acc'] += 1.0
+    elif ent.aux['acc'] > 0.5:
+      em.walker_move(ent, board, plot, em.M_E)
+      ent.aux['acc'] -= 1.0
+    if ent.virtual_position[0] >= board.shape[0]:
+      plot.add_reward(-1)
+      plot.terminate_episode()

@@ -47,7 +47,9 @@ class BatchedEngine(object):
     Env e uses games[e % len(games)]; with a single game the static level data
     (backdrop, immutable patterns, reset templates) is shared by all envs.
     env_offset: global index of this shard's env 0 (per-env RNG streams are
-    seeded rng_seed + global env index); rng_states: explicit u32 [B, 625]
+    seeded rng_seed + global env index — NumPy RandomState(seed) or, for games that
+    draw from Python's `random`, random.Random(seed)); rng_states: explicit u32 [B, 625]
+    (False: bind no RNG, for programs that can take their draws from the templates)
     MT19937 states (624 key words + position) instead of seeds.
     share_levels=False stores the static level data once PER ENV instead of once
     per level (the reference's layout: every Engine owns its backdrop)."""
@@ -151,9 +153,15 @@ class BatchedEngine(object):
                             2 * _lib.FIXTURE_DIRECTIVES
                             if g0.program == _lib.PROG_FIXTURE else 1)
     self.rng = None
-    if g0.needs_rng:
+    if g0.needs_rng and rng_states is not False:
       if rng_states is not None:
         states = np.ascontiguousarray(rng_states, dtype=np.uint32).reshape(B, _lib.MT_WORDS)
+      elif getattr(g0, 'rng_kind', 'numpy') == 'python':
+        # Python's `random` (apprehend.py:103): the 625 words of Random(seed).getstate()
+        import random as _random
+        states = np.empty((B, _lib.MT_WORDS), dtype=np.uint32)
+        for e in range(B):
+          states[e] = _random.Random(rng_seed + env_offset + e).getstate()[1]
       else:
         states = np.empty((B, _lib.MT_WORDS), dtype=np.uint32)
         for e in range(B):

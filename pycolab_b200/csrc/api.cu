@@ -210,6 +210,20 @@ int validate(const pcl_spec& s) {
         if (s.program_arg[k] != s.z_order[k]) return PCL_ERR_INVALID;
       return PCL_OK;
     }
+    case PCL_PROG_APPREHEND: {
+      if (s.n_sprites != 2 || s.n_drapes != 0) return PCL_ERR_UNSUPPORTED;
+      // one update group: the ball, then the catcher; the catcher is drawn on top
+      if (s.n_groups != 1 || s.group_len[0] != 2 || s.group_chars[0] != s.sprite_char[1] ||
+          s.group_chars[1] != s.sprite_char[0]) return PCL_ERR_UNSUPPORTED;
+      if (s.z_order[0] != s.sprite_char[1] || s.z_order[1] != s.sprite_char[0]) return PCL_ERR_UNSUPPORTED;
+      if (!s.sprite_confined[0] || s.sprite_confined[1]) return PCL_ERR_UNSUPPORTED;
+      for (int i = 0; i < 2; ++i) {
+        if (s.sprite_egocentric[i]) return PCL_ERR_UNSUPPORTED;
+        for (int w = 0; w < 4; ++w) if (s.impassable[i][w]) return PCL_ERR_UNSUPPORTED;
+      }
+      if (s.rows < 2) return PCL_ERR_INVALID;          // the slope divides by rows - 1
+      return PCL_OK;
+    }
     case PCL_PROG_ORDEAL: {
       const int chapter = s.program_arg[0];
       const int want_s = chapter == PCL_ORDEAL_CASTLE ? 2 : 1, want_d = chapter == PCL_ORDEAL_CAVERN ? 1 : 0;
@@ -293,6 +307,7 @@ int launch(pcl_handle* h, const StepParams& p, cudaStream_t stream) {
     case PCL_PROG_APERTURE: e = pcl::launch_aperture(p, stream); break;
     case PCL_PROG_ORDEAL: e = pcl::launch_ordeal(p, stream); break;
     case PCL_PROG_HELLO: e = pcl::launch_hello(p, stream); break;
+    case PCL_PROG_APPREHEND: e = pcl::launch_apprehend(p, stream); break;
     default: return PCL_ERR_UNSUPPORTED;
   }
   if (e != cudaSuccess) return cuda_failed(h, e, "step kernel launch");

@@ -46,6 +46,7 @@ cudaError_t launch_classics(const StepParams& p, cudaStream_t s);
 cudaError_t launch_aperture(const StepParams& p, cudaStream_t s);
 cudaError_t launch_ordeal(const StepParams& p, cudaStream_t s);
 cudaError_t launch_hello(const StepParams& p, cudaStream_t s);
+cudaError_t launch_apprehend(const StepParams& p, cudaStream_t s);
 
 struct RenderParams {
   int B, H, W, pitch, S, D;

@@ -121,7 +121,12 @@ class Engine(object):
     from pycolab_b200 import lowering
     lowered = lowering.lower(self)          # NotLoweredError if not accelerable
     rng_states = None
-    if lowered.needs_rng:
+    if lowered.needs_rng and lowered.rng_kind == 'python':
+      # apprehend.py:103 draws in the sprite's constructor, which has already run
+      # (from the global `random`, as upstream): the device takes the drawn value
+      # from the template and needs no generator for this one episode.
+      rng_states = False
+    elif lowered.needs_rng:
       # Upstream game code draws from the GLOBAL NumPy RNG
       # (extraterrestrial_marauders.py:253): hand its MT19937 state to the device
       # and write it back after every step.

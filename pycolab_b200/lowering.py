@@ -52,6 +52,8 @@ LOWERED_CLASSES = {
     ('aperture', 'ApertureDrape'): 'aperture.drape',
     ('hello_world', 'SlidingSprite'): 'hello.slider',
     ('hello_world', 'RollingDrape'): 'hello.roller',
+    ('apprehend', 'PlayerSprite'): 'apprehend.player',
+    ('apprehend', 'BallSprite'): 'apprehend.ball',
     ('ordeal', 'PlayerSprite'): 'ordeal.player',
     ('ordeal', 'DragonduckSprite'): 'ordeal.dragonduck',
     ('ordeal', 'SwordDrape'): 'ordeal.sword',
@@ -198,6 +200,8 @@ class LoweredGame(object):
     self.drapes = None          # i32 [D, 8]
     self.plot = None            # i32 [16]
     self.needs_rng = False
+    self.rng_kind = 'numpy'     # whose MT19937 stream the device continues: NumPy's legacy
+                                # RandomState ('numpy') or Python's `random` ('python')
     self.backdrop_chars = ''
     self.drape_kind = None      # per drape: 1 = Scrolly (fixture program only)
     self.dynamic_z = False      # per-env z-order array (Plot.change_z_order)
@@ -524,6 +528,41 @@ def _lower_hello(engine, roles):
   return game
 
 
+def _f64_words(x):
+  """float64 -> (lo, hi) int32 words, as the kernels' __hiloint2double reads them."""
+  lo, hi = np.array([x], dtype='<f8').view('<i4')
+  return int(lo), int(hi)
+
+
+def _lower_apprehend(engine, roles):
+  """examples/apprehend.py:56-131: the catcher 'P' and the falling ball, one group
+  [ball, catcher].  The ball's float64 slope (drawn when the Python sprite was built)
+  and accumulator travel as bit patterns; `needs_rng` lets a BATCHED engine draw a new
+  slope per episode on the device from per-env `random.Random` states."""
+  th = engine.things
+  players = [c for c, r in roles.items() if r == 'apprehend.player']
+  balls = [c for c, r in roles.items() if r == 'apprehend.ball']
+  if len(players) != 1 or len(balls) != 1 or len(roles) != 2:
+    raise NotLoweredError('apprehend program needs one PlayerSprite and one BallSprite')
+  game = LoweredGame()
+  _common(engine, game, _lib.PROG_APPREHEND)
+  pl, ball = th[players[0]], th[balls[0]]
+  if _update_order(engine) != [balls[0], players[0]] or len(game.groups) != 1:
+    raise NotLoweredError('apprehend program needs update_schedule [ball, player]')
+  if game.z_order != balls[0] + players[0]:
+    raise NotLoweredError('apprehend program draws the player over the ball')
+  lo, hi = _f64_words(ball._dx)
+  _set_sprites(game, [pl, ball], [_sprite_record(pl), _sprite_record(ball, aux0=lo, aux1=hi)])
+  alo, ahi = _f64_words(ball._x_accumulator)
+  game.drape_chars = ''
+  game.margins = []
+  game.drapes = np.zeros((0, _lib.DRAPE_WORDS), dtype=np.int32)
+  game.plot = np.array(_plot_record(aux0=alo, aux1=ahi), dtype=np.int32)
+  game.needs_rng = True
+  game.rng_kind = 'python'
+  return game
+
+
 def _update_order(engine):
   return [e.character for _, ents in sorted(engine._update_groups.items()) for e in ents]
 
@@ -694,7 +733,7 @@ def lower(engine):
               'marauders': _lower_marauders, 'fixture': _lower_fixture,
               'classics': _lower_classics, 'better': _lower_better_scrolly,
               'aperture': _lower_aperture, 'ordeal': _lower_ordeal,
-              'hello': _lower_hello}
+              'hello': _lower_hello, 'apprehend': _lower_apprehend}
   if family not in lowerers:
     raise NotLoweredError(family)
   game = lowerers[family](engine, roles)

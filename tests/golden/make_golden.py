@@ -271,6 +271,30 @@ def hellos():
          curtains=np.stack(curtains).astype(np.uint8), **traj)
 
 
+def apprehends():
+  """examples/apprehend.py: stock art; `random.seed` fixes the global stream the ball
+  sprites draw their slopes from (one draw per episode), actions 0-2 (2 = stay put)."""
+  import random
+  refdriver._import()
+  from pycolab.examples import apprehend as ref_app
+  for seed in range(3):
+    rs = np.random.RandomState(700 + seed)
+    actions = rs.randint(0, 3, size=300).tolist()
+    sprites, floats = [], []
+    rec = sprite_recorder('Pb', sprites)
+
+    def on_frame(env, out):
+      rec(env, out)
+      floats.append([env.things['b']._dx, env.things['b']._x_accumulator])
+    random.seed(700 + seed)
+    traj = tj.run_trajectory(ref_app.make_game, actions, on_frame=on_frame)
+    save('apprehend_stock_s%d' % seed, art=tj.art_to_u8(ref_app.GAME_ART),
+         actions=np.array(actions, dtype=np.int32), sprites=np.array(sprites, dtype=np.int32),
+         floats=np.array(floats, dtype=np.float64), random_seed=np.array([700 + seed]), **traj)
+    print('  apprehend_stock_s%d: %d episodes, reward sum %d' % (
+        seed, int(traj['game_over'].sum()), int(traj['reward'].sum())))
+
+
 def groups():
   for seed, margins in ((0, (2, 3)), (1, None), (2, (1, 2))):
     fixture_groups('fixture_groups_%d' % seed, seed, margins)
@@ -480,6 +504,8 @@ def main():
     return ordeals()
   if sys.argv[1:] == ['hello']:
     return hellos()
+  if sys.argv[1:] == ['apprehend']:
+    return apprehends()
   # BASELINE.json configs[0]: stock scrolly_maze, 1000 random-action steps.
   for level, T in ((0, 1000), (1, 400), (2, 400)):
     maze, board, beneath = refdriver.ref_stock_scrolly_art(level)
@@ -531,6 +557,7 @@ def main():
   groups()
   ordeals()
   hellos()
+  apprehends()
 
 
 # Same-shape (4x12) chapters for a list-style story without croppers.

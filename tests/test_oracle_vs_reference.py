@@ -324,3 +324,32 @@ def test_ordeal_story_random_walks(seed):
     np.testing.assert_array_equal(obs.board, view, err_msg='t=%d' % t)
     assert reward == my_reward and discount == my_discount, t
     assert story.game_over == mine.game_over, t
+
+
+def test_apprehend_many_episodes():
+  """examples/apprehend.py live: 200 episodes, the oracle drawing from
+  random.Random(seed) what the reference draws from the seeded global `random`;
+  boards, rewards (value and type), discounts and the float64 registers at 0 ulp."""
+  import random
+  refdriver._import()
+  from pycolab.examples import apprehend as ref_app
+  steps = wins = 0
+  for seed in range(200):
+    random.seed(seed)
+    ref = ref_app.make_game()
+    ora = games.make_apprehend(ref_app.GAME_ART, random.Random(seed))
+    r_out, o_out = ref.its_showtime(), ora.its_showtime()
+    rs = np.random.RandomState(seed)
+    while True:
+      np.testing.assert_array_equal(r_out[0].board, o_out[0])
+      assert r_out[1] == o_out[1] and type(r_out[1]) is type(o_out[1])
+      assert r_out[2] == o_out[2] and ref.game_over == ora.game_over
+      ball = ref.things['b']
+      assert (ball._dx, ball._x_accumulator) == (ora.things['b'].aux['dx'], ora.things['b'].aux['acc'])
+      if ref.game_over:
+        wins += r_out[1] == 1
+        break
+      a = int(rs.randint(0, 3))
+      r_out, o_out = ref.play(a), ora.play(a)
+      steps += 1
+  assert steps > 1500 and wins > 20

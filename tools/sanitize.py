@@ -23,7 +23,7 @@ def main():
   import torch
   from pycolab_b200 import batched, dist as pdist, levels, lowering
   from pycolab_b200.games import (aperture, better_scrolly_maze, extraterrestrial_marauders,
-                                  fixtures, fluvial_natation, hello_world, ordeal,
+                                  apprehend, fixtures, fluvial_natation, hello_world, ordeal,
                                   scrolly_maze, warehouse_manager)
   from pycolab_b200.games.classics import chain_walk, cliff_walk, four_rooms
   rs = np.random.RandomState(0)
@@ -79,6 +79,7 @@ def main():
     g.the_plot.this_chapter = mk.__name__[5:]
     run('ordeal_step ' + mk.__name__[5:], [g], 5, 5)
   run('hello_step', [hello_world.make_game()], 5, 6)
+  run('apprehend_step (device RNG)', [apprehend.make_game()], 5, 3, steps=30)
   pattern = rs.random_sample((17, 23)) < 0.2
   fx = fixtures.make_game(['           ', '   P       ', '      q    ', '           ',
                            '           ', '           '], ' ',
