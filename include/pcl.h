@@ -81,6 +81,10 @@ typedef enum pcl_program {
                                 AUX0 / AUX1 its x accumulator; with pcl_state.d_rng bound (the words of
                                 Python's random.Random(seed).getstate()) the slope is drawn on the device at
                                 every (re)start as random.uniform does, else taken from the reset template */
+  PCL_PROG_SHOCKWAVE = 11,   /* examples/shockwave.py:91-197: sprite 'P', drapes '@' (curtain bit-packed in
+                                d_bits[0], record AUX0 = impact cell index, AUX1 = steps since impact), ' '
+                                and '^' (static, d_bits_init[1..2]); program_arg[0] = ring width; d_rng =
+                                NumPy RandomState words (np.random.randint picks the impact cell) */
   PCL_PROG_ORDEAL = 8        /* examples/ordeal.py:74-266: program_arg[0] = PCL_ORDEAL_* chapter;
                                 plot words AUX0 has_sword, AUX1 last_position (row << 16 | col,
                                 -1 unset), AUX2 next_chapter chosen on the device, AUX3 prior chapter */

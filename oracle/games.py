@@ -777,3 +777,57 @@ def apprehend_program(world, ch, actions):
     if ent.virtual_position[0] >= board.shape[0]:
       plot.add_reward(-1)
       plot.terminate_episode()
+
+
+# ==========================================================================
+# shockwave: a walker climbing to the safe top row while rings of
+# fire expand from random impact points; `layers[...]` look-ups see the STALE board.
+# ==========================================================================
+
+def make_shockwave(art, rng, width=2):
+  """examples/shockwave.py:181-197.  `rng` is the np.random.RandomState standing
+  for NumPy's global generator (np.random.randint, :133)."""
+  backdrop, masks = split_art(art, ['P', '@', ' ', '^'], '+')
+  shape = backdrop.shape
+  player = em.Walker('P', shape, mask_position(masks['P']), impassable='=',
+                     confined=True)                                   # :94-96
+  wave = em.PlainDrape('@', masks['@'])
+  wave.aux.update(width=width, distance=np.zeros(shape), steps=0)     # :122-124
+  things = {'P': player, '@': wave, ' ': em.PlainDrape(' ', masks[' ']),
+            '^': em.PlainDrape('^', masks['^'])}
+  world = em.World(shape[0], shape[1], backdrop, things, z_order=[' ', '^', '@', 'P'],
+                   groups=[[' ', '^', 'P', '@']], program=shockwave_program)
+  world.rng = rng
+  return world
+
+
+def shockwave_program(world, ch, actions):
+  plot, ent, board = world.plot, world.things[ch], world.board
+  if ch == 'P':                                   # PlayerSprite.update :98-109
+    motion = {0: em.M_N, 1: em.M_W, 2: em.M_E, 3: em.M_STAY}.get(actions) \
+        if actions is not None else None
+    if motion is not None:
+      em.walker_move(ent, board, plot, motion)
+  elif ch == '@':                                 # ShockwaveDrape.update :126-165
+    aux = ent.aux
+    if not ent.curtain.any():
+      k = int(world.rng.randint(0, ent.curtain.size))                 # :133
+      ir, ic = divmod(k, world.cols)                                  # np.unravel_index
+      rr, cc = np.mgrid[0:world.rows, 0:world.cols]
+      # ndimage.distance_transform_edt of "everything but the impact point":
+      # the Euclidean distance to that point, float64
+      aux['distance'] = np.sqrt(((rr - ir) ** 2 + (cc - ic) ** 2).astype(np.float64))
+      aux['steps'] = 0
+    stale = world.layers                          # engine.py:725: layers of the last render
+    ent.curtain[:] = ((aux['distance'] > aux['steps']) &
+                      (aux['distance'] <= aux['steps'] + aux['width']) &
+                      np.logical_not(stale['=']))
+    pos = world.things['P'].position
+    if stale['^'][pos]:
+      plot.add_reward(1)
+      plot.terminate_episode()
+    if ent.curtain[pos] and world.things[' '].curtain[pos]:
+      plot.add_reward(-1)
+      plot.terminate_episode()
+    aux['steps'] += 1
+  # MinimalDrape.update (' ' and '^') does nothing :168-172

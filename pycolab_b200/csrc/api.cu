@@ -224,6 +224,20 @@ int validate(const pcl_spec& s) {
       if (s.rows < 2) return PCL_ERR_INVALID;          // the slope divides by rows - 1
       return PCL_OK;
     }
+    case PCL_PROG_SHOCKWAVE: {
+      if (s.n_sprites != 1 || s.n_drapes != 3) return PCL_ERR_UNSUPPORTED;
+      // one update group [' ', '^', P, '@'] (the two static drapes may come in either
+      // order), z-order ' ' '^' '@' P
+      if (s.n_groups != 1 || s.group_len[0] != 4 || s.group_chars[2] != s.sprite_char[0] ||
+          s.group_chars[3] != s.drape_char[0]) return PCL_ERR_UNSUPPORTED;
+      if (s.z_order[0] != s.drape_char[1] || s.z_order[1] != s.drape_char[2] ||
+          s.z_order[2] != s.drape_char[0] || s.z_order[3] != s.sprite_char[0]) return PCL_ERR_UNSUPPORTED;
+      if (!s.sprite_confined[0] || s.sprite_egocentric[0]) return PCL_ERR_UNSUPPORTED;
+      if (s.rows > 32 || s.cols > 64) return PCL_ERR_UNSUPPORTED;      // a curtain row per lane, 64-bit rows
+      if (s.bits_words < (s.cols + 31) / 32 + 1) return PCL_ERR_INVALID;
+      if (s.program_arg[0] < 0 || s.program_arg[0] > 1024) return PCL_ERR_INVALID;
+      return PCL_OK;
+    }
     case PCL_PROG_ORDEAL: {
       const int chapter = s.program_arg[0];
       const int want_s = chapter == PCL_ORDEAL_CASTLE ? 2 : 1, want_d = chapter == PCL_ORDEAL_CAVERN ? 1 : 0;
@@ -308,6 +322,7 @@ int launch(pcl_handle* h, const StepParams& p, cudaStream_t stream) {
     case PCL_PROG_ORDEAL: e = pcl::launch_ordeal(p, stream); break;
     case PCL_PROG_HELLO: e = pcl::launch_hello(p, stream); break;
     case PCL_PROG_APPREHEND: e = pcl::launch_apprehend(p, stream); break;
+    case PCL_PROG_SHOCKWAVE: e = pcl::launch_shockwave(p, stream); break;
     default: return PCL_ERR_UNSUPPORTED;
   }
   if (e != cudaSuccess) return cuda_failed(h, e, "step kernel launch");
@@ -410,6 +425,10 @@ int pcl_bind_state(pcl_handle* h, const pcl_state* st) {
     if (!st->d_rng) return PCL_ERR_INVALID;
   }
   if (h->spec.program == PCL_PROG_HELLO && !st->d_bits_init[0]) return PCL_ERR_INVALID;
+  if (h->spec.program == PCL_PROG_SHOCKWAVE) {
+    if (!st->d_bits[0] || st->bits_bstride[0] == 0 || !st->d_rng) return PCL_ERR_INVALID;
+    for (int d = 0; d < 3; ++d) if (!st->d_bits_init[d]) return PCL_ERR_INVALID;
+  }
   if (h->spec.program == PCL_PROG_ORDEAL) {
     if (h->spec.n_drapes && (!st->d_bits[0] || !st->d_bits_init[0] || st->bits_bstride[0] == 0))
       return PCL_ERR_INVALID;
@@ -626,6 +645,7 @@ int pcl_export_curtain(pcl_handle* h, int drape_index, uint8_t* d_out, void* str
     else p.level = h->st.d_level;            // the wall pattern is read-only: per level
   } else if (h->spec.program == PCL_PROG_MARAUDERS ||
              h->spec.program == PCL_PROG_BETTER_SCROLLY || h->spec.program == PCL_PROG_ORDEAL ||
+             h->spec.program == PCL_PROG_SHOCKWAVE ||
              (h->spec.program == PCL_PROG_FIXTURE && !h->spec.drape_kind[drape_index])) {
     p.scrolly = 0;
     p.bits = h->st.d_bits[drape_index];
@@ -666,7 +686,8 @@ int pcl_layers(pcl_handle* h, const uint8_t* chars, int32_t n_chars, uint8_t* d_
       p.stale_slot[d] = coins;
       p.per_level[d] = !coins && h->st.d_level != nullptr;   // read-only patterns: per level
     } else if (sp.program == PCL_PROG_MARAUDERS || sp.program == PCL_PROG_BETTER_SCROLLY ||
-               sp.program == PCL_PROG_FIXTURE || sp.program == PCL_PROG_ORDEAL) {
+               sp.program == PCL_PROG_FIXTURE || sp.program == PCL_PROG_ORDEAL ||
+               sp.program == PCL_PROG_SHOCKWAVE) {
       p.bits[d] = h->st.d_bits[d]; p.bits_bstride[d] = h->st.bits_bstride[d];
       p.row_words[d] = sp.bits_words;
     } else {

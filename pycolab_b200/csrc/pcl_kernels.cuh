@@ -47,6 +47,7 @@ cudaError_t launch_aperture(const StepParams& p, cudaStream_t s);
 cudaError_t launch_ordeal(const StepParams& p, cudaStream_t s);
 cudaError_t launch_hello(const StepParams& p, cudaStream_t s);
 cudaError_t launch_apprehend(const StepParams& p, cudaStream_t s);
+cudaError_t launch_shockwave(const StepParams& p, cudaStream_t s);
 
 struct RenderParams {
   int B, H, W, pitch, S, D;

@@ -192,3 +192,26 @@ def aperture_level():
           '#      ..  C  #',
           '###@###..##@###',
           '###############']
+
+
+def shockwave_level(seed, height=12, width=15, safety_density=0.15):
+  """A shockwave level in the vocabulary of examples/shockwave.py:40-88: a '^' safe row
+  on top, ' ' exposed cells, '+' bunkers, '=' wall runs on non-adjacent interior rows
+  (never the bottom row, always leaving gaps), one 'P' on the bottom row.  Same
+  ingredients as the reference's `random_level`, drawn from a private
+  RandomState(seed) (that function itself no longer runs: it uses `np.bool`)."""
+  rs = np.random.RandomState(seed)
+  level = np.full((height, width), ord(' '), dtype=np.uint8)
+  level[rs.random_sample(level.shape) < safety_density] = ord('+')
+  rows = set(range(1, height - 1))
+  while rows:
+    row = int(rs.choice(sorted(rows)))
+    n_walls = int(rs.randint(2, max(3, width - 3)))
+    mask = np.zeros((width,), dtype=bool)
+    mask[:n_walls] = True
+    rs.shuffle(mask)
+    level[row, mask] = ord('=')
+    rows -= {row - 1, row, row + 1}
+  level[-1, int(rs.randint(0, width - 1))] = ord('P')
+  level[0] = ord('^')
+  return _to_art(level)

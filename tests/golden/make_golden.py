@@ -295,6 +295,56 @@ def apprehends():
         seed, int(traj['game_over'].sum()), int(traj['reward'].sum())))
 
 
+def shockwaves():
+  """examples/shockwave.py: the stock level and two generated ones (12x15, 20x40);
+  `np.random.seed` fixes the global stream the impact points come from; actions 0-4
+  (4 = none of the keys), biased upwards so that some episodes are won."""
+  refdriver._import()
+  from pycolab.examples import shockwave as ref_shock
+  from pycolab_b200 import levels
+  cases = [('stock', ref_shock.LEVELS[0]), ('g12x15', levels.shockwave_level(1, safety_density=0.5)),
+           ('g20x40', levels.shockwave_level(2, 20, 40, 0.6))]
+  for seed, (tag, art) in enumerate(cases):
+    ref_shock.LEVELS.append(art)
+    make = lambda: ref_shock.make_game(len(ref_shock.LEVELS) - 1)
+    try:
+      # pass 1: a climbing policy that looks at the reference env (up when the cell
+      # above is free, else sideways; sometimes waits) chooses the actions ...
+      rs = np.random.RandomState(800 + seed)
+      np.random.seed(800 + seed)
+      actions, env = [], make()
+      env.its_showtime()
+      for _ in range(500):
+        if env.game_over:
+          env = make()
+          env.its_showtime()
+          actions.append(int(rs.randint(0, 5)))        # ignored by the protocol
+          continue
+        r, c = env.things['P'].position
+        up_free = r > 0 and art[r - 1][c] != '='
+        a = int(rs.choice([0, 1, 2, 3, 4], p=[.7, .08, .08, .1, .04] if up_free
+                          else [.05, .4, .4, .1, .05]))
+        actions.append(a)
+        env.play(a)
+      # ... pass 2 replays them through the shared trajectory protocol
+      sprites, curtains = [], []
+      rec = sprite_recorder('P', sprites)
+
+      def on_frame(env, out):
+        rec(env, out)
+        curtains.append(env.things['@'].curtain.copy())
+      np.random.seed(800 + seed)
+      traj = tj.run_trajectory(make, actions, on_frame=on_frame)
+    finally:
+      ref_shock.LEVELS.pop()
+    save('shockwave_%s' % tag, art=tj.art_to_u8(art), actions=np.array(actions, dtype=np.int32),
+         sprites=np.array(sprites, dtype=np.int32), curtains=np.stack(curtains).astype(np.uint8),
+         numpy_seed=np.array([800 + seed]), **traj)
+    print('  shockwave_%s: %d episodes, wins %d, deaths %d' % (
+        tag, int(traj['game_over'].sum()), int((traj['reward'] == 1).sum()),
+        int((traj['reward'] == -1).sum())))
+
+
 def groups():
   for seed, margins in ((0, (2, 3)), (1, None), (2, (1, 2))):
     fixture_groups('fixture_groups_%d' % seed, seed, margins)
@@ -506,6 +556,8 @@ def main():
     return hellos()
   if sys.argv[1:] == ['apprehend']:
     return apprehends()
+  if sys.argv[1:] == ['shockwave']:
+    return shockwaves()
   # BASELINE.json configs[0]: stock scrolly_maze, 1000 random-action steps.
   for level, T in ((0, 1000), (1, 400), (2, 400)):
     maze, board, beneath = refdriver.ref_stock_scrolly_art(level)
@@ -558,6 +610,7 @@ def main():
   ordeals()
   hellos()
   apprehends()
+  shockwaves()
 
 
 # Same-shape (4x12) chapters for a list-style story without croppers.

@@ -353,3 +353,36 @@ def test_apprehend_many_episodes():
       r_out, o_out = ref.play(a), ora.play(a)
       steps += 1
   assert steps > 1500 and wins > 20
+
+
+@pytest.mark.parametrize('level', ['stock', 'generated'])
+def test_shockwave_many_episodes(level):
+  """examples/shockwave.py live (scipy's distance transform, NumPy's global randint):
+  boards, rewards, discounts and the wave's curtain every step."""
+  refdriver._import()
+  from pycolab.examples import shockwave as ref_shock
+  from pycolab_b200 import levels
+  art = ref_shock.LEVELS[0] if level == 'stock' else levels.shockwave_level(7, 14, 31, 0.5)
+  ref_shock.LEVELS.append(art)
+  steps = ends = 0
+  try:
+    for seed in range(80):
+      np.random.seed(seed)
+      ref = ref_shock.make_game(len(ref_shock.LEVELS) - 1)
+      ora = games.make_shockwave(art, np.random.RandomState(seed))
+      r_out, o_out = ref.its_showtime(), ora.its_showtime()
+      rs = np.random.RandomState(100 + seed)
+      for _ in range(300):
+        np.testing.assert_array_equal(r_out[0].board, o_out[0])
+        np.testing.assert_array_equal(ref.things['@'].curtain, ora.things['@'].curtain)
+        assert r_out[1] == o_out[1] and type(r_out[1]) is type(o_out[1])
+        assert r_out[2] == o_out[2] and ref.game_over == ora.game_over
+        if ref.game_over:
+          ends += 1
+          break
+        a = int(rs.choice([0, 1, 2, 3, 4], p=[.55, .15, .15, .1, .05]))
+        r_out, o_out = ref.play(a), ora.play(a)
+        steps += 1
+  finally:
+    ref_shock.LEVELS.pop()
+  assert steps > 400 and ends > 60
