@@ -635,7 +635,7 @@ def other_config(name, torch, dist, dev, rank, world, barrier, peak, K):
     arts = [levels.scrolly_maze_level(1000 + i) for i in range(N_LEVELS)]
     games = [lowering.lower(g.make_game(*a)) for a in arts]
     B, R, n_act = 8192, 3, 5
-    a_step, kernel = A_STEP_BYTES + 81, 'scrolly_maze_step + crop_kernel'
+    a_step, kernel = A_STEP_BYTES + 81, 'scrolly_maze_step with the cropper as its epilogue'
     what = ('scrolly_maze 64x64 + ScrollingCropper 9x9 egocentric, 8192 envs per GPU '
             '(configs[4] = 65536 over 8 GPUs)')
     crop_spec = batched.scrolling_crop_spec(9, 9, 0, pad_char=' ', scroll_margins=(None, None))
@@ -656,16 +656,22 @@ def other_config(name, torch, dist, dev, rank, world, barrier, peak, K):
   crops = [torch.empty((B, 9, 9), dtype=torch.uint8, device=dev) for _ in engines] \
       if crop_spec is not None else None
 
+  fused_crop = False
+  if crop_spec is not None and os.environ.get('PCL_BENCH_SEPARATE_CROP') != '1':
+    for r, e in enumerate(engines):            # the cropper as the step kernel's epilogue
+      e.attach_cropper(crop_spec, state=states[r], out=crops[r])
+    fused_crop = all(e._attached[3] for e in engines)
+
   def step(t):
     e = engines[t % R]
     e.play(acts[t])
-    if crop_spec is not None:
+    if crop_spec is not None and e._attached is None:
       e.crop(crop_spec, state=states[t % R], out=crops[t % R])
 
   l0 = sum(e.launch_count() for e in engines)
   timed = Timed(torch, dev, step, W, K)
   per_step_launches = (sum(e.launch_count() for e in engines) - l0) / float(W + K) \
-      if timed.graphs else (2 if crop_spec is not None else 1)
+      if timed.graphs else (2 if crop_spec is not None and not fused_crop else 1)
   ramp_clocks(torch, dev, timed, 0.15)
   for e, r0 in zip(engines, rng0):
     if r0 is not None:
@@ -687,6 +693,13 @@ def other_config(name, torch, dist, dev, rank, world, barrier, peak, K):
       n += sampled_check.final_state_check(eng, lambda e: make(base + r * B + e), ids, streams,
                                            sprite_chars or '')
     parity = {'envs': 2 * len(ids), 'env_steps': n, 'vs': 'oracle replay, final state identical'}
+  crop_checked = None
+  if crop_spec is not None and fused_crop:
+    # the epilogue's views against the stand-alone crop kernel on the same boards (a
+    # perfectly egocentric window depends on the current position only: fresh state)
+    crop_checked = all(bool((crops[r] == e.crop(crop_spec, state=e.new_crop_state())).all())
+                       for r, e in enumerate(engines))
+    assert crop_checked, 'attached cropper != crop_kernel'
   # end to end
   n_e2e = max(2 * R, min(K, 60))
   secs, _ = e2e_pipelined(torch, dev, engines, acts_np, n_e2e, barrier, crop_spec, states)
@@ -706,6 +719,10 @@ def other_config(name, torch, dist, dev, rank, world, barrier, peak, K):
                       'note': 'SURVEY 8d reference-layout bytes; static level data is shared '
                               'per level here, so frac may exceed what DRAM actually moves'},
          'parity_checked': parity, 'env_errors': errors}
+  if crop_spec is not None:
+    out['cropper'] = ('epilogue of the step kernel (pcl_attach_cropper)' if fused_crop
+                      else 'separate crop_kernel launch')
+    out['crop_checked'] = crop_checked
   for e in engines:
     e.close()
   del engines

@@ -340,6 +340,18 @@ typedef struct pcl_crop_spec {
 int pcl_crop(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d_board,
              uint8_t* d_crop, int32_t* d_crop_state, void* stream);
 
+/* Attach ONE cropper to the handle: every later pcl_reset / pcl_step / pcl_run then also
+ * writes the cropper's view of the new board into d_crop (u8 [B, rows, cols]) from INSIDE
+ * the step kernel — what pcl_crop would produce if called right after the step, without
+ * the second launch.  d_crop_state as for pcl_crop (NULL = the plot record's slot).
+ * crop == NULL detaches.  Step programs without the epilogue (today every program but
+ * PCL_PROG_SCROLLY_MAZE) and tracking lists that name drapes return PCL_ERR_UNSUPPORTED:
+ * call pcl_crop after the step instead.  The buffers must outlive the attachment;
+ * pcl_bind_state detaches.  pcl_step_host_async given the SAME spec, d_crop and
+ * d_crop_state does not launch the cropper a second time. */
+int pcl_attach_cropper(pcl_handle* h, const pcl_crop_spec* crop, uint8_t* d_crop,
+                       int32_t* d_crop_state);
+
 /* pcl_crop for a ScrollingCropper whose `to_track` names several entities
  * (cropping.py:544-598): the window follows the FIRST entry of crop->track that is
  * visible — a sprite that is visible, or a drape whose curtain has any cell, in

@@ -186,6 +186,7 @@ class BatchedEngine(object):
     self._slot_shape = {}
     self._crop_dev = None
     self._crop_out = None
+    self._attached = None       # attach_cropper: (spec, state, out, runs inside the step kernel)
 
     self._spec = g0.make_spec(self.auto_reset)
     handle = C.c_void_p()
@@ -215,6 +216,7 @@ class BatchedEngine(object):
     self._showtime = True
     _lib.check(self._lib.pcl_reset(self._h, None, C.byref(self._out), self._stream()),
                'pcl_reset', self._h)
+    self._after_step()
     return self._result()
 
   def reset(self, env_mask=None):
@@ -226,6 +228,7 @@ class BatchedEngine(object):
       mask = env_mask.to(device=self.device, dtype=_torch().uint8).contiguous()
     _lib.check(self._lib.pcl_reset(self._h, None if mask is None else mask.data_ptr(),
                                    C.byref(self._out), self._stream()), 'pcl_reset', self._h)
+    self._after_step()
     return self._result()
 
   def play(self, actions):
@@ -246,6 +249,7 @@ class BatchedEngine(object):
           self.batch * self.actions_per_env, actions.numel()))
     _lib.check(self._lib.pcl_step(self._h, actions.data_ptr(), C.byref(self._out),
                                   self._stream()), 'pcl_step', self._h)
+    self._after_step()
     return self._result()
 
   def run(self, actions):
@@ -298,7 +302,12 @@ class BatchedEngine(object):
       shape = (self.batch, self.rows, self.pitch)
     else:
       shape = (self.batch, crop_spec.rows, crop_spec.cols)
-      if self._crop_dev is None or tuple(self._crop_dev.shape) != shape:
+      att = getattr(self, '_attached', None)
+      if (att is not None and att[3] and bytes(att[0]) == bytes(crop_spec) and
+          (crop_state is None or crop_state.data_ptr() == att[1].data_ptr())):
+        # this very cropper runs inside the step kernel: ship its view, launch nothing more
+        self._crop_dev, crop_state = att[2], att[1]
+      elif self._crop_dev is None or tuple(self._crop_dev.shape) != shape:
         self._crop_dev = _torch().empty(shape, dtype=_torch().uint8, device=self.device)
     h, n = self._host_buffers(slot, shape)
     n['actions'][:] = np.asarray(actions, dtype=np.int32).reshape(-1)
@@ -398,6 +407,36 @@ class BatchedEngine(object):
     """Corner state of one cropper object: i32 [B, 4] (row, col, initialised,
     episode), zero = not yet initialised.  One per ScrollingCropper."""
     return _torch().zeros((self.batch, 4), dtype=_torch().int32, device=self.device)
+
+  def attach_cropper(self, crop_spec, state=None, out=None):
+    """Make every later its_showtime() / play() / run() also produce this cropper's view
+    of the new boards — from inside the step kernel where the game program supports it
+    (`pcl_attach_cropper`: no second launch), else by a crop launch after each step.
+    Returns the u8 [B, rows, cols] tensor that always holds the latest views.
+    `crop_spec=None` detaches."""
+    torch = _torch()
+    if crop_spec is None:
+      _lib.check(self._lib.pcl_attach_cropper(self._h, None, None, None), 'pcl_attach_cropper')
+      self._attached = None
+      return None
+    if out is None:
+      out = torch.zeros((self.batch, crop_spec.rows, crop_spec.cols), dtype=torch.uint8,
+                        device=self.device)
+    if state is None:
+      state = self.new_crop_state()
+    status = self._lib.pcl_attach_cropper(self._h, C.byref(crop_spec), out.data_ptr(),
+                                          state.data_ptr())
+    if status == _lib.ERR_UNSUPPORTED:          # no epilogue in this program: crop after the step
+      self._attached = (crop_spec, state, out, False)
+    else:
+      _lib.check(status, 'pcl_attach_cropper', self._h)
+      self._attached = (crop_spec, state, out, True)
+    return out
+
+  def _after_step(self):
+    att = getattr(self, '_attached', None)
+    if att is not None and not att[3]:
+      self.crop(att[0], state=att[1], out=att[2])
 
   def crop(self, crop_spec, state=None, out=None):
     """ScrollingCropper / FixedCropper .crop over the last boards: u8 [B, rows,

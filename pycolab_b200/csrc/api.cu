@@ -589,7 +589,12 @@ int pcl_step_host_async(pcl_handle* h, const int32_t* h_actions, int32_t* d_acti
   const uint8_t* d_view = out->d_board;
   size_t view_bytes = (size_t)h->batch * h->spec.rows * h->spec.pitch;
   if (crop) {                    // only the cropped view crosses PCIe
-    e = pcl_crop(h, crop, out->d_board, d_crop, d_crop_state, stream);
+    // The same cropper attached to the handle (pcl_attach_cropper) has already run as
+    // the step kernel's epilogue: nothing more to launch.
+    const bool fused = h->base.has_cropper && h->base.cropper.out == d_crop &&
+                       h->base.cropper.state == d_crop_state &&
+                       memcmp(&h->base.cropper.crop, crop, sizeof(*crop)) == 0;
+    e = fused ? PCL_OK : pcl_crop(h, crop, out->d_board, d_crop, d_crop_state, stream);
     if (e != PCL_OK) return e;
     d_view = d_crop;
     view_bytes = (size_t)h->batch * crop->rows * crop->cols;
@@ -702,6 +707,47 @@ int pcl_layers(pcl_handle* h, const uint8_t* chars, int32_t n_chars, uint8_t* d_
     for (int d = 0; d < sp.n_drapes; ++d) if (sp.drape_char[d] == chars[k]) p.drape_of[k] = (int8_t)d;
   }
   return launched(h, pcl::launch_layers(p, (cudaStream_t)stream), "launch_layers");
+}
+
+namespace {
+// cropping.py:362-391: what a ScrollingCropper / FixedCropper accepts.
+int crop_spec_ok(const pcl_handle* h, const pcl_crop_spec* crop) {
+  if (crop->rows <= 0 || crop->cols <= 0) return PCL_ERR_INVALID;
+  if (crop->track[0] == 0 && crop->sprite_index >= h->spec.n_sprites) return PCL_ERR_INVALID;
+  if (crop->sprite_index >= 0 &&
+      (2 * crop->margin_rows >= crop->rows || 2 * crop->margin_cols >= crop->cols))
+    return PCL_ERR_INVALID;                                  // cropping.py:374-380
+  if (crop->pad_char < 0 && (crop->rows > h->spec.rows || crop->cols > h->spec.cols))
+    return PCL_ERR_INVALID;                                  // cropping.py:384-391
+  return PCL_OK;
+}
+}  // namespace
+
+int pcl_attach_cropper(pcl_handle* h, const pcl_crop_spec* crop, uint8_t* d_crop,
+                       int32_t* d_crop_state) {
+  if (!h) return PCL_ERR_INVALID;
+  if (!h->bound) return PCL_ERR_UNBOUND;
+  if (!crop) {                                               // detach
+    h->base.has_cropper = 0;
+    return PCL_OK;
+  }
+  if (!d_crop) return PCL_ERR_INVALID;
+  if (h->spec.program != PCL_PROG_SCROLLY_MAZE) return PCL_ERR_UNSUPPORTED;
+  const int ok = crop_spec_ok(h, crop);
+  if (ok != PCL_OK) return ok;
+  if ((int64_t)crop->rows * crop->cols >= 65536) return PCL_ERR_UNSUPPORTED;
+  for (int i = 0; i < PCL_MAX_TRACK; ++i) {
+    if (crop->track[i] < 0) return PCL_ERR_UNSUPPORTED;      // drape medians need scratch memory
+    if (crop->track[i] > h->spec.n_sprites) return PCL_ERR_INVALID;
+  }
+  pcl::CropParams& c = h->base.cropper;
+  memset(&c, 0, sizeof(c));
+  c.B = h->batch; c.H = h->spec.rows; c.W = h->spec.cols; c.pitch = h->spec.pitch;
+  c.S = h->spec.n_sprites; c.crop = *crop;
+  c.sprites = h->st.d_sprites; c.plot = h->st.d_plot; c.out = d_crop; c.state = d_crop_state;
+  c.cols_recip = crop->cols > 1 ? (uint32_t)(0x100000000ull / (uint32_t)crop->cols) + 1u : 0u;
+  h->base.has_cropper = 1;
+  return PCL_OK;
 }
 
 int pcl_crop(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d_board, uint8_t* d_crop,

@@ -8,6 +8,18 @@
 
 namespace pcl {
 
+struct CropParams {
+  int B, H, W, pitch, S;
+  pcl_crop_spec crop;
+  const int32_t* sprites;
+  int32_t* plot;
+  int32_t* state;                // i32 [B, 4] per-cropper corner state, or NULL
+  const uint8_t* board;
+  uint8_t* out;
+  const uint8_t* curtains[PCL_MAX_TRACK];   // byte curtains of tracked drapes (or NULL)
+  uint32_t cols_recip;           // floor(2^32 / crop.cols) + 1, set by the launcher
+};
+
 // Everything a fused step kernel needs, by value (fits the 4 KB param space).
 struct StepParams {
   int B, H, W, pitch;
@@ -35,6 +47,8 @@ struct StepParams {
   pcl_outputs out;
   const int32_t* actions;        // i32 [B, actions_per_env] (MODE_STEP)
   const uint8_t* env_mask;       // u8 [B] or NULL (MODE_RESET)
+  int has_cropper;               // pcl_attach_cropper: crop the new board as the kernel's epilogue
+  CropParams cropper;            // (board is taken from `out` at launch time)
 };
 
 cudaError_t launch_scrolly_maze(const StepParams& p, cudaStream_t s);
@@ -104,17 +118,6 @@ struct ObserveParams {
 };
 cudaError_t launch_observe(const ObserveParams& p, cudaStream_t s);
 
-struct CropParams {
-  int B, H, W, pitch, S;
-  pcl_crop_spec crop;
-  const int32_t* sprites;
-  int32_t* plot;
-  int32_t* state;                // i32 [B, 4] per-cropper corner state, or NULL
-  const uint8_t* board;
-  uint8_t* out;
-  const uint8_t* curtains[PCL_MAX_TRACK];   // byte curtains of tracked drapes (or NULL)
-  uint32_t cols_recip;           // floor(2^32 / crop.cols) + 1, set by the launcher
-};
 cudaError_t launch_crop(const CropParams& p, cudaStream_t s);
 
 // Exchange state of the fused crop + hand-off kernel (pcl_crop_handoff).

@@ -47,6 +47,7 @@
 // coins left in the pattern.
 #include "pcl_device.cuh"
 #include "pcl_kernels.cuh"
+#include "pcl_crop.cuh"
 
 namespace pcl {
 
@@ -226,6 +227,10 @@ scrolly_maze_step(const StepParams p) {
   // Everything above ran without touching state earlier kernels may have
   // produced (g_sel is a constant); from here on the kernel reads such state.
   pdl_wait_prior_grids();
+  // An attached cropper reads its corner state at the very end: start that line's trip
+  // from DRAM now (a hint, no register held).
+  if (p.has_cropper && p.cropper.state && live && lane == 0)
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p.cropper.state + (int64_t)env * 4));
   if (!live) {                 // ragged last block: only the selector copy to drain
     cp_async_wait_all();
     return;
@@ -632,6 +637,13 @@ scrolly_maze_step(const StepParams p) {
       else px.w = (px.w & p_keep) | p_char;
     }
     dst[seg] = px;
+  }
+  // ---- 6. an attached cropper (pcl_attach_cropper): the egocentric view of the board
+  // this warp has just stored, without a second kernel (ScrollingCropper.crop,
+  // cropping.py:393-426).
+  if (p.has_cropper) {
+    __syncwarp();
+    crop_epilogue(p.cropper, p.out.d_board, env, lane, rec, rec + 48);
   }
 }
 

@@ -273,6 +273,80 @@ def test_batched_crop_vs_oracle():
         outs[e] = worlds[e].play(int(actions[t, e]))
 
 
+@pytest.mark.parametrize('pad,margins,rows,cols', [(' ', (None, None), 9, 9), (None, (2, 3), 11, 13),
+                                                   ('.', (1, 1), 5, 7)])
+def test_attached_cropper_vs_oracle(pad, margins, rows, cols):
+  """pcl_attach_cropper: the cropper as the step kernel's epilogue (no crop launch)
+  against the oracle's ScrollingCropper, through auto-resets, and bit-identical to the
+  stand-alone crop kernel run on the same boards with its own corner state."""
+  from pycolab_b200 import batched, levels
+  from pycolab_b200.games import scrolly_maze
+  art = levels.scrolly_maze_level(32, world_shape=(65, 65), board_shape=(32, 32))
+  B, T = 19, 120
+  eng = batched.BatchedEngine([scrolly_maze.make_game(*art)], batch=B)
+  spec = batched.scrolling_crop_spec(rows, cols, 0, pad_char=pad, scroll_margins=margins)
+  view = eng.attach_cropper(spec)
+  assert eng._attached[3], 'the scrolly program runs the cropper inside the step kernel'
+  twin_state = eng.new_crop_state()
+  worlds = [ogames.make_scrolly_maze(art[0], art[1], '+', art[2]) for _ in range(B)]
+  crops = [em.ScrollingCrop(rows, cols, ['P'], pad_char=pad, scroll_margins=margins)
+           for _ in range(B)]
+  outs = []
+  for w, c in zip(worlds, crops):
+    c.set_engine(w)
+    outs.append(w.its_showtime())
+  l0 = eng.launch_count()
+  eng.its_showtime()
+  rs = np.random.RandomState(6)
+  actions = rs.randint(0, 5, size=(T, B)).astype(np.int32)
+  torch = _torch()
+  for t in range(T + 1):
+    assert eng.launch_count() == l0 + t + 1                    # one launch per step, crop included
+    got = view.cpu().numpy()
+    l1 = eng.launch_count()
+    twin = eng.crop(spec, state=twin_state).cpu().numpy()      # the stand-alone kernel
+    l0 += eng.launch_count() - l1
+    np.testing.assert_array_equal(got, twin)
+    for e in range(B):
+      np.testing.assert_array_equal(got[e], crops[e].crop(outs[e][0]),
+                                    err_msg='t=%d env=%d' % (t, e))
+    if t == T:
+      break
+    eng.play(torch.from_numpy(actions[t]).cuda())
+    for e in range(B):
+      if worlds[e].game_over:
+        worlds[e] = ogames.make_scrolly_maze(art[0], art[1], '+', art[2])
+        crops[e].set_engine(worlds[e])
+        outs[e] = worlds[e].its_showtime()
+      else:
+        outs[e] = worlds[e].play(int(actions[t, e]))
+  eng.attach_cropper(None)
+  before = view.clone()
+  eng.play(torch.from_numpy(actions[0]).cuda())
+  assert bool((view == before).all())                          # detached: untouched
+
+
+def test_attached_cropper_falls_back_to_a_crop_launch():
+  """A program without the epilogue keeps the same Python contract: the attached view
+  is refreshed by a crop launch after every step."""
+  from pycolab_b200 import batched, levels
+  from pycolab_b200.games import warehouse_manager
+  art = levels.warehouse_level(3, shape=(20, 24))
+  B = 6
+  eng = batched.BatchedEngine([warehouse_manager.make_game(art)], batch=B)
+  spec = batched.scrolling_crop_spec(7, 7, len(eng.sprite_chars) - 1, pad_char=' ',
+                                     scroll_margins=(None, None))
+  view = eng.attach_cropper(spec)
+  assert not eng._attached[3]
+  eng.its_showtime()
+  torch = _torch()
+  state = eng.new_crop_state()
+  rs = np.random.RandomState(1)
+  for t in range(20):
+    np.testing.assert_array_equal(view.cpu().numpy(), eng.crop(spec, state=state).cpu().numpy())
+    eng.play(torch.from_numpy(rs.randint(0, 4, size=B).astype(np.int32)).cuda())
+
+
 # ------------------------------------------------------- stand-alone render
 
 @pytest.mark.parametrize('shape,S,D', [((10, 30), 4, 2), ((64, 64), 4, 2),
