@@ -1030,9 +1030,12 @@ def handoff_bench(torch, dist, dev, rank, world, engines, actions, W, K, barrier
   spec = batched.scrolling_crop_spec(9, 9, 0, pad_char=' ', scroll_margins=(None, None))
   fused_err = None
   try:
-    handoffs = [pdist.FusedHandoff(e, spec, world * B) for e in engines]
-    transport = ('one kernel per step: crop + pack + %s into symmetric memory + in-kernel flag '
-                 'barrier' % handoffs[0].transport)
+    one_kernel = os.environ.get('PCL_BENCH_HANDOFF_SINGLE_KERNEL') == '1'
+    handoffs = [pdist.FusedHandoff(e, spec, world * B, signal_kernel=not one_kernel)
+                for e in engines]
+    transport = ('crop + pack + %s into symmetric memory in one kernel, %s' % (
+        handoffs[0].transport, 'flag barrier in the same kernel' if one_kernel else
+        'flags published and awaited by a one-warp kernel behind it'))
     kind = 'fused'
   except Exception as err:      # noqa: BLE001 - any failure to set peer mapping up
     fused_err = str(err).splitlines()[0][:120] if str(err) else type(err).__name__
@@ -1087,7 +1090,46 @@ def handoff_bench(torch, dist, dev, rank, world, engines, actions, W, K, barrier
   flag = torch.tensor([1 if ok else 0], device=dev)
   dist.all_reduce(flag, op=dist.ReduceOp.MIN)
   rec = handoffs[0].rec if kind == 'fused' else pdist.handoff_record_bytes(81)
-  return {'what': 'step + 9x9 crop + hand-off of the packed (crop, reward, discount, done) '
+  # ---- split phase (lag 1): signal this step, wait only for the previous one ----------
+  split = None
+  if kind == 'fused':
+    try:
+      lagged = [pdist.FusedHandoff(e, spec, world * B, lag=1, signal_kernel=not one_kernel)
+                for e in engines]
+
+      def step_and_send(t):
+        engines[t % R].play(actions[W + (t % K)])
+        return lagged[t % R].gather()
+      for t in range(2 * R):
+        step_and_send(t)
+      barrier()
+      timed2 = Timed(torch, dev, step_and_send, 0, n_h)
+      if timed2.graphs:
+        timed2.run()
+        ms2_local = timed2.time_ms(barrier) / n_h
+        ms2, per_rank2 = max_over_ranks(torch, dist, dev, world, ms2_local)
+        # correctness: one more step outside the graph; after flush() the records of that
+        # step equal the stand-alone cropper + NCCL all-gather, on every rank
+        barrier()
+        step_and_send(0)
+        got = lagged[0].flush()
+        e0 = engines[0]
+        mine2 = e0.crop(spec, state=e0.new_crop_state())        # egocentric: position only
+        want2 = pdist.allgather_outputs([mine2, e0.reward, e0.discount, e0.done, e0.has_reward],
+                                        world * B)
+        ok2 = all(bool((g == w).all()) for g, w in zip(got, want2))
+        flag2 = torch.tensor([1 if ok2 else 0], device=dev)
+        dist.all_reduce(flag2, op=dist.ReduceOp.MIN)
+        split = {'what': 'the same hand-off, split phase: the kernel of step t signals t and waits '
+                         'only for step t - 1 of the peers (three buffer parts), consumers read one '
+                         'step behind, a host barrier completes the last step',
+                 'ms_per_step': ms2, 'per_rank_ms_per_step': per_rank2, 'steps': n_h,
+                 'value': world * B / (ms2 / 1000.0), 'unit': 'env-steps/s',
+                 'handoff_checked': bool(int(flag2.item()))}
+    except Exception as err:        # noqa: BLE001 - the strict figure above stands on its own
+      split = {'error': str(err).splitlines()[0][:160] if str(err) else type(err).__name__}
+  return {'split_phase': split,
+          'what': 'step + 9x9 crop + hand-off of the packed (crop, reward, discount, done) '
                   'records to every rank', 'transport': transport, 'launch_path': path,
           'ms_per_step': ms, 'per_rank_ms_per_step': per_rank, 'steps': n_h,
           'value': world * B / (ms / 1000.0), 'unit': 'env-steps/s',

@@ -416,11 +416,13 @@ int pcl_pack_handoff_peers(pcl_handle* h, const uint8_t* d_view, int32_t view_by
  * all ranks' records of this step.  No collective call and no separate barrier
  * kernel; the step count lives in device memory (`d_local`), so the launch can be
  * captured in a CUDA graph.  Every rank must make the same sequence of calls.
- *   gather buffer of a rank: u8 [2, rows, record_bytes]  (two halves alternate)
+ *   gather buffer of a rank: u8 [n_bufs, rows, record_bytes]  (parts alternate by step)
  *   flag array of a rank:    u32 [PCL_MAX_PEERS], zero-initialised; word s = steps
  *                            whose records from rank s have landed here
  *   d_local:                 u32 [2] zero-initialised device memory of this rank
  * record_bytes: multiple of 16, >= PCL_HANDOFF_RECORD_BYTES(crop rows * cols), <= 256. */
+#define PCL_HANDOFF_LAG 1
+#define PCL_HANDOFF_SIGNAL_KERNEL 2
 typedef struct pcl_handoff {
   int32_t n_peers, rank;
   int32_t record_bytes;
@@ -429,6 +431,18 @@ typedef struct pcl_handoff {
   uint32_t* d_peer_flags[PCL_MAX_PEERS]; /* peer-mapped: every rank's flag array   */
   uint8_t* d_multicast;                  /* multicast mapping of the gather buffers, or NULL */
   uint32_t* d_local;
+  int32_t n_bufs;   /* parts of a gather buffer that alternate by step: 0 or 2 = two halves */
+  int32_t mode;     /* bit flags:
+                     * PCL_HANDOFF_LAG (1), split phase: signal this step but only wait for the
+                     *   PREVIOUS one, so the cross-GPU wait leaves the critical path: when the call
+                     *   for step s retires, part (s - 1) % n_bufs holds every rank's records of step
+                     *   s - 1.  Needs n_bufs >= 3 (a peer one step ahead writes part (s + 1) % n_bufs
+                     *   while part (s - 1) % n_bufs is being read); the last step is completed by any
+                     *   host-level barrier after the stream has drained.
+                     * PCL_HANDOFF_SIGNAL_KERNEL (2): the records kernel neither fences nor counts
+                     *   blocks; a second, one-warp kernel behind it (the kernel boundary completes
+                     *   the peer stores) publishes the flags and waits.  Measured faster than
+                     *   1024 blocks each waiting for its NVLink acknowledgements. */
 } pcl_handoff;
 int pcl_crop_handoff(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d_board,
                      int32_t* d_crop_state, const pcl_outputs* out, const pcl_handoff* x,

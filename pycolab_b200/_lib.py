@@ -128,12 +128,16 @@ class CropSpec(C.Structure):
 MAX_PEERS = 8
 
 
+HANDOFF_LAG, HANDOFF_SIGNAL_KERNEL = 1, 2
+
+
 class HandoffState(C.Structure):
   """include/pcl.h pcl_handoff."""
   _fields_ = [('n_peers', C.c_int32), ('rank', C.c_int32), ('record_bytes', C.c_int32),
               ('rows', C.c_int64), ('first_row', C.c_int64),
               ('d_peer_base', C.c_void_p * MAX_PEERS), ('d_peer_flags', C.c_void_p * MAX_PEERS),
-              ('d_multicast', C.c_void_p), ('d_local', C.c_void_p)]
+              ('d_multicast', C.c_void_p), ('d_local', C.c_void_p),
+              ('n_bufs', C.c_int32), ('mode', C.c_int32)]
 
 
 class ObserveSpec(C.Structure):

@@ -829,7 +829,14 @@ int pcl_crop_handoff(pcl_handle* h, const pcl_crop_spec* crop, const uint8_t* d_
     q.peer_base[i] = x->d_peer_base[i]; q.peer_flags[i] = x->d_peer_flags[i];
   }
   q.multicast = x->d_multicast; q.local = x->d_local; q.out = *out;
-  return launched(h, pcl::launch_crop_handoff(p, q, (cudaStream_t)stream), "launch_crop_handoff");
+  q.n_bufs = x->n_bufs == 0 ? 2 : x->n_bufs;
+  if (x->mode & ~(PCL_HANDOFF_LAG | PCL_HANDOFF_SIGNAL_KERNEL)) return PCL_ERR_INVALID;
+  q.lag = (x->mode & PCL_HANDOFF_LAG) ? 1 : 0;
+  q.signal_kernel = (x->mode & PCL_HANDOFF_SIGNAL_KERNEL) ? 1 : 0;
+  if (q.n_bufs < 2 || q.n_bufs > 8 || (q.lag == 1 && q.n_bufs < 3)) return PCL_ERR_INVALID;
+  const int r = launched(h, pcl::launch_crop_handoff(p, q, (cudaStream_t)stream), "launch_crop_handoff");
+  if (r == PCL_OK && q.signal_kernel) h->launches += 1;      // the one-warp publish kernel
+  return r;
 }
 
 int pcl_pack_handoff(pcl_handle* h, const uint8_t* d_view, int32_t view_bytes,

@@ -129,6 +129,8 @@ struct HandoffParams {
   uint32_t* peer_flags[PCL_MAX_PEERS];  // peer-mapped flag arrays u32 [PCL_MAX_PEERS] of every rank
   uint8_t* multicast;            // NVLS multicast mapping of the gather buffers, or NULL
   uint32_t* local;               // device-local u32 [2]: steps done, block ticket
+  int n_bufs, lag;               // parts of the gather buffer; 1 = wait for the previous step only
+  int signal_kernel;             // 1: a second one-warp kernel publishes and waits (no fences here)
   pcl_outputs out;
 };
 cudaError_t launch_crop_handoff(const CropParams& p, const HandoffParams& x, cudaStream_t s);

@@ -233,8 +233,11 @@ __global__ void __launch_bounds__(128) crop_kernel(const CropParams p) {
 // block to finish publishes this rank's step number in every peer's flag word and
 // then waits until every peer has published the same step here, so when the kernel
 // retires the local gather buffer holds all ranks' records: no collective call, no
-// separate barrier kernel.  Two halves alternate by step parity; the step counter
-// lives in device memory, so the launch is CUDA-graph capturable.
+// separate barrier kernel.  The parts of the gather buffer alternate by step; the step
+// counter lives in device memory, so the launch is CUDA-graph capturable.  With lag 1
+// (split phase, >= 3 parts) the kernel signals this step but waits only for the previous
+// one, which by then has long arrived: the cross-GPU wait leaves the critical path and
+// consumers read one step behind.
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(128) crop_handoff_kernel(const CropParams p,
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t step = x.local[0];                        // steps completed so far
-  const int64_t half = (int64_t)(step & 1u) * x.rows * x.record_bytes;
+  const int64_t half = (int64_t)(step % (uint32_t)x.n_bufs) * x.rows * x.record_bytes;   // this step's part
   if (env < p.B) {
     int wr, wc;
     crop_corner(p, env, lane, s_hist[warp], &wr, &wc);
@@ -293,6 +296,7 @@ __global__ void __launch_bounds__(128) crop_handoff_kernel(const CropParams p,
     }
   }
   // ---- publish: every block fences its peer stores, the last one signals --------
+  if (x.signal_kernel) return;         // handoff_signal_kernel, launched behind this one, does it
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(&x.local[1], 1u) == gridDim.x - 1);
@@ -301,12 +305,32 @@ __global__ void __launch_bounds__(128) crop_handoff_kernel(const CropParams p,
   __threadfence_system();
   if (threadIdx.x < x.n_peers)                             // my step has landed on peer d
     st_release_sys(x.peer_flags[threadIdx.x] + x.rank, step + 1);
-  if (threadIdx.x < x.n_peers) {                           // wait for every peer's records
-    const uint32_t* mine = x.peer_flags[x.rank] + threadIdx.x;
-    while ((int32_t)(ld_acquire_sys(mine) - (step + 1)) < 0) { __nanosleep(20); }
+  if (threadIdx.x < x.n_peers) {       // wait for every peer's records: of this step, or
+    const uint32_t* mine = x.peer_flags[x.rank] + threadIdx.x;          // (lag 1) of the previous one
+    const uint32_t want = step + 1u - (uint32_t)x.lag;
+    while ((int32_t)(ld_acquire_sys(mine) - want) < 0) { __nanosleep(20); }
   }
   __syncthreads();
   if (threadIdx.x == 0) { x.local[1] = 0; x.local[0] = step + 1; __threadfence(); }
+}
+
+// The publish step as its own one-warp kernel, stream-ordered behind crop_handoff_kernel
+// (PCL_HANDOFF_SIGNAL_KERNEL).  That kernel has RETIRED when this one starts, so its peer
+// stores are complete (a grid's memory operations are performed before a dependent grid
+// begins); what is left is one release store per peer and the acquire poll.  Measured at
+// N = 2 (profiles/r02_handoff_probes.txt): the per-block system fences cost 5.3 us and the
+// last block's signalling another 5.3 us inside the big kernel; this kernel costs ~2.
+__global__ void __launch_bounds__(32) handoff_signal_kernel(const HandoffParams x) {
+  const uint32_t step = x.local[0];
+  if (threadIdx.x < x.n_peers) {
+    __threadfence_system();
+    st_release_sys(x.peer_flags[threadIdx.x] + x.rank, step + 1);
+    const uint32_t* mine = x.peer_flags[x.rank] + threadIdx.x;
+    const uint32_t want = step + 1u - (uint32_t)x.lag;
+    while ((int32_t)(ld_acquire_sys(mine) - want) < 0) { __nanosleep(20); }
+  }
+  __syncwarp();
+  if (threadIdx.x == 0) { x.local[0] = step + 1; __threadfence(); }
 }
 
 }  // namespace
@@ -358,7 +382,10 @@ cudaError_t launch_crop(const CropParams& p, cudaStream_t s) {
 }
 cudaError_t launch_crop_handoff(const CropParams& p, const HandoffParams& x, cudaStream_t s) {
   if (p.crop.cols < 1 || (int64_t)p.crop.rows * p.crop.cols >= 65536) return cudaErrorInvalidValue;
-  return launch_pdl(crop_handoff_kernel, (p.B + 3) / 4, 128, s, with_recip(p), x);
+  cudaError_t e = launch_pdl(crop_handoff_kernel, (p.B + 3) / 4, 128, s, with_recip(p), x);
+  if (e != cudaSuccess || !x.signal_kernel) return e;
+  handoff_signal_kernel<<<1, 32, 0, s>>>(x);          // plain stream order: after the grid above retires
+  return cudaGetLastError();
 }
 
 }  // namespace pcl

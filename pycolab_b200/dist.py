@@ -174,9 +174,18 @@ class FusedHandoff(object):
   NVLS multicast store) and the cross-GPU flag barrier.  Gather buffers and flag
   arrays live in symmetric memory; nothing from a collective library runs per step
   and the launch can be captured in a CUDA graph (the step counter is on the
-  device).  With a single rank it degenerates to crop + pack into a local buffer."""
+  device).  With a single rank it degenerates to crop + pack into a local buffer.
 
-  def __init__(self, engine, crop_spec, global_batch, group=None, multicast=True):
+  lag=1 is the split-phase form: the kernel of step s signals s but waits only for
+  step s - 1 of the peers, so the cross-GPU wait is off the critical path; `gather()`
+  then returns the records of the PREVIOUS step (None on the first call) and `flush()`
+  — a host-level barrier — completes the last one.  Three buffer parts alternate.
+
+  signal_kernel=True (default) publishes and waits in a second one-warp kernel behind
+  the records kernel instead of fencing in each of its thread blocks (measured faster)."""
+
+  def __init__(self, engine, crop_spec, global_batch, group=None, multicast=True, lag=0,
+               signal_kernel=True):
     import ctypes as C
     import torch
     import torch.distributed as dist
@@ -195,9 +204,11 @@ class FusedHandoff(object):
     self.rows = world * self.biggest
     self.rec = (handoff_record_bytes(self.view_bytes) + 15) & ~15
     self.first_row = rank * self.biggest
+    self.lag = int(lag)
+    self.n_bufs = 3 if self.lag else 2
     half = self.rows * self.rec
     flag_bytes = 256
-    total = 2 * half + flag_bytes
+    total = self.n_bufs * half + flag_bytes
     self.handle = None
     mc_ptr = 0
     if world > 1:
@@ -222,12 +233,16 @@ class FusedHandoff(object):
     st.rows, st.first_row = self.rows, self.first_row
     for i, b in enumerate(bases):
       st.d_peer_base[i] = b
-      st.d_peer_flags[i] = b + 2 * half
+      st.d_peer_flags[i] = b + self.n_bufs * half
     st.d_multicast = mc_ptr or None
     st.d_local = self.local.data_ptr()
+    st.n_bufs = self.n_bufs
+    st.mode = ((_lib.HANDOFF_LAG if self.lag else 0) |
+               (_lib.HANDOFF_SIGNAL_KERNEL if signal_kernel else 0))
+    self.signal_kernel = bool(signal_kernel)
     self._state = st
     self.halves = [self.buffer[k * half:(k + 1) * half].view(self.rows, self.rec)
-                   for k in (0, 1)]
+                   for k in range(self.n_bufs)]
     self.crop_state = engine.new_crop_state()
     self.step = 0
     torch.cuda.synchronize(engine.device)
@@ -236,13 +251,35 @@ class FusedHandoff(object):
 
   def gather(self):
     """Crop the engine's last boards and exchange: (view u8 [N, rows, cols], reward,
-    discount, done, has_reward) of ALL ranks' envs, views into this rank's buffer."""
-    k = self.step & 1
+    discount, done, has_reward) of ALL ranks' envs, views into this rank's buffer.
+    With lag=1: of the PREVIOUS step (None on the first call)."""
+    k = self.step % self.n_bufs
     self.step += 1
     self.engine.crop_handoff(self.crop_spec, self.crop_state, self._state)
+    if self.lag:
+      if self.step == 1:
+        return None
+      k = (self.step - 2) % self.n_bufs
+    return self._unpack(k)
+
+  def _unpack(self, k):
     records = self.halves[k]
     if any(c != self.biggest for c in self.counts):
       import torch
       records = torch.cat([records[r * self.biggest: r * self.biggest + c]
                            for r, c in enumerate(self.counts)])
     return unpack_handoff(records, self.view_shape)
+
+  def flush(self):
+    """lag=1: make the LAST step's records complete everywhere (stream drained + a
+    host-level barrier: every rank's kernel has retired, and a retired kernel's peer
+    stores are visible) and return them."""
+    import torch
+    torch.cuda.synchronize(self.engine.device)
+    if self.handle is not None:
+      self.handle.barrier(channel=0)
+    # the DEVICE's step count names the part (CUDA-graph replays advance it without
+    # passing through gather())
+    done = int(self.local[0].item())
+    self.step = done
+    return self._unpack((done - 1) % self.n_bufs)

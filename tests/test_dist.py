@@ -135,10 +135,14 @@ def _peer_worker(rank, world, port, ok):
   spec = batched.scrolling_crop_spec(9, 9, 0, pad_char=' ', scroll_margins=(None, None))
   nccl, peer = pdist.Handoff(eng, (9, 9), total), pdist.PeerHandoff(eng, (9, 9), total)
   # the one-kernel path (crop + pack + stores + flag barrier), unicast and multicast
-  fused = [pdist.FusedHandoff(eng, spec, total, multicast=False),
-           pdist.FusedHandoff(eng, spec, total, multicast=True)]
+  fused = [pdist.FusedHandoff(eng, spec, total, multicast=False, signal_kernel=False),
+           pdist.FusedHandoff(eng, spec, total, multicast=True, signal_kernel=False),
+           pdist.FusedHandoff(eng, spec, total, multicast=True)]   # + the publish kernel
+  # split phase: signal this step, wait for the previous one, read one step behind
+  lagged = pdist.FusedHandoff(eng, spec, total, lag=1)
   rs = np.random.RandomState(rank)
-  for _ in range(25):
+  previous = None
+  for t in range(25):
     eng.play(torch.from_numpy(rs.randint(0, 5, size=eng.batch).astype(np.int32)).cuda())
     crop = eng.crop(spec).clone()
     want = [t.clone() for t in nccl.gather(crop)]
@@ -150,6 +154,14 @@ def _peer_worker(rank, world, port, ok):
       got = f.gather()
       torch.cuda.synchronize()
       good = good and all(bool((g == w).all()) for g, w in zip(got, want))
+    got = lagged.gather()                      # the PREVIOUS step's records, complete
+    torch.cuda.synchronize()
+    good = good and ((got is None) == (t == 0))
+    if got is not None:
+      good = good and all(bool((g == w).all()) for g, w in zip(got, previous))
+    previous = want
+  got = lagged.flush()                         # ... and the last step after a host barrier
+  good = good and all(bool((g == w).all()) for g, w in zip(got, previous))
   ok[rank] = 1 if good else 0
   dist.destroy_process_group()
 
@@ -205,7 +217,7 @@ def test_fused_crop_handoff_kernel_single_rank():
   rs = np.random.RandomState(1)
   spec = batched.scrolling_crop_spec(9, 9, 0, pad_char=' ', scroll_margins=(None, None))
   state = eng.new_crop_state()
-  fused = pdist.FusedHandoff(eng, spec, 37)
+  fused = pdist.FusedHandoff(eng, spec, 37, signal_kernel=False)
   assert fused.rec == 96 and fused.transport.startswith('local')
   for t in range(41):
     res = eng.play(torch.from_numpy(rs.randint(0, 5, size=37).astype(np.int32)).cuda())
@@ -228,6 +240,35 @@ def test_fused_crop_handoff_kernel_single_rank():
     torch.cuda.synchronize()
     assert bool((view == crop).all()), t
     assert not fused2.halves[t & 1][:, 35 + 1 + 12:].any()    # padding stays zero
+
+
+@pytest.mark.gpu
+def test_fused_crop_handoff_split_phase_single_rank():
+  """lag=1 (three buffer parts, wait for the previous step): gather() hands back step
+  t - 1, flush() the last step."""
+  import torch
+  from pycolab_b200 import batched, levels
+  from pycolab_b200.games import scrolly_maze
+  art = levels.scrolly_maze_level(71, world_shape=(65, 65), board_shape=(30, 45))
+  eng = batched.BatchedEngine([scrolly_maze.make_game(*art)], batch=21)
+  eng.its_showtime()
+  rs = np.random.RandomState(2)
+  spec = batched.scrolling_crop_spec(9, 9, 0, pad_char=' ', scroll_margins=(None, None))
+  state = eng.new_crop_state()
+  fused = pdist.FusedHandoff(eng, spec, 21, lag=1)
+  assert fused.n_bufs == 3
+  prev = None
+  for t in range(10):
+    res = eng.play(torch.from_numpy(rs.randint(0, 5, size=21).astype(np.int32)).cuda())
+    now = (eng.crop(spec, state=state).clone(), res.reward.clone(), res.discount.clone(),
+           res.done.clone(), res.has_reward.clone())
+    got = fused.gather()
+    torch.cuda.synchronize()
+    assert (got is None) == (t == 0)
+    if got is not None:
+      assert all(bool((g == w).all()) for g, w in zip(got, prev)), t
+    prev = now
+  assert all(bool((g == w).all()) for g, w in zip(fused.flush(), prev))
 
 
 @pytest.mark.gpu
