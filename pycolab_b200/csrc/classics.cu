@@ -118,6 +118,7 @@ classics_step(const StepParams p) {
       if (src >= W) src -= W;
       s_bd[r * pitch + c] = __ldg(backdrop + r * pitch + src);
     }
+    __syncwarp();               // the walker's neighbourhood test reads cells other lanes wrote
     if (even) walker_move(sp, 0, PCL_M_W, plot, H, W, p.confined[0] != 0, false, lane, blocked);
     motion = action == 0 ? PCL_M_W : action == 1 ? PCL_M_E : PCL_M_NONE;
   } else if (rule == PCL_CLASSIC_CHAIN_WALK) {
