@@ -120,6 +120,16 @@ class Engine(object):
     from pycolab_b200 import batched
     from pycolab_b200 import lowering
     lowered = lowering.lower(self)          # NotLoweredError if not accelerable
+    # Upstream folds directives issued BEFORE its_showtime() into frame 0
+    # (engine.py:761-847 runs on whatever the Plot holds).  The device's frame 0 starts
+    # from clean directives, so such a set-up is refused rather than silently dropped.
+    pending = self._the_plot._engine_directives
+    if (pending.z_updates or pending.summed_reward is not None or pending.game_over or
+        pending.discount != 1.0):
+      from pycolab_b200.errors import NotLoweredError
+      raise NotLoweredError('Plot directives issued before its_showtime() (add_reward, '
+                            'terminate_episode, change_default_discount, change_z_order) are '
+                            'not carried into the device\'s first frame')
     rng_states = None
     if lowered.needs_rng and lowered.rng_kind == 'python':
       # apprehend.py:103 draws in the sprite's constructor, which has already run

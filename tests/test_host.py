@@ -533,3 +533,16 @@ def test_reference_test_fixtures_load_and_lower(compat_examples):
   assert a.program == _lib.PROG_FIXTURE and a.dynamic_z
   assert a.drape_kind == [1, 1] and a.egocentric == b.egocentric
   _same_lowering(a, b)
+
+
+@pytest.mark.parametrize('call', [lambda p: p.add_reward(1), lambda p: p.terminate_episode(),
+                                  lambda p: p.change_default_discount(0.5),
+                                  lambda p: p.change_z_order('P', None)])
+def test_plot_directives_before_showtime_are_refused(call):
+  """engine.py:761-847 folds whatever the Plot holds into frame 0; the device's frame 0
+  starts from clean directives, so the facade refuses instead of dropping them."""
+  art = levels.scrolly_maze_level(3, world_shape=(33, 33), board_shape=(16, 16))
+  game = g_scrolly.make_game(*art)
+  call(game.the_plot)
+  with pytest.raises(NotLoweredError, match='before its_showtime'):
+    game.its_showtime()
