@@ -58,8 +58,11 @@ constexpr int kWarpsPerBlock = 4;
 constexpr int kRecWords = 64;     // 4 sprites * 8 + 2 drapes * 8 + plot 16
 
 __device__ __forceinline__ int action_to_motion(int a) {   // scrolly_maze.py:262-271
-  return a == 0 ? PCL_M_N : a == 1 ? PCL_M_S : a == 2 ? PCL_M_W
-       : a == 3 ? PCL_M_E : a == 4 ? PCL_M_STAY : PCL_M_NONE;
+  // actions 0..4 = N S W E stay (motion codes 0 4 6 2 8), anything else = no motion:
+  // one nibble per action in a constant instead of a chain of selects
+  constexpr unsigned kTable = (PCL_M_N) | (PCL_M_S << 4) | (PCL_M_W << 8) | (PCL_M_E << 12) |
+                              (PCL_M_STAY << 16);
+  return (unsigned)a < 5u ? (int)((kTable >> (4 * a)) & 15u) : PCL_M_NONE;
 }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
