@@ -605,8 +605,10 @@ scrolly_maze_step(const StepParams p) {
     }
   }
   // a, b, c lie under both drapes, so they are patched into the staged backdrop
-  // up front, in z-order (a lane each, one after the other); the player is the top
-  // layer and is patched into the one segment that holds it.
+  // up front, in z-order (a lane each, one after the other); the player is the TOP
+  // layer: its character also goes into the staged tile, and both drape bits of its
+  // cell are cleared so that the compose below keeps the tile's byte there — the
+  // streaming loop then has no sprite test at all.
   __syncwarp();
   if (lane == 0 && coins.aux0 >= 0)
     s_seg[coins.aux0 * spr + (coins.aux1 >> 4)] |= 1u << (coins.aux1 & 15);
@@ -615,14 +617,14 @@ scrolly_maze_step(const StepParams p) {
     if (lane == i && visible(mine)) s_bd[mine.row * pitch + mine.col] = p.sprite_char[i];
     __syncwarp();
   }
-  __syncwarp();                              // this warp's s_sel copy has landed (waited above)
+  if (lane == 0 && visible(pl)) {
+    s_bd[pl.row * pitch + pl.col] = p.sprite_char[0];
+    s_seg[pl.row * spr + (pl.col >> 4)] &= ~(0x00010001u << (pl.col & 15));
+  }
+  __syncwarp();                              // (also: this warp's s_sel copy has landed, waited above)
   // 5b. The streaming loop: 16 cells per lane per iteration, segment index ==
   // 16-byte index into both the staged tile and the board (pitch = 16 * spr).
   const int total = H * spr;
-  const int p_seg = visible(pl) ? pl.row * spr + (pl.col >> 4) : -1;
-  const int p_word = (pl.col & 15) >> 2;
-  const uint32_t p_keep = ~(0xffu << ((pl.col & 3) * 8));
-  const uint32_t p_char = (uint32_t)p.sprite_char[0] << ((pl.col & 3) * 8);
   const unsigned drape_chars = ('#' << 8) | '@';           // bytes 4 and 5 of the permute
   const uint4* src = reinterpret_cast<const uint4*>(s_bd);
   uint4* dst = reinterpret_cast<uint4*>(p.out.d_board + (int64_t)env * H * pitch);
@@ -633,12 +635,6 @@ scrolly_maze_step(const StepParams p) {
     px.y = prmt(px.y, drape_chars, s_sel[((bits >> 16) & 0xf0u) | ((bits >> 4) & 0xfu)]);
     px.z = prmt(px.z, drape_chars, s_sel[((bits >> 20) & 0xf0u) | ((bits >> 8) & 0xfu)]);
     px.w = prmt(px.w, drape_chars, s_sel[((bits >> 24) & 0xf0u) | ((bits >> 12) & 0xfu)]);
-    if (seg == p_seg) {
-      if (p_word == 0) px.x = (px.x & p_keep) | p_char;
-      else if (p_word == 1) px.y = (px.y & p_keep) | p_char;
-      else if (p_word == 2) px.z = (px.z & p_keep) | p_char;
-      else px.w = (px.w & p_keep) | p_char;
-    }
     dst[seg] = px;
   }
   // ---- 6. an attached cropper (pcl_attach_cropper): the egocentric view of the board
