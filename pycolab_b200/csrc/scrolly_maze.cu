@@ -246,6 +246,11 @@ scrolly_maze_step(const StepParams p) {
   const uint32_t* wall_pat = p.st.d_pattern[0] + lvl * p.st.pattern_bstride[0];
   uint32_t* coin_pat = p.st.d_pattern[1] + (int64_t)env * p.st.pattern_bstride[1];
 
+  // The env's action word does not depend on the records either: issue its load now,
+  // beside theirs, instead of one memory round trip later (it is only USED if the env
+  // neither restarts nor is frozen).
+  int action_early = PCL_ACTION_NONE;
+  if (p.mode == MODE_STEP) action_early = p.actions[(int64_t)env * p.actions_per_env];
   // ---- 0. the backdrop tile depends on nothing: get it moving first --------
   {
     const uint8_t* src = p.st.d_backdrop + lvl * p.st.backdrop_bstride + lane * 16;
@@ -290,7 +295,7 @@ scrolly_maze_step(const StepParams p) {
     __syncwarp();
     action = PCL_ACTION_NONE;
   } else {
-    action = p.actions[(int64_t)env * p.actions_per_env];
+    action = action_early;
   }
 
   // ---- registers: the drapes / plot / player fields every lane needs, plus ONE
