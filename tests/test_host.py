@@ -546,3 +546,89 @@ def test_plot_directives_before_showtime_are_refused(call):
   call(game.the_plot)
   with pytest.raises(NotLoweredError, match='before its_showtime'):
     game.its_showtime()
+
+
+def _bound_handle(game, batch=4):
+  """A handle created and BOUND on the CPU: pcl_bind_state only records pointers, so
+  made-up non-null addresses are enough to reach the argument checks of the entry
+  points behind it (nothing is launched)."""
+  import ctypes as C
+  lib = _lib.load()
+  handle = C.c_void_p()
+  spec = game.make_spec(True)
+  assert lib.pcl_create(C.byref(spec), batch, -1, C.byref(handle)) == _lib.OK
+  st = _lib.State()
+  fake = 0x10000
+  for name in ('d_backdrop', 'd_sprites', 'd_sprites_init', 'd_drapes', 'd_drapes_init',
+               'd_plot', 'd_plot_init'):
+    setattr(st, name, fake)
+  for d in range(2):
+    st.d_pattern[d], st.d_pattern_init[d] = fake, fake
+    st.pattern_bstride[d], st.pattern_init_bstride[d] = 64, 64
+  assert lib.pcl_bind_state(handle, C.byref(st)) == _lib.OK
+  return lib, handle
+
+
+def test_attach_cropper_argument_checks_on_cpu():
+  """pcl_attach_cropper: unbound handle, bad window, drape tracking, programs without
+  the epilogue, detach — all decided before anything touches the device."""
+  import ctypes as C
+  from pycolab_b200 import batched
+  art = levels.scrolly_maze_level(3, world_shape=(33, 33), board_shape=(16, 16))
+  game = lowering.lower(g_scrolly.make_game(*art))
+  lib = _lib.load()
+  raw = C.c_void_p()
+  spec0 = game.make_spec(True)
+  assert lib.pcl_create(C.byref(spec0), 4, -1, C.byref(raw)) == _lib.OK
+  crop = batched.scrolling_crop_spec(5, 5, 0, pad_char=' ', scroll_margins=(None, None))
+  assert lib.pcl_attach_cropper(raw, C.byref(crop), 0x20000, 0x30000) == _lib.ERR_UNBOUND
+  lib.pcl_destroy(raw)
+
+  lib, h = _bound_handle(game)
+  assert lib.pcl_attach_cropper(h, C.byref(crop), 0x20000, 0x30000) == _lib.OK
+  assert lib.pcl_attach_cropper(h, C.byref(crop), None, 0x30000) == _lib.ERR_INVALID
+  assert lib.pcl_attach_cropper(h, None, None, None) == _lib.OK              # detach
+  too_big = batched.scrolling_crop_spec(31, 31, 0, pad_char=None, scroll_margins=(2, 3))
+  assert lib.pcl_attach_cropper(h, C.byref(too_big), 0x20000, 0x30000) == _lib.ERR_INVALID
+  drape = batched.scrolling_crop_spec(5, 5, 0, pad_char=' ', scroll_margins=(None, None),
+                                      track=[-1, 1])
+  assert lib.pcl_attach_cropper(h, C.byref(drape), 0x20000, 0x30000) == _lib.ERR_UNSUPPORTED
+  no_such = batched.scrolling_crop_spec(5, 5, 0, pad_char=' ', scroll_margins=(None, None),
+                                        track=[9])
+  assert lib.pcl_attach_cropper(h, C.byref(no_such), 0x20000, 0x30000) == _lib.ERR_INVALID
+  lib.pcl_destroy(h)
+
+  other = lowering.lower(g_warehouse.make_game(levels.warehouse_level(1, shape=(20, 24))))
+  lib, h = _bound_handle(other)
+  crop = batched.scrolling_crop_spec(5, 5, 0, pad_char=' ', scroll_margins=(None, None))
+  assert lib.pcl_attach_cropper(h, C.byref(crop), 0x20000, 0x30000) == _lib.ERR_UNSUPPORTED
+  lib.pcl_destroy(h)
+
+
+def test_crop_handoff_mode_checks_on_cpu():
+  """pcl_crop_handoff refuses inconsistent hand-off descriptions before it launches:
+  unknown mode bits, split phase with fewer than three buffer parts, record sizes."""
+  import ctypes as C
+  from pycolab_b200 import batched
+  art = levels.scrolly_maze_level(3, world_shape=(33, 33), board_shape=(16, 16))
+  lib, h = _bound_handle(lowering.lower(g_scrolly.make_game(*art)))
+  crop = batched.scrolling_crop_spec(9, 9, 0, pad_char=' ', scroll_margins=(None, None))
+  out = _lib.Outputs(0x1000, 0x2000, 0x3000, 0x4000, 0x5000)
+
+  def call(**kw):
+    x = _lib.HandoffState()
+    x.n_peers, x.rank, x.record_bytes, x.rows, x.first_row = 1, 0, 96, 4, 0
+    x.d_peer_base[0], x.d_peer_flags[0], x.d_local = 0x6000, 0x7000, 0x8000
+    for k, v in kw.items():
+      setattr(x, k, v)
+    return lib.pcl_crop_handoff(h, C.byref(crop), 0x9000, 0xa000, C.byref(out), C.byref(x), None)
+
+  assert call(mode=8) == _lib.ERR_INVALID                              # unknown bit
+  assert call(mode=_lib.HANDOFF_LAG, n_bufs=2) == _lib.ERR_INVALID     # split phase needs 3 parts
+  assert call(mode=_lib.HANDOFF_LAG) == _lib.ERR_INVALID               # n_bufs 0 means 2
+  assert call(n_bufs=9) == _lib.ERR_INVALID
+  assert call(record_bytes=90) == _lib.ERR_INVALID                     # not a multiple of 16
+  assert call(record_bytes=80) == _lib.ERR_INVALID                     # too small for 81 + 9 bytes
+  assert call(rows=3) == _lib.ERR_INVALID                              # this rank's rows do not fit
+  assert call(rank=1) == _lib.ERR_INVALID
+  lib.pcl_destroy(h)
